@@ -1,0 +1,93 @@
+// Fp2 = Fp[i]/(i^2+1) on top of fp.cuh.  Replaces MIRACL's FP2_* for the device path
+// (reference: 3rd-party/miracl-core/fp2_BLS12381.cpp:199 conj, :241 sqr, :266 mul, :334 inv, :373 mul_ip).
+// Also the overload set (add/sub/mul/sqr/...) the curve templates in ec.cuh are written against, for both
+// Fp (G1) and Fp2 (G2).
+#pragma once
+#include "fp.cuh"
+
+namespace c12 {
+
+// ---- uniform field interface over Fp --------------------------------------------------------------------
+C12_HD Fp add(const Fp& a, const Fp& b) { return fp_add(a, b); }
+C12_HD Fp sub(const Fp& a, const Fp& b) { return fp_sub(a, b); }
+C12_HD Fp mul(const Fp& a, const Fp& b) { return fp_mul(a, b); }
+C12_HD Fp sqr(const Fp& a) { return fp_sqr(a); }
+C12_HD Fp neg(const Fp& a) { return fp_neg(a); }
+C12_HD Fp dbl(const Fp& a) { return fp_dbl(a); }
+C12_HD bool is_zero(const Fp& a) { return fp_is_zero(a); }
+C12_HD bool eq(const Fp& a, const Fp& b) { return fp_eq(a, b); }
+C12_HD Fp select(bool c, const Fp& a, const Fp& b) { return fp_select(c, a, b); }
+C12_HD Fp inv(const Fp& a) { return fp_inv(a); }
+
+// ---- Fp2 ------------------------------------------------------------------------------------------------
+C12_HD Fp2 fp2_zero() { return Fp2{fp_zero(), fp_zero()}; }
+C12_HD Fp2 fp2_one() { return Fp2{fp_one(), fp_zero()}; }
+C12_HD Fp2 add(const Fp2& x, const Fp2& y) { return Fp2{fp_add(x.a, y.a), fp_add(x.b, y.b)}; }
+C12_HD Fp2 sub(const Fp2& x, const Fp2& y) { return Fp2{fp_sub(x.a, y.a), fp_sub(x.b, y.b)}; }
+C12_HD Fp2 neg(const Fp2& x) { return Fp2{fp_neg(x.a), fp_neg(x.b)}; }
+C12_HD Fp2 dbl(const Fp2& x) { return Fp2{fp_dbl(x.a), fp_dbl(x.b)}; }
+C12_HD Fp2 conj(const Fp2& x) { return Fp2{x.a, fp_neg(x.b)}; }
+C12_HD bool is_zero(const Fp2& x) { return fp_is_zero(x.a) && fp_is_zero(x.b); }
+C12_HD bool eq(const Fp2& x, const Fp2& y) { return fp_eq(x.a, y.a) && fp_eq(x.b, y.b); }
+C12_HD Fp2 select(bool c, const Fp2& x, const Fp2& y)
+{
+    return Fp2{fp_select(c, x.a, y.a), fp_select(c, x.b, y.b)};
+}
+
+// Karatsuba: 3 Fp products
+C12_HD Fp2 mul(const Fp2& x, const Fp2& y)
+{
+    Fp t0 = fp_mul(x.a, y.a);
+    Fp t1 = fp_mul(x.b, y.b);
+    Fp t2 = fp_mul(fp_add(x.a, x.b), fp_add(y.a, y.b));
+    return Fp2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
+}
+
+// (a+b)(a-b) + 2ab i : 2 Fp products
+C12_HD Fp2 sqr(const Fp2& x)
+{
+    Fp t0 = fp_mul(fp_add(x.a, x.b), fp_sub(x.a, x.b));
+    Fp t1 = fp_mul(x.a, x.b);
+    return Fp2{t0, fp_dbl(t1)};
+}
+
+C12_HD Fp2 mul_fp(const Fp2& x, const Fp& s) { return Fp2{fp_mul(x.a, s), fp_mul(x.b, s)}; }
+
+// x * (1+i): the non-residue of the tower (QNRI = 0)
+C12_HD Fp2 mul_ip(const Fp2& x) { return Fp2{fp_sub(x.a, x.b), fp_add(x.a, x.b)}; }
+
+C12_HD Fp2 inv(const Fp2& x)
+{
+    Fp n = fp_inv(fp_add(fp_sqr(x.a), fp_sqr(x.b)));
+    return Fp2{fp_mul(x.a, n), fp_neg(fp_mul(x.b, n))};
+}
+
+C12_HD Fp2 mul3(const Fp2& x) { return Fp2{fp_mul3(x.a), fp_mul3(x.b)}; }
+C12_HD Fp2 mul4(const Fp2& x) { return Fp2{fp_mul4(x.a), fp_mul4(x.b)}; }
+C12_HD Fp2 mul8(const Fp2& x) { return Fp2{fp_mul8(x.a), fp_mul8(x.b)}; }
+C12_HD Fp2 mul12(const Fp2& x) { return Fp2{fp_mul12(x.a), fp_mul12(x.b)}; }
+C12_HD Fp mul3(const Fp& x) { return fp_mul3(x); }
+C12_HD Fp mul4(const Fp& x) { return fp_mul4(x); }
+C12_HD Fp mul8(const Fp& x) { return fp_mul8(x); }
+C12_HD Fp mul12(const Fp& x) { return fp_mul12(x); }
+
+// FP2_sign (3rd-party/miracl-core/fp2_BLS12381.cpp:168-181): parity of the real part, of the imaginary part
+// when the real part is zero
+C12_HD int fp2_sign(const Fp2& x) { return fp_is_zero(x.a) ? fp_sign(x.b) : fp_sign(x.a); }
+
+// field traits used by ec.cuh
+template <class F> struct FieldOps;
+template <> struct FieldOps<Fp> {
+    static C12_HD Fp zero() { return fp_zero(); }
+    static C12_HD Fp one() { return fp_one(); }
+    // 3b with b = 4  (G1: y^2 = x^3 + 4)
+    static C12_HD Fp mul_b3(const Fp& x) { return fp_mul12(x); }
+};
+template <> struct FieldOps<Fp2> {
+    static C12_HD Fp2 zero() { return fp2_zero(); }
+    static C12_HD Fp2 one() { return fp2_one(); }
+    // 3b' with b' = 4(1+i)  (M-type twist, 3rd-party/miracl-core/ecp2_BLS12381.cpp:270-296)
+    static C12_HD Fp2 mul_b3(const Fp2& x) { return mul_ip(mul12(x)); }
+};
+
+} // namespace c12

@@ -1,0 +1,235 @@
+// Multi-scalar multiplication: signed-window Pippenger bodies, templated on the coordinate field
+// (Fp -> G1, Fp2 -> G2).  Replaces the reference's MSM seam `sum_of_products` -> ECP_muln (4-bit unsigned
+// windows, complete adds in input order; src/miracl_core_interface.cpp:134-137,
+// 3rd-party/miracl-core/ecp_BLS12381.cpp:1112-1148) and the live DSL loop of ECP_mul2 calls
+// (include/crypto12381/g1_point.hpp:371-404); for G2 the per-term PAIR_G2mul + ECP2_add loop
+// (g2_point.hpp:202-236).  Outputs are compared on normalised affine encodings, so any evaluation order of
+// the same group sum is bit-exact.
+//
+// Every function here is a per-thread BODY (host+device) so the indexing and the algorithm can be executed
+// serially by tests/hostmirror on the CPU; the __global__ wrappers live in msm.cu.
+//
+// Plan for n terms with window width c:  W = ceil(256 / c) windows, 2^(c-1) buckets per window.
+//   digit recode : k = sum_w d_w 2^(c w), d_w in [-2^(c-1)+1, 2^(c-1)]   (top window cannot overflow: W c >= 256)
+//   key          : w * 2^(c-1) + (|d_w| - 1); value = term index | sign << 31; zero digits get key = INVALID
+//   (radix sort by key; bucket b owns sorted[start[b] .. end[b]))
+//   accumulate   : one XYZZ accumulator per bucket, mixed additions of the affine terms
+//   reduce       : per window sum_k k * B_k by segmented running sums, then a tree
+//   combine      : Horner over windows, c doublings per step
+#pragma once
+#include "ec.cuh"
+
+namespace c12 {
+
+struct MsmPlan {
+    uint32_t n;           // terms
+    uint32_t c;           // window bits
+    uint32_t windows;     // W
+    uint32_t half;        // 2^(c-1) buckets per window
+    uint32_t total;       // W * half
+    uint32_t seg_len;     // buckets per reduce-1 thread
+    uint32_t segs;        // segments per window = ceil(half / seg_len)
+};
+
+C12_HD uint32_t msm_invalid_key(const MsmPlan& pl) { return pl.total; }
+
+// scalars arrive as 32-byte big-endian; limbs little-endian
+struct Scalar256 {
+    uint32_t v[8];
+};
+
+C12_HD Scalar256 scalar_from_be32(const uint8_t* b)
+{
+    Scalar256 s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint8_t* q = b + 28 - 4 * i;
+        s.v[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+    }
+    return s;
+}
+
+// c bits starting at bit position `pos` (pos + c may run past 256: zero-extended)
+C12_HD uint32_t scalar_bits(const Scalar256& s, uint32_t pos, uint32_t c)
+{
+    uint32_t limb = pos >> 5, off = pos & 31u;
+    if (limb >= 8) return 0;
+    uint64_t lo = s.v[limb];
+    uint64_t hi = (limb + 1 < 8) ? s.v[limb + 1] : 0;
+    uint64_t x = (lo | (hi << 32)) >> off;
+    return (uint32_t)(x & ((1ull << c) - 1ull));
+}
+
+// Body of the recode kernel for term i: writes W (key, value) pairs at out index w * n + i.
+// The w-major layout keeps each window's entries in term order before the (stable) sort.
+C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalars_be32, uint32_t* keys, uint32_t* vals)
+{
+    Scalar256 s = scalar_from_be32(scalars_be32 + 32ull * i);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < pl.windows; ++w) {
+        uint32_t d = scalar_bits(s, w * pl.c, pl.c) + carry;
+        uint32_t neg = 0;
+        carry = 0;
+        if (d > pl.half) {  // d in (2^(c-1), 2^c] -> d - 2^c in (-2^(c-1), 0]
+            d = (1u << pl.c) - d;
+            neg = 1;
+            carry = 1;
+        }
+        uint64_t o = (uint64_t)w * pl.n + i;
+        if (d == 0) {
+            keys[o] = msm_invalid_key(pl);
+            vals[o] = i;
+        } else {
+            keys[o] = w * pl.half + (d - 1);
+            vals[o] = i | (neg << 31);
+        }
+    }
+}
+
+// Body of the bucket-accumulation kernel for bucket b: sum of its (signed) affine terms.
+template <class F>
+C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint32_t* end, const uint32_t* vals,
+                                   const Affine<F>* points)
+{
+    XYZZ<F> acc = xyzz_inf<F>();
+    uint32_t lo = start[b], hi = end[b];
+    for (uint32_t j = lo; j < hi; ++j) {
+        uint32_t v = vals[j];
+        Affine<F> pt = points[v & 0x7fffffffu];
+        if (affine_is_inf(pt)) continue;
+        if (v >> 31) pt.y = neg(pt.y);
+        xyzz_madd(acc, pt);
+    }
+    return xyzz_to_proj(acc);
+}
+
+// Body of reduce-1 for (window w, segment t): buckets with digit value k in [t*L+1, min((t+1)*L, half)]
+// (array index k-1).  Returns sum_k k * B_k over the segment.
+template <class F>
+C12_HD Proj<F> msm_reduce1_body(const MsmPlan& pl, uint32_t w, uint32_t t, const Proj<F>* buckets)
+{
+    uint32_t lo = t * pl.seg_len;                       // first array index of the segment
+    uint32_t hi = lo + pl.seg_len;
+    if (hi > pl.half) hi = pl.half;
+    const Proj<F>* B = buckets + (uint64_t)w * pl.half;
+    Proj<F> run = proj_inf<F>();
+    Proj<F> sum = proj_inf<F>();
+    for (uint32_t j = hi; j > lo; --j) {
+        run = proj_add(run, B[j - 1]);
+        sum = proj_add(sum, run);
+    }
+    // sum = sum_j (j - lo) * B[j-1] (digit value = j); add lo * run
+    if (lo) sum = proj_add(sum, proj_mul_small(run, lo));
+    return sum;
+}
+
+// Horner over window sums S_w (w = W-1 .. 0): acc = 2^c acc + S_w
+template <class F> C12_HD Proj<F> msm_horner_body(const MsmPlan& pl, const Proj<F>* window_sums)
+{
+    Proj<F> acc = window_sums[pl.windows - 1];
+    for (uint32_t w = pl.windows - 1; w > 0; --w) {
+        for (uint32_t k = 0; k < pl.c; ++k) acc = proj_dbl(acc);
+        acc = proj_add(acc, window_sums[w - 1]);
+    }
+    return acc;
+}
+
+// ---- wire formats ---------------------------------------------------------------------------------------
+// G1 affine 96 B = x || y big-endian (canonical); identity = zeros.  Returns false on non-canonical
+// coordinates or a point off the curve (ECP_set, ecp_BLS12381.cpp:~280-300).
+C12_HD bool g1_from_bytes96(Affine<Fp>& out, const uint8_t* b)
+{
+    Fp x = fp_from_be48(b), y = fp_from_be48(b + 48);
+    if (fp_is_zero(x) && fp_is_zero(y)) {
+        out = affine_inf<Fp>();
+        return true;
+    }
+    if (!fp_is_canonical(x) || !fp_is_canonical(y)) {
+        out = affine_inf<Fp>();
+        return false;
+    }
+    out.x = fp_to_mont(x);
+    out.y = fp_to_mont(y);
+    Fp rhs = fp_add(fp_mul(fp_sqr(out.x), out.x), fp_mul4(fp_one()));
+    if (!fp_eq(fp_sqr(out.y), rhs)) {
+        out = affine_inf<Fp>();
+        return false;
+    }
+    return true;
+}
+
+// G2 affine 192 B = x.b || x.a || y.b || y.a (imaginary part first: FP2_toBytes, fp2_BLS12381.cpp:83-87)
+C12_HD bool g2_from_bytes192(Affine<Fp2>& out, const uint8_t* b)
+{
+    Fp xb = fp_from_be48(b), xa = fp_from_be48(b + 48), yb = fp_from_be48(b + 96), ya = fp_from_be48(b + 144);
+    if (fp_is_zero(xa) && fp_is_zero(xb) && fp_is_zero(ya) && fp_is_zero(yb)) {
+        out = affine_inf<Fp2>();
+        return true;
+    }
+    if (!fp_is_canonical(xa) || !fp_is_canonical(xb) || !fp_is_canonical(ya) || !fp_is_canonical(yb)) {
+        out = affine_inf<Fp2>();
+        return false;
+    }
+    out.x = Fp2{fp_to_mont(xa), fp_to_mont(xb)};
+    out.y = Fp2{fp_to_mont(ya), fp_to_mont(yb)};
+    Fp2 four = Fp2{fp_mul4(fp_one()), fp_zero()};
+    Fp2 rhs = add(mul(sqr(out.x), out.x), mul_ip(four));  // x^3 + 4(1+i)
+    if (!eq(sqr(out.y), rhs)) {
+        out = affine_inf<Fp2>();
+        return false;
+    }
+    return true;
+}
+
+template <class F> struct Wire;
+template <> struct Wire<Fp> {
+    static constexpr int AFFINE = 96, COMPRESSED = 49;
+    static C12_HD bool parse(Affine<Fp>& o, const uint8_t* b) { return g1_from_bytes96(o, b); }
+    // ECP_toOctet compressed: 0x02 | parity(y), x  (ecp_BLS12381.cpp:445-491); identity = zeros (g1_point.hpp:113-117)
+    static C12_HD void compress(uint8_t* o, const Affine<Fp>& p)
+    {
+        if (affine_is_inf(p)) {
+            for (int i = 0; i < 49; ++i) o[i] = 0;
+            return;
+        }
+        o[0] = (uint8_t)(0x02 | fp_sign(p.y));
+        fp_to_be48(o + 1, fp_from_mont(p.x));
+    }
+    static C12_HD void serialize(uint8_t* o, const Affine<Fp>& p)
+    {
+        if (affine_is_inf(p)) {
+            for (int i = 0; i < 96; ++i) o[i] = 0;
+            return;
+        }
+        fp_to_be48(o, fp_from_mont(p.x));
+        fp_to_be48(o + 48, fp_from_mont(p.y));
+    }
+};
+template <> struct Wire<Fp2> {
+    static constexpr int AFFINE = 192, COMPRESSED = 97;
+    static C12_HD bool parse(Affine<Fp2>& o, const uint8_t* b) { return g2_from_bytes192(o, b); }
+    // ECP2_toOctet compressed: 0x02 | FP2_sign(y), x.b, x.a (ecp2_BLS12381.cpp:184-222); identity = zeros
+    static C12_HD void compress(uint8_t* o, const Affine<Fp2>& p)
+    {
+        if (affine_is_inf(p)) {
+            for (int i = 0; i < 97; ++i) o[i] = 0;
+            return;
+        }
+        o[0] = (uint8_t)(0x02 | fp2_sign(p.y));
+        fp_to_be48(o + 1, fp_from_mont(p.x.b));
+        fp_to_be48(o + 49, fp_from_mont(p.x.a));
+    }
+    static C12_HD void serialize(uint8_t* o, const Affine<Fp2>& p)
+    {
+        if (affine_is_inf(p)) {
+            for (int i = 0; i < 192; ++i) o[i] = 0;
+            return;
+        }
+        fp_to_be48(o, fp_from_mont(p.x.b));
+        fp_to_be48(o + 48, fp_from_mont(p.x.a));
+        fp_to_be48(o + 96, fp_from_mont(p.y.b));
+        fp_to_be48(o + 144, fp_from_mont(p.y.a));
+    }
+};
+
+} // namespace c12

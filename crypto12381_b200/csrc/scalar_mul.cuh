@@ -1,0 +1,76 @@
+// Batched scalar multiplication bodies (one (P, k) per thread), templated on the coordinate field.
+// Replaces `multiply(point1&, const big&)` -> PAIR_G1mul and `multiply(point2&, const big&)` -> PAIR_G2mul
+// (reference: src/miracl_core_interface.cpp:174-177,202-205; 3rd-party/miracl-core/pair_BLS12381.cpp:876-983)
+// and the fixed-base `select` path g^x (include/crypto12381/g1_point.hpp:355-369, g2_point.hpp:129-143).
+// The value k*P is independent of the evaluation strategy (MIRACL: GLV/GS + joint windows), outputs are
+// compared on normalised encodings.
+#pragma once
+#include "msm_core.cuh"
+
+namespace c12 {
+
+// r (group order), little-endian limbs
+C12_HD bool scalar_is_canonical(const Scalar256& s)
+{
+    const uint32_t r[8] = C12_R_LIMBS;
+    bool lt = false, decided = false;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (!decided && s.v[i] != r[i]) {
+            lt = s.v[i] < r[i];
+            decided = true;
+        }
+    }
+    return lt;
+}
+
+// k * P, 4-bit fixed windows over 256 bits on the complete projective formulas
+template <class F> C12_HD Proj<F> proj_scalar_mul(const Affine<F>& p, const Scalar256& k)
+{
+    if (affine_is_inf(p)) return proj_inf<F>();
+    Proj<F> tab[16];
+    tab[0] = proj_inf<F>();
+    tab[1] = proj_from_affine(p);
+    tab[2] = proj_dbl(tab[1]);
+    for (int i = 3; i < 16; ++i) tab[i] = proj_add_affine_nz(tab[i - 1], p);
+    Proj<F> acc = proj_inf<F>();
+    bool started = false;
+    for (int i = 63; i >= 0; --i) {
+        if (started) {
+            acc = proj_dbl(acc);
+            acc = proj_dbl(acc);
+            acc = proj_dbl(acc);
+            acc = proj_dbl(acc);
+        }
+        uint32_t d = (k.v[i >> 3] >> ((i & 7) * 4)) & 15u;
+        if (d) {
+            acc = started ? proj_add(acc, tab[d]) : tab[d];
+            started = true;
+        }
+    }
+    return acc;
+}
+
+template <class F> C12_HD bool scalar_mul_body(const uint8_t* point_bytes, const uint8_t* scalar_be32, uint8_t* out_compressed)
+{
+    Affine<F> p;
+    bool ok = Wire<F>::parse(p, point_bytes);
+    Scalar256 k = scalar_from_be32(scalar_be32);
+    Proj<F> r = proj_scalar_mul(p, k);
+    Wire<F>::compress(out_compressed, proj_to_affine(r));
+    return ok;
+}
+
+template <class F> C12_HD Affine<F> generator();
+template <> C12_HD Affine<Fp> generator<Fp>() { return Affine<Fp>{g1_gen_x_m(), g1_gen_y_m()}; }
+template <> C12_HD Affine<Fp2> generator<Fp2>() { return Affine<Fp2>{g2_gen_x_m(), g2_gen_y_m()}; }
+
+// g^x with g the default generator (ECP_generator / ECP2_generator); affine output bytes
+template <class F> C12_HD void fixed_base_body(const uint8_t* scalar_be32, uint8_t* out_affine)
+{
+    Scalar256 k = scalar_from_be32(scalar_be32);
+    Proj<F> r = proj_scalar_mul(generator<F>(), k);
+    Wire<F>::serialize(out_affine, proj_to_affine(r));
+}
+
+} // namespace c12

@@ -1,0 +1,131 @@
+// TEST-ONLY host mirror: compiles the product's host+device templates (crypto12381_b200/csrc/*.cuh) with a
+// plain C++ compiler and runs the per-thread kernel BODIES serially on the CPU, so the algorithms, indexing
+// and wire formats can be checked against the oracle in the GPU-less build container.  The product never
+// loads this library; the device build uses the inline-PTX field primitives instead of the portable ones.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../crypto12381_b200/csrc/msm_core.cuh"
+#include "../../crypto12381_b200/csrc/scalar_mul.cuh"
+#include "../../crypto12381_b200/csrc/pairing.cuh"
+
+using namespace c12;
+
+namespace {
+MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len)
+{
+    MsmPlan pl;
+    pl.n = n;
+    pl.c = c;
+    pl.windows = (256 + c - 1) / c;
+    pl.half = 1u << (c - 1);
+    pl.total = pl.windows * pl.half;
+    pl.seg_len = seg_len;
+    pl.segs = (pl.half + seg_len - 1) / seg_len;
+    return pl;
+}
+
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n, uint32_t c, uint32_t seg_len, uint8_t* out)
+{
+    using W = Wire<F>;
+    if (n == 0) {
+        W::compress(out, affine_inf<F>());
+        return 0;
+    }
+    MsmPlan pl = make_plan(n, c, seg_len);
+    std::vector<Affine<F>> P(n);
+    for (uint32_t i = 0; i < n; ++i)
+        if (!W::parse(P[i], pts + (size_t)W::AFFINE * i)) return -1;
+    size_t N = (size_t)n * pl.windows;
+    std::vector<uint32_t> keys(N), vals(N);
+    for (uint32_t i = 0; i < n; ++i) msm_recode_body(pl, i, sc, keys.data(), vals.data());
+    std::vector<uint32_t> order(N);
+    for (size_t i = 0; i < N; ++i) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint32_t> sk(N), sv(N);
+    for (size_t i = 0; i < N; ++i) { sk[i] = keys[order[i]]; sv[i] = vals[order[i]]; }
+    std::vector<uint32_t> start(pl.total, 0), end(pl.total, 0);
+    for (size_t i = 0; i < N; ++i) {
+        uint32_t k = sk[i];
+        if (k >= pl.total) continue;
+        if (i == 0 || sk[i - 1] != k) start[k] = (uint32_t)i;
+        if (i + 1 == N || sk[i + 1] != k) end[k] = (uint32_t)i + 1;
+    }
+    std::vector<Proj<F>> buckets(pl.total);
+    for (uint32_t b = 0; b < pl.total; ++b) buckets[b] = msm_accumulate_body<F>(b, start.data(), end.data(), sv.data(), P.data());
+    std::vector<Proj<F>> wsum(pl.windows);
+    for (uint32_t w = 0; w < pl.windows; ++w) {
+        Proj<F> acc = proj_inf<F>();
+        for (uint32_t t = 0; t < pl.segs; ++t) acc = proj_add(acc, msm_reduce1_body<F>(pl, w, t, buckets.data()));
+        wsum[w] = acc;
+    }
+    Proj<F> r = msm_horner_body<F>(pl, wsum.data());
+    W::compress(out, proj_to_affine(r));
+    return 0;
+}
+} // namespace
+
+extern "C" {
+// plain-integer (48 B BE) field ops through the Montgomery code path: op 0 mul, 1 add, 2 sub, 3 inv, 4 neg, 5 sqrt
+void hm_fp_op(int op, const uint8_t* a48, const uint8_t* b48, uint8_t* out48)
+{
+    Fp a = fp_to_mont(fp_from_be48(a48));
+    Fp b = fp_to_mont(fp_from_be48(b48));
+    Fp r;
+    switch (op) {
+    case 0: r = fp_mul(a, b); break;
+    case 1: r = fp_add(a, b); break;
+    case 2: r = fp_sub(a, b); break;
+    case 3: r = fp_inv(a); break;
+    case 4: r = fp_neg(a); break;
+    default: r = fp_sqrt_candidate(a); break;
+    }
+    fp_to_be48(out48, fp_from_mont(r));
+}
+
+int hm_g1_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out49) { return msm<Fp>(p, s, n, c, seg, out49); }
+int hm_g2_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out97) { return msm<Fp2>(p, s, n, c, seg, out97); }
+
+int hm_g1_mul(const uint8_t* p96, const uint8_t* s32, uint32_t n, uint8_t* out49)
+{
+    for (uint32_t i = 0; i < n; ++i)
+        if (!scalar_mul_body<Fp>(p96 + 96 * (size_t)i, s32 + 32 * (size_t)i, out49 + 49 * (size_t)i)) return -1;
+    return 0;
+}
+int hm_g2_mul(const uint8_t* p192, const uint8_t* s32, uint32_t n, uint8_t* out97)
+{
+    for (uint32_t i = 0; i < n; ++i)
+        if (!scalar_mul_body<Fp2>(p192 + 192 * (size_t)i, s32 + 32 * (size_t)i, out97 + 97 * (size_t)i)) return -1;
+    return 0;
+}
+void hm_g1_fixed_base(const uint8_t* s32, uint32_t n, uint8_t* out96)
+{
+    for (uint32_t i = 0; i < n; ++i) fixed_base_body<Fp>(s32 + 32 * (size_t)i, out96 + 96 * (size_t)i);
+}
+void hm_g2_fixed_base(const uint8_t* s32, uint32_t n, uint8_t* out192)
+{
+    for (uint32_t i = 0; i < n; ++i) fixed_base_body<Fp2>(s32 + 32 * (size_t)i, out192 + 192 * (size_t)i);
+}
+
+// pairings: B instances x k pairs; mode 0 raw Miller value, 1 final-exponentiated GT
+int hm_pairing_product(const uint8_t* g1, const uint8_t* g2, uint32_t B, uint32_t k, int mode, uint8_t* out576)
+{
+    for (uint32_t b = 0; b < B; ++b)
+        if (!pairing_product_body(g1 + 96 * (size_t)b * k, g2 + 192 * (size_t)b * k, k, mode, out576 + 576 * (size_t)b)) return -1;
+    return 0;
+}
+void hm_final_exp(const uint8_t* in576, uint32_t B, uint8_t* out576)
+{
+    for (uint32_t b = 0; b < B; ++b) final_exp_body(in576 + 576 * (size_t)b, out576 + 576 * (size_t)b);
+}
+void hm_gt_mul(const uint8_t* a, const uint8_t* b, uint32_t B, uint8_t* out576)
+{
+    for (uint32_t i = 0; i < B; ++i) gt_mul_body(a + 576 * (size_t)i, b + 576 * (size_t)i, out576 + 576 * (size_t)i);
+}
+void hm_gt_pow(const uint8_t* a, const uint8_t* s32, uint32_t B, uint8_t* out576)
+{
+    for (uint32_t i = 0; i < B; ++i) gt_pow_body(a + 576 * (size_t)i, s32 + 32 * (size_t)i, out576 + 576 * (size_t)i);
+}
+}
