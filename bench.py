@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the crypto12381 hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log-n 20]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): G1 MSM points/s at n = 2^20 (configs[1]); one step = one G1 multi-scalar sum over 2^20
+seeded synthetic (point, scalar) terms per GPU.  With N GPUs every rank owns 2^20 terms of one N*2^20-term sum
+(weak scaling): per-rank partial -> one all-gather of the 96-byte partials over NCCL -> every rank adds them.
+  value      whole-job points/s with inputs resident in HBM (device entries, CUDA events, max over ranks)
+  e2e        the same through the host-pointer C-ABI call c12381_g1_msm (pinned host buffers, H2D + D2H inside)
+  roofline   dominant kernel k_accumulate against the integer-multiply peak measured live by c12381_probe
+  cpu_baseline   the reference's own CPU path (oracle/_ref: MIRACL ECP_muln via the unmodified bridge) on a
+             bounded sample of the same points, all host threads, rank 0 only
+  secondary  batched 4-pair pairing products (BASELINE configs[3]) as pairings/s, same run
+`--impl reference` times only the reference CPU path (rank 0), same metric/unit/config."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "g1_msm_points_per_s"
+UNIT = "points/s"
+FP_MUL_PER_BUCKET_ADD = 10      # XYZZ mixed addition: 8 M + 2 S
+MAC_PER_FP_MUL = 300            # 12x12 product + 12x12 reduction + 12 quotient digits
+R_TOP = 0x73
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=20)
+    ap.add_argument("--pairing-instances", type=int, default=1 << 14)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=15)
+    ap.add_argument("--no-secondary", action="store_true")
+    return ap.parse_args()
+
+
+def config(args, world):
+    n = 1 << args.log_n
+    return {"workload": f"G1 MSM sweep point n=2^{args.log_n} per GPU (BASELINE configs[1]), seeded random points k_i*G and scalars < r",
+            "n_per_gpu": n, "n_total": n * world, "parallelism": f"points sharded over {world} GPU(s), one all-gather of 96-byte partials",
+            "l2": "explicit 256 MiB flush write between timed steps; per-step working set (128 MiB inputs + ~0.9 GiB scratch) also exceeds the 126 MB L2"}
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(rows[0][1]) if rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(r[2]) for r in rows if r[2].replace(".", "").isdigit()), default=None), "samples": len(rows), "reasons": reasons}
+
+
+def rand_scalars(n, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    a[:, 0] = rng.integers(0, R_TOP, size=n, dtype=np.uint8)   # top byte < 0x73 keeps every scalar below r
+    return a
+
+
+# ---- the reference arm ---------------------------------------------------------------------------------------------
+def reference_points(n, seed):
+    """n seeded points k_i*G made by the REFERENCE on the host (all threads): the CPU arm needs no GPU."""
+    from oracle import ref
+    ks = rand_scalars(n, seed).tobytes()
+    return ref.g1_fixed_base_mul(ks, ref.hardware_threads())
+
+
+def time_reference(points: bytes, scalars: bytes, steps: int, warmup: int):
+    from oracle import ref
+    threads = ref.hardware_threads()
+    n = len(scalars) // 32
+    for _ in range(warmup):
+        ref.g1_msm(points, scalars, 0, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = ref.g1_msm(points, scalars, 0, threads)
+    dt = (time.perf_counter() - t0) / steps
+    return n / dt, dt, threads, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    from oracle import ref
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref12381.so was not built (needs /root/reference at build time)"}))
+        return
+    n = 1 << args.cpu_sample_log_n
+    pts = reference_points(n, 1000)
+    ss = rand_scalars(n, 2000).tobytes()
+    v, dt, threads, _ = time_reference(pts, ss, max(1, args.steps), max(1, args.warmup))
+    sample = f"2^{args.cpu_sample_log_n}-term G1 sum per step (bounded sample of the 2^{args.log_n} workload), sum_of_products -> MIRACL ECP_muln, chunked over {threads} host threads"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 (7x58-bit limbs, CPU)",
+            "data": "synthetic", "config": config(args, world),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---- our arm ----------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from crypto12381_b200 import _lib, device as dv
+    from crypto12381_b200.distributed import g1_msm_sharded
+    _lib.init(local)
+    lib = _lib.lib()
+    n = 1 << args.log_n
+    dev = torch.device("cuda", local)
+
+    # synthetic seeded inputs: points k_i*G made on the GPU by the fixed-base kernel (setup, untimed)
+    h_k = torch.from_numpy(rand_scalars(n, 1000 + rank)).reshape(-1)
+    h_s = torch.from_numpy(rand_scalars(n, 2000 + rank)).reshape(-1).pin_memory()
+    d_s = h_s.to(dev)
+    d_p = dv.g1_fixed_base_mul_batch(h_k.to(dev))
+    dv.sync_status()
+    h_p = d_p.cpu().pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = torch.empty(49, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return g1_msm_sharded(d_p, d_s)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    acc_ms, tot_ms = [], []
+    l0 = int(lib.c12381_launch_count())
+    barrier()
+    t0 = time.time()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        res = step()
+        b.record()
+        b.synchronize()
+        st = dv.last_msm_stats()
+        acc_ms.append(st["accumulate_ms"])
+        tot_ms.append(st["total_ms"])
+    barrier()
+    t1 = time.time()
+    launches = int(lib.c12381_launch_count()) - l0
+    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = float(t.item())
+    clocks = sampler.stop(t0, t1)
+    result = bytes(res.cpu().numpy())
+    stats = dv.last_msm_stats()
+
+    # e2e: host-pointer C-ABI call, pinned host buffers, H2D + D2H inside the timed region (per rank, its own shard)
+    import ctypes
+    h_out = torch.empty(49, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        _lib.check(lib.c12381_g1_msm(h_p.data_ptr(), h_s.data_ptr(), n, h_out.data_ptr()))
+    barrier()
+    te = time.perf_counter()
+    for _ in range(args.steps):
+        _lib.check(lib.c12381_g1_msm(h_p.data_ptr(), h_s.data_ptr(), n, h_out.data_ptr()))
+    e2e_ms = (time.perf_counter() - te) / args.steps * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    if world == 1:
+        assert bytes(h_out.numpy()) == result, "host-pointer and device-pointer entries disagree"
+
+    line = None
+    if rank == 0:
+        # integer-multiply peak, measured live on this GPU (probe kind 2: IMAD.WIDE 32x32+64 multiply-adds)
+        probes = {k: dv.probe(i, 4000) for i, k in enumerate(["imad", "madc_pairs", "imad_wide", "fp_mul", "fp_sqr"])}
+        peak_gmacs = max(probes["imad_wide"]["gops"], probes["madc_pairs"]["gops"] / 2.0)
+        adds = stats["bucket_adds"]
+        acc = statistics.mean(acc_ms)
+        achieved = adds * FP_MUL_PER_BUCKET_ADD * MAC_PER_FP_MUL / (acc * 1e-3) / 1e9
+        roofline = {"bound": "int32_mad", "kernel": "k_accumulate<Fp>", "achieved": achieved, "peak": peak_gmacs, "unit": "GMAC/s (32x32->64 multiply-adds)",
+                    "frac": achieved / peak_gmacs, "traffic": None,
+                    "peak_source": "measured live: c12381_probe kind 2 (mad.wide.u32 chains) / kind 1 (mad.lo.cc+madc.hi.cc pairs), same GPU, same run",
+                    "algorithmic": f"{adds} bucket additions/launch x {FP_MUL_PER_BUCKET_ADD} Fp-mul x {MAC_PER_FP_MUL} MAC",
+                    "kernel_ms": acc, "kernel_share_of_step": acc / statistics.mean(tot_ms), "window_bits": stats["window_bits"],
+                    "fp_mul_gops": probes["fp_mul"]["gops"], "fp_sqr_gops": probes["fp_sqr"]["gops"], "probes": probes}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                hbm = json.load(f)["hbm_gbs"]
+            hbm_src = "MEASURED_PEAKS.json"
+        except Exception:
+            hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        W = (256 + stats["window_bits"] - 1) // stats["window_bits"]
+        passes = (stats["window_bits"] + 7) // 8
+        sort_ms = statistics.mean(tot_ms) - acc   # everything that is not accumulation (upper bound for the scatter phase)
+        roofline["hbm_phase"] = {"what": "recode + segmented radix sort (keys+indices)", "algorithmic_bytes": n * W * 8 * 2 * passes,
+                                 "upper_bound_ms": sort_ms, "peak_gbs": hbm, "peak_source": hbm_src}
+        cpu = None
+        try:
+            from oracle import ref
+            if ref.available():
+                m = 1 << args.cpu_sample_log_n
+                pts, ss = bytes(h_p[:96 * m].numpy()), bytes(h_s[:32 * m].numpy())
+                v, dt, threads, cpu_out = time_reference(pts, ss, 1, 0)
+                # same inputs, so the sample doubles as a parity check of the CUDA path against the reference
+                got = bytes(dv.g1_msm(d_p[:96 * m], d_s[:32 * m]).cpu().numpy())
+                cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "bit_exact_vs_gpu_on_sample": got == cpu_out,
+                       "sample": f"first 2^{args.cpu_sample_log_n} terms of rank 0's inputs, one pass ({dt:.2f} s), sum_of_products -> MIRACL ECP_muln chunked over {threads} host threads (oracle/_ref, -O2)"}
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        line = {"metric": METRIC, "value": n * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (12x32-bit limbs, Montgomery R=2^384)",
+                "data": "synthetic", "config": config(args, world), "clocks": clocks,
+                "e2e": {"value": n * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": 49, "ms_per_step": e2e_ms,
+                        "call": "c12381_g1_msm (host pointers, pinned), per rank on its own shard"},
+                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "result_hex": result.hex()}
+
+    # secondary: batched 4-pair pairing products (BASELINE configs[3]); instances sharded over ranks, no collective
+    if not args.no_secondary:
+        B, k = max(1, args.pairing_instances // world), 4
+        a = torch.from_numpy(rand_scalars(B * k, 3000 + rank)).reshape(-1).to(dev)
+        b = torch.from_numpy(rand_scalars(B * k, 4000 + rank)).reshape(-1).to(dev)
+        g1, g2 = dv.g1_fixed_base_mul_batch(a), dv.g2_fixed_base_mul_batch(b)
+        gt = torch.empty(B * 576, dtype=torch.uint8, device=dev)
+        dv.pairing_product_batch(g1, g2, k, gt)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dv.pairing_product_batch(g1, g2, k, gt)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ms = float(t.item())
+            sec = {"metric": "pairings_per_s", "value": B * world * k / (ms * 1e-3), "unit": "pairings/s", "products_per_s": B * world / (ms * 1e-3),
+                   "instances": B * world, "pairs_per_instance": k, "ms": ms,
+                   "fp_mul_per_instance_ref_count": 31600, "gmacs": B * 31600 * MAC_PER_FP_MUL / (ms * 1e-3) / 1e9}
+            sec["frac_of_int32_mad_peak"] = sec["gmacs"] / line["roofline"]["peak"]
+            try:
+                from oracle import ref
+                if ref.available():
+                    m = min(B, 4 * ref.hardware_threads())
+                    p1, p2 = bytes(g1[:96 * k * m].cpu().numpy()), bytes(g2[:192 * k * m].cpu().numpy())
+                    tc = time.perf_counter()
+                    want = ref.pairing_product_batch(p1, p2, k, 1, ref.hardware_threads())
+                    dtc = time.perf_counter() - tc
+                    sec["cpu_baseline"] = {"value": m * k / dtc, "unit": "pairings/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                           "sample": f"{m} instances x {k} pairs", "bit_exact_vs_gpu_on_sample": want == bytes(gt[:576 * m].cpu().numpy())}
+            except Exception as e:
+                sec["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+            line["secondary"] = sec
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

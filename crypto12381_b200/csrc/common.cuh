@@ -1,0 +1,67 @@
+// Host-side context shared by the translation units of libc12381_cuda.so: the bound device, its stream, a
+// grow-only device scratch arena, the launch counter and the last error string.  One context per process
+// (one process per GPU); not re-entrant (SURVEY §8b "Threading").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/c12381_cuda.h"
+
+namespace c12 {
+
+struct MsmStats {
+    double accumulate_ms = 0, total_ms = 0;
+    unsigned long long bucket_adds = 0;
+    int window_bits = 0;
+};
+
+struct Ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    unsigned long long launches = 0;
+    // scratch arena: one allocation, bump-allocated per call, grown (after a stream sync) when too small
+    uint8_t* arena = nullptr;
+    size_t arena_bytes = 0;
+    size_t arena_used = 0;
+    // pinned staging for small results / flags
+    int* h_flags = nullptr;
+    int* d_flags = nullptr;
+    int forced_window = 0;
+    MsmStats stats;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+Ctx& ctx();
+int set_error(int code, const char* what, cudaError_t e = cudaSuccess);
+
+// Reserve `bytes` of scratch for the CURRENT call.  Call arena_begin(total) once per entry point with an upper
+// bound, then carve with arena_take.
+int arena_begin(size_t total_bytes, cudaStream_t s);
+void* arena_take(size_t bytes);
+
+#define C12_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) return c12::set_error(C12381_ECUDA, #call, e__);            \
+    } while (0)
+
+#define C12_LAUNCHED()                                                                      \
+    do {                                                                                    \
+        c12::ctx().launches++;                                                              \
+        cudaError_t e__ = cudaGetLastError();                                               \
+        if (e__ != cudaSuccess) return c12::set_error(C12381_ECUDA, "kernel launch", e__);  \
+    } while (0)
+
+#define C12_REQUIRE_CTX()                                                                   \
+    do {                                                                                    \
+        if (c12::ctx().device < 0) return c12::set_error(C12381_ENODEV, "c12381_init was not called or no CUDA device"); \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+} // namespace c12

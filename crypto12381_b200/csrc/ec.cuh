@@ -203,6 +203,7 @@ template <class F> C12_HD Proj<F> proj_mul_small(const Proj<F>& p, uint32_t k)
     int top = 31;
     while (!((k >> top) & 1u)) --top;
     Proj<F> r = p;
+#pragma unroll 1
     for (int i = top - 1; i >= 0; --i) {
         r = proj_dbl(r);
         if ((k >> i) & 1u) r = proj_add(r, p);

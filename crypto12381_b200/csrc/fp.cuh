@@ -242,8 +242,10 @@ C12_HD_NOINLINE Fp fp_inv(const Fp& a)
     Fp tab[16];
     tab[0] = fp_one();
     tab[1] = a;
+#pragma unroll 1
     for (int i = 2; i < 16; ++i) tab[i] = fp_mul(tab[i - 1], a);
     Fp r = fp_one();
+#pragma unroll 1
     for (int i = 95; i >= 0; --i) {
         if (i != 95) {
             r = fp_sqr(r);
@@ -267,8 +269,10 @@ C12_HD_NOINLINE Fp fp_sqrt_candidate(const Fp& a)
     Fp tab[16];
     tab[0] = fp_one();
     tab[1] = a;
+#pragma unroll 1
     for (int i = 2; i < 16; ++i) tab[i] = fp_mul(tab[i - 1], a);
     Fp r = fp_one();
+#pragma unroll 1
     for (int i = 95; i >= 0; --i) {
         if (i != 95) {
             r = fp_sqr(r);

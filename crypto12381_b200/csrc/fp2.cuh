@@ -34,8 +34,9 @@ C12_HD Fp2 select(bool c, const Fp2& x, const Fp2& y)
     return Fp2{fp_select(c, x.a, y.a), fp_select(c, x.b, y.b)};
 }
 
-// Karatsuba: 3 Fp products
-C12_HD Fp2 mul(const Fp2& x, const Fp2& y)
+// Karatsuba: 3 Fp products.  A real call on the device: the towers above it (Fp4/Fp12, G2 curve formulas)
+// would otherwise inline ~2,000 SASS instructions per use and thrash the instruction cache.
+C12_HD_NOINLINE Fp2 mul(const Fp2& x, const Fp2& y)
 {
     Fp t0 = fp_mul(x.a, y.a);
     Fp t1 = fp_mul(x.b, y.b);
@@ -44,7 +45,7 @@ C12_HD Fp2 mul(const Fp2& x, const Fp2& y)
 }
 
 // (a+b)(a-b) + 2ab i : 2 Fp products
-C12_HD Fp2 sqr(const Fp2& x)
+C12_HD_NOINLINE Fp2 sqr(const Fp2& x)
 {
     Fp t0 = fp_mul(fp_add(x.a, x.b), fp_sub(x.a, x.b));
     Fp t1 = fp_mul(x.a, x.b);

@@ -1,0 +1,96 @@
+// Field-independent parts of the MSM pipeline: scalar recoding, the segmented radix sort driver, bucket bounds,
+// and the input-validation flag word.  (Kernels here are launched only through the host functions below, so the
+// per-field translation units never reference a __global__ symbol of another TU.)
+#include "msm_impl.cuh"
+#include "sort.cuh"
+
+namespace c12 {
+
+__global__ void __launch_bounds__(128) k_recode(MsmPlan pl, const uint8_t* __restrict__ scalars, uint32_t* __restrict__ keys,
+                                                uint32_t* __restrict__ vals, int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= pl.n) return;
+    if (!scalar_is_canonical(scalar_from_be32(scalars + 32ull * i))) atomicOr(flags, FLAG_BAD_SCALAR);
+    msm_recode_body(pl, i, scalars, keys, vals);
+}
+
+int launch_recode(const MsmPlan& pl, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s)
+{
+    k_recode<<<cdiv(pl.n, 128), 128, 0, s>>>(pl, d_scalars, keys, vals, flags);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s)
+{
+    C12_CUDA(cudaMemsetAsync(start, 0, 4 * (size_t)pl.total, s));
+    C12_CUDA(cudaMemsetAsync(end, 0, 4 * (size_t)pl.total, s));
+    k_bucket_bounds<<<dim3(cdiv(pl.n, 256), pl.windows), 256, 0, s>>>(keys, pl.n, pl.half, start, end);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words)
+{
+    size_t nblk = cdiv(n, SORT_TILE);
+    size_t m = (size_t)nseg * 256 * nblk;
+    if (tile_words) *tile_words = cdiv(m, SCAN_TILE) + 1;
+    return m;
+}
+
+// Stable LSD sort of nseg independent segments of n (key, value) pairs each, keys < 2^key_bits.
+// On return `keys`/`vals` point at the sorted arrays (the pointers are swapped per pass).
+int sort_pairs_segmented(uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, uint32_t*& vals_alt, uint32_t n, uint32_t nseg,
+                         uint32_t key_bits, uint32_t* hist, uint32_t* tile_sums, cudaStream_t s)
+{
+    const uint32_t nblk = cdiv(n, SORT_TILE);
+    const size_t m = (size_t)nseg * 256 * nblk;
+    const uint32_t ntiles = cdiv(m, SCAN_TILE);
+    for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+        k_radix_hist<<<dim3(nblk, nseg), SORT_THREADS, 0, s>>>(keys, n, (int)shift, hist, nblk);
+        C12_LAUNCHED();
+        k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, s>>>(hist, m, tile_sums);
+        C12_LAUNCHED();
+        k_scan_top<<<1, SCAN_THREADS, 0, s>>>(tile_sums, ntiles);
+        C12_LAUNCHED();
+        k_scan_apply<<<ntiles, SCAN_THREADS, 0, s>>>(hist, m, tile_sums);
+        C12_LAUNCHED();
+        k_radix_scatter<<<dim3(nblk, nseg), SORT_THREADS, 0, s>>>(keys, vals, keys_alt, vals_alt, n, (int)shift, hist, nblk);
+        C12_LAUNCHED();
+        uint32_t* t = keys; keys = keys_alt; keys_alt = t;
+        t = vals; vals = vals_alt; vals_alt = t;
+    }
+    return C12381_OK;
+}
+
+int flags_reset(cudaStream_t s)
+{
+    C12_CUDA(cudaMemsetAsync(ctx().d_flags, 0, sizeof(int), s));
+    return C12381_OK;
+}
+
+int flags_collect(cudaStream_t s)
+{
+    Ctx& c = ctx();
+    C12_CUDA(cudaMemcpyAsync(c.h_flags, c.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    C12_CUDA(cudaStreamSynchronize(s));
+    C12_CUDA(cudaGetLastError());
+    int f = c.h_flags[0];
+    if (f) {
+        cudaMemsetAsync(c.d_flags, 0, sizeof(int), s);
+        return set_error(C12381_EINPUT, (f & FLAG_BAD_POINT) ? "malformed input: non-canonical coordinate or point off the curve"
+                                                              : "malformed input: scalar >= group order");
+    }
+    return C12381_OK;
+}
+
+} // namespace c12
+
+using namespace c12;
+
+extern "C" int c12381_sync_status(void* stream)
+{
+    C12_REQUIRE_CTX();
+    return flags_collect(stream ? (cudaStream_t)stream : ctx().stream);
+}

@@ -11,8 +11,9 @@
 //
 // Plan for n terms with window width c:  W = ceil(256 / c) windows, 2^(c-1) buckets per window.
 //   digit recode : k = sum_w d_w 2^(c w), d_w in [-2^(c-1)+1, 2^(c-1)]   (top window cannot overflow: W c >= 256)
-//   key          : w * 2^(c-1) + (|d_w| - 1); value = term index | sign << 31; zero digits get key = INVALID
-//   (radix sort by key; bucket b owns sorted[start[b] .. end[b]))
+//   key          : window-local |d_w| - 1, stored at [w*n + i]; value = term index | sign << 31; zero digits get
+//                  key = 2^(c-1) (owns no bucket)
+//   (segmented radix sort by key, one segment per window; bucket b = w*2^(c-1) + key owns sorted[start[b] .. end[b]))
 //   accumulate   : one XYZZ accumulator per bucket, mixed additions of the affine terms
 //   reduce       : per window sum_k k * B_k by segmented running sums, then a tree
 //   combine      : Horner over windows, c doublings per step
@@ -31,7 +32,43 @@ struct MsmPlan {
     uint32_t segs;        // segments per window = ceil(half / seg_len)
 };
 
-C12_HD uint32_t msm_invalid_key(const MsmPlan& pl) { return pl.total; }
+// Window width for n terms: minimises  W * (10 n + 45 * 2^(c-1))  Fp products (10 per mixed bucket addition,
+// ~45 per bucket for the two-level reduction), c in [4, 16] so window-local keys always fit two 8-bit radix
+// passes.  W c >= 256 and scalars < r < 2^255 guarantee the signed recoding never carries out of the top window.
+inline uint32_t msm_choose_window(uint64_t n)
+{
+    uint32_t best = 4;
+    double best_cost = 1e300;
+    for (uint32_t c = 4; c <= 16; ++c) {
+        double W = (double)((256 + c - 1) / c);
+        double cost = W * (10.0 * (double)n + 45.0 * (double)(1u << (c - 1)));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+
+inline MsmPlan msm_make_plan(uint32_t n, uint32_t c)
+{
+    MsmPlan pl;
+    pl.n = n;
+    pl.c = c;
+    pl.windows = (256 + c - 1) / c;
+    pl.half = 1u << (c - 1);
+    pl.total = pl.windows * pl.half;
+    // reduce-1 segment length: aim for >= 64 Ki threads, between 4 and 64 buckets per thread
+    uint32_t seg = pl.total / 65536u;
+    if (seg < 4) seg = 4;
+    if (seg > 64) seg = 64;
+    if (seg > pl.half) seg = pl.half;
+    pl.seg_len = seg;
+    pl.segs = (pl.half + seg - 1) / seg;
+    return pl;
+}
+
+C12_HD uint32_t msm_invalid_key(const MsmPlan& pl) { return pl.half; }
 
 // scalars arrive as 32-byte big-endian; limbs little-endian
 struct Scalar256 {
@@ -80,7 +117,7 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
             keys[o] = msm_invalid_key(pl);
             vals[o] = i;
         } else {
-            keys[o] = w * pl.half + (d - 1);
+            keys[o] = d - 1;
             vals[o] = i | (neg << 31);
         }
     }
@@ -93,6 +130,7 @@ C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint
 {
     XYZZ<F> acc = xyzz_inf<F>();
     uint32_t lo = start[b], hi = end[b];
+#pragma unroll 1
     for (uint32_t j = lo; j < hi; ++j) {
         uint32_t v = vals[j];
         Affine<F> pt = points[v & 0x7fffffffu];
@@ -114,6 +152,7 @@ C12_HD Proj<F> msm_reduce1_body(const MsmPlan& pl, uint32_t w, uint32_t t, const
     const Proj<F>* B = buckets + (uint64_t)w * pl.half;
     Proj<F> run = proj_inf<F>();
     Proj<F> sum = proj_inf<F>();
+#pragma unroll 1
     for (uint32_t j = hi; j > lo; --j) {
         run = proj_add(run, B[j - 1]);
         sum = proj_add(sum, run);
@@ -127,7 +166,9 @@ C12_HD Proj<F> msm_reduce1_body(const MsmPlan& pl, uint32_t w, uint32_t t, const
 template <class F> C12_HD Proj<F> msm_horner_body(const MsmPlan& pl, const Proj<F>* window_sums)
 {
     Proj<F> acc = window_sums[pl.windows - 1];
+#pragma unroll 1
     for (uint32_t w = pl.windows - 1; w > 0; --w) {
+#pragma unroll 1
         for (uint32_t k = 0; k < pl.c; ++k) acc = proj_dbl(acc);
         acc = proj_add(acc, window_sums[w - 1]);
     }

@@ -1,0 +1,14 @@
+// G1 instantiation of the MSM / scalar-multiplication pipeline and its C-ABI entries (include/c12381_cuda.h).
+#include "msm_impl.cuh"
+using namespace c12;
+
+extern "C" {
+int c12381_g1_msm(const uint8_t* points96, const uint8_t* scalars32, size_t n, uint8_t out49[49]) { return entry_msm_host<Fp>(points96, scalars32, n, out49); }
+int c12381_g1_msm_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp>(p, s, n, o, OUT_COMPRESSED, st); }
+int c12381_g1_msm_partial_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp>(p, s, n, o, OUT_AFFINE, st); }
+int c12381_g1_sum_dev(const uint8_t* p, size_t n, uint8_t* o, void* st) { return entry_sum_dev<Fp>(p, n, o, st); }
+int c12381_g1_mul_batch(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o) { return entry_mul_host<Fp>(p, s, n, o); }
+int c12381_g1_mul_batch_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_mul_dev<Fp>(p, s, n, o, st); }
+int c12381_g1_fixed_base_mul_batch(const uint8_t* s, size_t n, uint8_t* o) { return entry_fixed_host<Fp>(s, n, o); }
+int c12381_g1_fixed_base_mul_batch_dev(const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_fixed_dev<Fp>(s, n, o, st); }
+}

@@ -1,0 +1,14 @@
+// G2 instantiation of the MSM / scalar-multiplication pipeline and its C-ABI entries (include/c12381_cuda.h).
+#include "msm_impl.cuh"
+using namespace c12;
+
+extern "C" {
+int c12381_g2_msm(const uint8_t* points192, const uint8_t* scalars32, size_t n, uint8_t out97[97]) { return entry_msm_host<Fp2>(points192, scalars32, n, out97); }
+int c12381_g2_msm_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp2>(p, s, n, o, OUT_COMPRESSED, st); }
+int c12381_g2_msm_partial_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp2>(p, s, n, o, OUT_AFFINE, st); }
+int c12381_g2_sum_dev(const uint8_t* p, size_t n, uint8_t* o, void* st) { return entry_sum_dev<Fp2>(p, n, o, st); }
+int c12381_g2_mul_batch(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o) { return entry_mul_host<Fp2>(p, s, n, o); }
+int c12381_g2_mul_batch_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_mul_dev<Fp2>(p, s, n, o, st); }
+int c12381_g2_fixed_base_mul_batch(const uint8_t* s, size_t n, uint8_t* o) { return entry_fixed_host<Fp2>(s, n, o); }
+int c12381_g2_fixed_base_mul_batch_dev(const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_fixed_dev<Fp2>(s, n, o, st); }
+}

@@ -1,0 +1,378 @@
+// __global__ wrappers and the host-side pipeline of the MSM / batched scalar multiplication entries, templated
+// on the coordinate field (Fp -> G1, Fp2 -> G2).  Included by msm_g1.cu and msm_g2.cu, which instantiate one
+// field each so the two compile in parallel.  The per-thread bodies are in msm_core.cuh / scalar_mul.cuh.
+//
+// Pipeline of one MSM (all on the caller's stream, no host synchronisation inside):
+//   k_parse_points   wire bytes -> Montgomery affine points in HBM (canonical + on-curve checks)
+//   k_recode         scalars -> signed window digits -> (window-local key, term|sign) pairs, window-major
+//   radix sort       segmented per window, ceil(c/8) passes of hist / scan / scatter  (sort.cuh)
+//   k_bucket_bounds  [start, end) of every bucket in the sorted pairs
+//   k_accumulate     one thread per bucket: XYZZ mixed additions of its terms        <- the dominant kernel
+//   k_reduce1        one thread per (window, segment): running sums  sum_k k B_k
+//   k_reduce2        one block per window: warp-shuffle tree over the segment sums
+//   k_finish         Horner over windows, affine normalisation, wire encoding
+#pragma once
+#include "common.cuh"
+#include "scalar_mul.cuh"
+
+namespace c12 {
+
+enum { FLAG_BAD_POINT = 1, FLAG_BAD_SCALAR = 2 };
+enum { OUT_COMPRESSED = 0, OUT_AFFINE = 1 };
+
+template <class T> __device__ __forceinline__ T shfl_down_obj(const T& x, int delta)
+{
+    static_assert(sizeof(T) % 4 == 0, "word-sized objects only");
+    T r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&x);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) d[i] = __shfl_down_sync(0xffffffffu, s[i], delta);
+    return r;
+}
+
+// Sum of one value per thread over a 256-thread block (fixed tree: deterministic).  Result valid in thread 0.
+template <class F> __device__ Proj<F> block_sum_256(Proj<F> acc)
+{
+    __shared__ Proj<F> warp_part[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) {
+        Proj<F> o = shfl_down_obj(acc, off);
+        acc = proj_add(acc, o);
+    }
+    if (lane == 0) warp_part[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        acc = lane < 8 ? warp_part[lane] : proj_inf<F>();
+#pragma unroll 1
+        for (int off = 4; off >= 1; off >>= 1) {
+            Proj<F> o = shfl_down_obj(acc, off);
+            acc = proj_add(acc, o);
+        }
+    }
+    return acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t n, Affine<F>* __restrict__ pts,
+                                                      int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p;
+    if (!Wire<F>::parse(p, bytes + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
+    pts[i] = p;
+}
+
+// defined once in msm_common.cu (kernels there are launched through these host functions)
+int launch_recode(const MsmPlan& pl, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s);
+int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s);
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                                    const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
+                                                    Proj<F>* __restrict__ buckets)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    buckets[b] = msm_accumulate_body<F>(b, start, end, vals, pts);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_reduce1(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ partial)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pl.segs) return;
+    uint32_t w = blockIdx.y;
+    partial[(size_t)w * pl.segs + t] = msm_reduce1_body<F>(pl, w, t, buckets);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) k_reduce2(MsmPlan pl, const Proj<F>* __restrict__ partial, Proj<F>* __restrict__ wsum)
+{
+    uint32_t w = blockIdx.x;
+    Proj<F> acc = proj_inf<F>();
+    for (uint32_t t = threadIdx.x; t < pl.segs; t += 256) acc = proj_add(acc, partial[(size_t)w * pl.segs + t]);
+    acc = block_sum_256(acc);
+    if (threadIdx.x == 0) wsum[w] = acc;
+}
+
+template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, int out_mode)
+{
+    Affine<F> a = proj_to_affine(r);
+    if (out_mode == OUT_AFFINE)
+        Wire<F>::serialize(out, a);
+    else
+        Wire<F>::compress(out, a);
+}
+
+template <class F> __global__ void k_finish(MsmPlan pl, const Proj<F>* __restrict__ wsum, uint8_t* out, int out_mode)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    write_point<F>(out, msm_horner_body<F>(pl, wsum), out_mode);
+}
+
+// sum of n wire-format points (merging all-gathered per-rank partials; also a general point-sum entry)
+template <class F>
+__global__ void __launch_bounds__(256) k_sum_points(const uint8_t* __restrict__ bytes, uint32_t n, uint8_t* out, int out_mode, int* flags)
+{
+    Proj<F> acc = proj_inf<F>();
+    for (uint32_t i = threadIdx.x; i < n; i += 256) {
+        Affine<F> p;
+        if (!Wire<F>::parse(p, bytes + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
+        acc = proj_add_affine(acc, p);
+    }
+    acc = block_sum_256(acc);
+    if (threadIdx.x == 0) write_point<F>(out, acc, out_mode);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_scalar_mul(const uint8_t* __restrict__ pts, const uint8_t* __restrict__ scalars, uint32_t n,
+                                                    uint8_t* __restrict__ out, int out_mode, int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Scalar256 k = scalar_from_be32(scalars + 32ull * i);
+    if (!scalar_is_canonical(k)) atomicOr(flags, FLAG_BAD_SCALAR);
+    const size_t stride = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
+    if (!scalar_mul_body<F>(pts + (size_t)Wire<F>::AFFINE * i, scalars + 32ull * i, out + stride * i, out_mode == OUT_AFFINE))
+        atomicOr(flags, FLAG_BAD_POINT);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_base(const uint8_t* __restrict__ scalars, uint32_t n, uint8_t* __restrict__ out, int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Scalar256 k = scalar_from_be32(scalars + 32ull * i);
+    if (!scalar_is_canonical(k)) atomicOr(flags, FLAG_BAD_SCALAR);
+    fixed_base_body<F>(scalars + 32ull * i, out + (size_t)Wire<F>::AFFINE * i);
+}
+
+// ---- host pipeline ------------------------------------------------------------------------------------------
+int sort_pairs_segmented(uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, uint32_t*& vals_alt, uint32_t n, uint32_t nseg,
+                         uint32_t key_bits, uint32_t* hist, uint32_t* tile_sums, cudaStream_t s);
+size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words);
+
+template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
+{
+    size_t N = (size_t)pl.n * pl.windows;
+    size_t tile_words = 0;
+    size_t hist_words = sort_scratch_words(pl.n, pl.windows, &tile_words);
+    size_t b = 0;
+    b += align_up(sizeof(Affine<F>) * (size_t)pl.n);
+    b += 4 * align_up(4 * N);
+    b += align_up(4 * hist_words) + align_up(4 * tile_words);
+    b += 2 * align_up(4 * (size_t)pl.total);
+    b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
+    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
+    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows);
+    return b + 65536;
+}
+
+// scratch bound for an n-term MSM under the current window setting (callers arena_begin with at least this much)
+template <class F> size_t msm_scratch_for(size_t n)
+{
+    if (n == 0 || n > (1ull << 27)) return 0;
+    uint32_t cbits = ctx().forced_window ? (uint32_t)ctx().forced_window : msm_choose_window(n);
+    if (cbits < 2 || cbits > 16) return 0;
+    return msm_scratch_bytes<F>(msm_make_plan((uint32_t)n, cbits));
+}
+
+// The caller has arena_begin()'d at least msm_scratch_for<F>(n) bytes beyond what it took itself.
+// d_points: n wire-format affine points; d_scalars: n x 32 B big-endian; d_out: Wire<F>::COMPRESSED or ::AFFINE bytes.
+// Everything is enqueued on `s`; malformed input is reported through the context flag word (c12381_sync_status /
+// the host entry's return code), never by a different code path.
+template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint8_t* d_out, int out_mode, cudaStream_t s)
+{
+    Ctx& c = ctx();
+    const int out_bytes = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
+    if (n_sz == 0) {
+        C12_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, s));
+        return C12381_OK;
+    }
+    if (n_sz > (1ull << 27)) return set_error(C12381_EARG, "msm: n > 2^27 terms per call is not supported");
+    const uint32_t n = (uint32_t)n_sz;
+    uint32_t cbits = c.forced_window ? (uint32_t)c.forced_window : msm_choose_window(n);
+    if (cbits < 2 || cbits > 16) return set_error(C12381_EARG, "msm: window width must be in [2, 16]");
+    const MsmPlan pl = msm_make_plan(n, cbits);
+    const size_t N = (size_t)n * pl.windows;
+
+    int rc;
+    size_t tile_words = 0;
+    size_t hist_words = sort_scratch_words(n, pl.windows, &tile_words);
+    Affine<F>* pts = (Affine<F>*)arena_take(sizeof(Affine<F>) * (size_t)n);
+    uint32_t* keys = (uint32_t*)arena_take(4 * N);
+    uint32_t* vals = (uint32_t*)arena_take(4 * N);
+    uint32_t* keys2 = (uint32_t*)arena_take(4 * N);
+    uint32_t* vals2 = (uint32_t*)arena_take(4 * N);
+    uint32_t* hist = (uint32_t*)arena_take(4 * hist_words);
+    uint32_t* tiles = (uint32_t*)arena_take(4 * tile_words);
+    uint32_t* start = (uint32_t*)arena_take(4 * (size_t)pl.total);
+    uint32_t* end = (uint32_t*)arena_take(4 * (size_t)pl.total);
+    Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
+    Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
+    Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows);
+    if (!wsum) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
+
+    C12_CUDA(cudaEventRecord(c.ev[0], s));
+    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pts, c.d_flags);
+    C12_LAUNCHED();
+    rc = launch_recode(pl, d_scalars, keys, vals, c.d_flags, s);
+    if (rc) return rc;
+    rc = sort_pairs_segmented(keys, vals, keys2, vals2, n, pl.windows, pl.c, hist, tiles, s);
+    if (rc) return rc;
+    rc = launch_bucket_bounds(pl, keys, start, end, s);
+    if (rc) return rc;
+    C12_CUDA(cudaEventRecord(c.ev[1], s));
+    k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, buckets);
+    C12_LAUNCHED();
+    C12_CUDA(cudaEventRecord(c.ev[2], s));
+    k_reduce1<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);
+    C12_LAUNCHED();
+    k_reduce2<F><<<pl.windows, 256, 0, s>>>(pl, partial, wsum);
+    C12_LAUNCHED();
+    k_finish<F><<<1, 32, 0, s>>>(pl, wsum, d_out, out_mode);
+    C12_LAUNCHED();
+    C12_CUDA(cudaEventRecord(c.ev[3], s));
+    c.stats.window_bits = (int)pl.c;
+    c.stats.bucket_adds = N;
+    c.stats.accumulate_ms = -1.0;  // resolved lazily by c12381_last_msm_stats
+    return C12381_OK;
+}
+
+template <class F> int sum_run(const uint8_t* d_points, size_t n, uint8_t* d_out, int out_mode, cudaStream_t s)
+{
+    Ctx& c = ctx();
+    if (n > 0xffffffffull) return set_error(C12381_EARG, "sum: too many points");
+    k_sum_points<F><<<1, 256, 0, s>>>(d_points, (uint32_t)n, d_out, out_mode, c.d_flags);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+template <class F>
+int scalar_mul_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n, uint8_t* d_out, cudaStream_t s, int out_mode = OUT_COMPRESSED)
+{
+    Ctx& c = ctx();
+    if (n == 0) return C12381_OK;
+    if (n > 0x7fffffffull) return set_error(C12381_EARG, "mul_batch: too many terms");
+    k_scalar_mul<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, d_scalars, (uint32_t)n, d_out, out_mode, c.d_flags);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+template <class F> int fixed_base_run(const uint8_t* d_scalars, size_t n, uint8_t* d_out, cudaStream_t s)
+{
+    Ctx& c = ctx();
+    if (n == 0) return C12381_OK;
+    if (n > 0x7fffffffull) return set_error(C12381_EARG, "fixed_base: too many terms");
+    k_fixed_base<F><<<cdiv(n, 128), 128, 0, s>>>(d_scalars, (uint32_t)n, d_out, c.d_flags);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+// ---- host-pointer wrappers: stage in, run, stage out, report the flag word ---------------------------------------
+int flags_reset(cudaStream_t s);
+int flags_collect(cudaStream_t s);  // synchronises `s`; returns C12381_EINPUT if any input was malformed
+
+// Host-pointer entry: one arena reservation covers staging + pipeline scratch; copies ride the context stream.
+// run(d_in[], d_out, stream) enqueues the device pipeline.
+template <class Fn>
+int with_staged(const void* const* host_in, const size_t* in_bytes, int n_in, void* host_out, size_t out_bytes, size_t scratch, Fn&& run)
+{
+    Ctx& c = ctx();
+    cudaStream_t s = c.stream;
+    size_t total = scratch + align_up(out_bytes) + 4096;
+    for (int i = 0; i < n_in; ++i) total += align_up(in_bytes[i]);
+    int rc = arena_begin(total, s);
+    if (rc) return rc;
+    uint8_t* d_in[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < n_in; ++i) {
+        d_in[i] = (uint8_t*)arena_take(in_bytes[i] ? in_bytes[i] : 4);
+        if (in_bytes[i]) C12_CUDA(cudaMemcpyAsync(d_in[i], host_in[i], in_bytes[i], cudaMemcpyHostToDevice, s));
+    }
+    uint8_t* d_out = (uint8_t*)arena_take(out_bytes ? out_bytes : 4);
+    rc = flags_reset(s);
+    if (rc) return rc;
+    rc = run(d_in, d_out, s);
+    if (rc) {
+        cudaStreamSynchronize(s);
+        return rc;
+    }
+    if (out_bytes) C12_CUDA(cudaMemcpyAsync(host_out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    return flags_collect(s);
+}
+
+} // namespace c12
+
+// ---- entry-point bodies shared by the G1 and G2 translation units --------------------------------------------
+namespace c12 {
+
+static inline cudaStream_t pick_stream(void* stream) { return stream ? (cudaStream_t)stream : ctx().stream; }
+
+template <class F> int entry_msm_dev(const uint8_t* d_points, const uint8_t* d_scalars, size_t n, uint8_t* d_out, int out_mode, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (!d_out || (n && (!d_points || !d_scalars))) return set_error(C12381_EARG, "msm: null pointer");
+    cudaStream_t s = pick_stream(stream);
+    int rc = arena_begin(msm_scratch_for<F>(n), s);
+    if (rc) return rc;
+    return msm_run<F>(d_points, d_scalars, n, d_out, out_mode, s);
+}
+
+template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out)
+{
+    C12_REQUIRE_CTX();
+    if (!out || (n && (!points || !scalars))) return set_error(C12381_EARG, "msm: null pointer");
+    const void* in[2] = {points, scalars};
+    size_t sz[2] = {n * Wire<F>::AFFINE, n * 32};
+    return with_staged(in, sz, 2, out, Wire<F>::COMPRESSED, msm_scratch_for<F>(n), [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+        return msm_run<F>(d_in[0], d_in[1], n, d_out, OUT_COMPRESSED, s);
+    });
+}
+
+template <class F> int entry_sum_dev(const uint8_t* d_points, size_t n, uint8_t* d_out, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (!d_out || (n && !d_points)) return set_error(C12381_EARG, "sum: null pointer");
+    return sum_run<F>(d_points, n, d_out, OUT_COMPRESSED, pick_stream(stream));
+}
+
+template <class F> int entry_mul_dev(const uint8_t* d_points, const uint8_t* d_scalars, size_t n, uint8_t* d_out, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!d_out || !d_points || !d_scalars)) return set_error(C12381_EARG, "mul_batch: null pointer");
+    return scalar_mul_run<F>(d_points, d_scalars, n, d_out, pick_stream(stream));
+}
+
+template <class F> int entry_mul_host(const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!out || !points || !scalars)) return set_error(C12381_EARG, "mul_batch: null pointer");
+    const void* in[2] = {points, scalars};
+    size_t sz[2] = {n * Wire<F>::AFFINE, n * 32};
+    return with_staged(in, sz, 2, out, n * Wire<F>::COMPRESSED, 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+        return scalar_mul_run<F>(d_in[0], d_in[1], n, d_out, s);
+    });
+}
+
+template <class F> int entry_fixed_dev(const uint8_t* d_scalars, size_t n, uint8_t* d_out, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!d_out || !d_scalars)) return set_error(C12381_EARG, "fixed_base: null pointer");
+    return fixed_base_run<F>(d_scalars, n, d_out, pick_stream(stream));
+}
+
+template <class F> int entry_fixed_host(const uint8_t* scalars, size_t n, uint8_t* out)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!out || !scalars)) return set_error(C12381_EARG, "fixed_base: null pointer");
+    const void* in[1] = {scalars};
+    size_t sz[1] = {n * 32};
+    return with_staged(in, sz, 1, out, n * Wire<F>::AFFINE, 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+        return fixed_base_run<F>(d_in[0], n, d_out, s);
+    });
+}
+
+} // namespace c12

@@ -139,6 +139,7 @@ C12_HD_NOINLINE Fp12 pow_x_abs(const Fp12& x)
 {
     const uint64_t e = C12_X_ABS;
     Fp12 r = x;
+#pragma unroll 1
     for (int i = 62; i >= 0; --i) {
         r = usqr(r);
         if ((e >> i) & 1ull) r = mul(r, x);
@@ -170,6 +171,7 @@ C12_HD_NOINLINE Fp12 gt_pow(const Fp12& a, const Scalar256& k)
 {
     Fp12 r = fp12_one();
     bool started = false;
+#pragma unroll 1
     for (int i = 255; i >= 0; --i) {
         if (started) r = usqr(r);
         if ((k.v[i >> 5] >> (i & 31)) & 1u) {
@@ -221,6 +223,7 @@ C12_HD_NOINLINE Fp12 miller_loop(const Affine<Fp>* P, const Affine<Fp2>* Q, uint
 {
     Proj<Fp2> A[C12_MAX_PAIRS], B[C12_MAX_PAIRS];
     bool live[C12_MAX_PAIRS];
+#pragma unroll 1
     for (uint32_t j = 0; j < k; ++j) {
         live[j] = !affine_is_inf(P[j]);
         B[j] = proj_from_affine(Q[j]);  // identity stays (0:1:0), as ECP2_affine leaves it
@@ -229,8 +232,10 @@ C12_HD_NOINLINE Fp12 miller_loop(const Affine<Fp>* P, const Affine<Fp2>* Q, uint
     Fp12 r = fp12_one();
     // digit_i = bit_i(3|x|) - bit_i(|x|) for i = 64 .. 1 (pair_BLS12381.cpp:147-169,466-483); bit i-1 of the masks
     const uint64_t pos = 0x1201000000010000ull, negm = 0x4000000000000000ull;
+#pragma unroll 1
     for (int i = 64; i >= 1; --i) {
         r = sqr(r);
+#pragma unroll 1
         for (uint32_t j = 0; j < k; ++j) {
             if (!live[j]) continue;
             LineCoeffs l = pair_double(A[j]);
@@ -238,6 +243,7 @@ C12_HD_NOINLINE Fp12 miller_loop(const Affine<Fp>* P, const Affine<Fp2>* Q, uint
         }
         int bt = (int)((pos >> (i - 1)) & 1ull) - (int)((negm >> (i - 1)) & 1ull);
         if (bt != 0) {
+#pragma unroll 1
             for (uint32_t j = 0; j < k; ++j) {
                 if (!live[j]) continue;
                 Proj<Fp2> T = B[j];
@@ -288,6 +294,7 @@ C12_HD bool pairing_product_body(const uint8_t* g1, const uint8_t* g2, uint32_t 
     Affine<Fp2> Q[C12_MAX_PAIRS];
     bool ok = k <= C12_MAX_PAIRS;
     if (!ok) k = 0;
+#pragma unroll 1
     for (uint32_t j = 0; j < k; ++j) {
         ok = g1_from_bytes96(P[j], g1 + 96 * j) && ok;
         ok = g2_from_bytes192(Q[j], g2 + 192 * j) && ok;

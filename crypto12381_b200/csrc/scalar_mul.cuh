@@ -32,9 +32,11 @@ template <class F> C12_HD Proj<F> proj_scalar_mul(const Affine<F>& p, const Scal
     tab[0] = proj_inf<F>();
     tab[1] = proj_from_affine(p);
     tab[2] = proj_dbl(tab[1]);
+#pragma unroll 1
     for (int i = 3; i < 16; ++i) tab[i] = proj_add_affine_nz(tab[i - 1], p);
     Proj<F> acc = proj_inf<F>();
     bool started = false;
+#pragma unroll 1
     for (int i = 63; i >= 0; --i) {
         if (started) {
             acc = proj_dbl(acc);
@@ -51,13 +53,17 @@ template <class F> C12_HD Proj<F> proj_scalar_mul(const Affine<F>& p, const Scal
     return acc;
 }
 
-template <class F> C12_HD bool scalar_mul_body(const uint8_t* point_bytes, const uint8_t* scalar_be32, uint8_t* out_compressed)
+// affine_out = false: Wire<F>::COMPRESSED bytes; true: Wire<F>::AFFINE bytes
+template <class F> C12_HD bool scalar_mul_body(const uint8_t* point_bytes, const uint8_t* scalar_be32, uint8_t* out, bool affine_out = false)
 {
     Affine<F> p;
     bool ok = Wire<F>::parse(p, point_bytes);
     Scalar256 k = scalar_from_be32(scalar_be32);
     Proj<F> r = proj_scalar_mul(p, k);
-    Wire<F>::compress(out_compressed, proj_to_affine(r));
+    if (affine_out)
+        Wire<F>::serialize(out, proj_to_affine(r));
+    else
+        Wire<F>::compress(out, proj_to_affine(r));
     return ok;
 }
 

@@ -1,0 +1,198 @@
+"""The hot-path operations on CUDA-resident data: torch uint8 tensors in, torch uint8 tensors out, work enqueued on
+torch's CURRENT stream (so torch.cuda.Event timing brackets it).  PyTorch is only the owner of device memory and
+streams here; every kernel is this library's own (libc12381_cuda.so `_dev` entries).
+
+Malformed input cannot be reported by an enqueue-only call: use `sync_status()` (synchronises, raises
+C12381Error(EINPUT) if a kernel flagged anything since the last check)."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, ensure_init, lib
+
+G1_AFFINE, G2_AFFINE, G1_COMPRESSED, G2_COMPRESSED, GT_BYTES, SCALAR = 96, 192, 49, 97, 576, 32
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{what}: need a contiguous CUDA uint8 tensor")
+    return t
+
+
+def _new(n: int, like: torch.Tensor) -> torch.Tensor:
+    return torch.empty(max(n, 1), dtype=torch.uint8, device=like.device)[:n]
+
+
+def sync_status() -> None:
+    ensure_init()
+    check(lib().c12381_sync_status(_stream()))
+
+
+def _msm(fn_name: str, point_bytes: int, out_bytes: int, points: torch.Tensor, scalars: torch.Tensor, out=None):
+    ensure_init()
+    _chk(points, "points"), _chk(scalars, "scalars")
+    n = scalars.numel() // SCALAR
+    if scalars.numel() != n * SCALAR or points.numel() != n * point_bytes:
+        raise ValueError("points / scalars size mismatch")
+    if out is None:
+        out = _new(out_bytes, points)
+    check(getattr(lib(), fn_name)(points.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def g1_msm(points, scalars, out=None):
+    """Σ scalars[i]·points[i] over G1 -> 49-byte compressed point."""
+    return _msm("c12381_g1_msm_dev", G1_AFFINE, G1_COMPRESSED, points, scalars, out)
+
+
+def g1_msm_partial(points, scalars, out=None):
+    """Same sum as a 96-byte AFFINE point: the per-rank partial of a sharded MSM."""
+    return _msm("c12381_g1_msm_partial_dev", G1_AFFINE, G1_AFFINE, points, scalars, out)
+
+
+def g2_msm(points, scalars, out=None):
+    return _msm("c12381_g2_msm_dev", G2_AFFINE, G2_COMPRESSED, points, scalars, out)
+
+
+def g2_msm_partial(points, scalars, out=None):
+    return _msm("c12381_g2_msm_partial_dev", G2_AFFINE, G2_AFFINE, points, scalars, out)
+
+
+def g1_sum(points, out=None):
+    """Σ points[i] (merging all-gathered partials) -> 49-byte compressed point."""
+    ensure_init()
+    _chk(points, "points")
+    n = points.numel() // G1_AFFINE
+    if out is None:
+        out = _new(G1_COMPRESSED, points)
+    check(lib().c12381_g1_sum_dev(points.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def g2_sum(points, out=None):
+    ensure_init()
+    _chk(points, "points")
+    n = points.numel() // G2_AFFINE
+    if out is None:
+        out = _new(G2_COMPRESSED, points)
+    check(lib().c12381_g2_sum_dev(points.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def g1_mul_batch(points, scalars, out=None):
+    ensure_init()
+    n = _chk(scalars, "scalars").numel() // SCALAR
+    _chk(points, "points")
+    if out is None:
+        out = _new(n * G1_COMPRESSED, points)
+    check(lib().c12381_g1_mul_batch_dev(points.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def g2_mul_batch(points, scalars, out=None):
+    ensure_init()
+    n = _chk(scalars, "scalars").numel() // SCALAR
+    _chk(points, "points")
+    if out is None:
+        out = _new(n * G2_COMPRESSED, points)
+    check(lib().c12381_g2_mul_batch_dev(points.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def g1_fixed_base_mul_batch(scalars, out=None):
+    ensure_init()
+    n = _chk(scalars, "scalars").numel() // SCALAR
+    if out is None:
+        out = _new(n * G1_AFFINE, scalars)
+    check(lib().c12381_g1_fixed_base_mul_batch_dev(scalars.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def g2_fixed_base_mul_batch(scalars, out=None):
+    ensure_init()
+    n = _chk(scalars, "scalars").numel() // SCALAR
+    if out is None:
+        out = _new(n * G2_AFFINE, scalars)
+    check(lib().c12381_g2_fixed_base_mul_batch_dev(scalars.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def _pairing(fn_name: str, g1s, g2s, k: int, out_per_instance: int, out=None):
+    ensure_init()
+    _chk(g1s, "g1s"), _chk(g2s, "g2s")
+    if not 1 <= k <= _lib.MAX_PAIRS:
+        raise ValueError("k out of range")
+    b = g1s.numel() // (G1_AFFINE * k)
+    if g1s.numel() != b * G1_AFFINE * k or g2s.numel() != b * G2_AFFINE * k:
+        raise ValueError("g1s / g2s size mismatch")
+    if out is None:
+        out = _new(b * out_per_instance, g1s)
+    check(getattr(lib(), fn_name)(g1s.data_ptr(), g2s.data_ptr(), b, k, out.data_ptr(), _stream()))
+    return out
+
+
+def miller_batch(g1s, g2s, k, out=None):
+    return _pairing("c12381_miller_batch_dev", g1s, g2s, k, GT_BYTES, out)
+
+
+def pairing_product_batch(g1s, g2s, k, out=None):
+    return _pairing("c12381_pairing_product_batch_dev", g1s, g2s, k, GT_BYTES, out)
+
+
+def pairing_check_batch(g1s, g2s, k, out=None):
+    return _pairing("c12381_pairing_check_batch_dev", g1s, g2s, k, 1, out)
+
+
+def final_exp_batch(values, out=None):
+    ensure_init()
+    b = _chk(values, "values").numel() // GT_BYTES
+    if out is None:
+        out = _new(b * GT_BYTES, values)
+    check(lib().c12381_final_exp_batch_dev(values.data_ptr(), b, out.data_ptr(), _stream()))
+    return out
+
+
+def gt_mul_batch(a, b, out=None):
+    ensure_init()
+    n = _chk(a, "a").numel() // GT_BYTES
+    _chk(b, "b")
+    if out is None:
+        out = _new(n * GT_BYTES, a)
+    check(lib().c12381_gt_mul_batch_dev(a.data_ptr(), b.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def gt_pow_batch(a, scalars, out=None):
+    ensure_init()
+    n = _chk(a, "a").numel() // GT_BYTES
+    _chk(scalars, "scalars")
+    if out is None:
+        out = _new(n * GT_BYTES, a)
+    check(lib().c12381_gt_pow_batch_dev(a.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def launch_count() -> int:
+    return int(lib().c12381_launch_count())
+
+
+def last_msm_stats() -> dict:
+    import ctypes
+    a, t = ctypes.c_double(), ctypes.c_double()
+    adds, c = ctypes.c_ulonglong(), ctypes.c_int()
+    check(lib().c12381_last_msm_stats(ctypes.byref(a), ctypes.byref(t), ctypes.byref(adds), ctypes.byref(c)))
+    return {"accumulate_ms": a.value, "total_ms": t.value, "bucket_adds": adds.value, "window_bits": c.value}
+
+
+def probe(kind: int, iters: int = 2000) -> dict:
+    """Integer-multiply roofline probes; see include/c12381_cuda.h for the kinds."""
+    import ctypes
+    ensure_init()
+    g, ms = ctypes.c_double(), ctypes.c_double()
+    check(lib().c12381_probe(kind, iters, ctypes.byref(g), ctypes.byref(ms)))
+    return {"gops": g.value, "ms": ms.value}

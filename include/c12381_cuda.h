@@ -1,0 +1,162 @@
+/* c12381_cuda.h — C ABI of libc12381_cuda.so: the B200 (sm_100a) implementation of crypto12381's data-parallel
+ * hot path.  These entry points are what a replacement of the reference bridge
+ * (`crypto12381::detail::miracl_core`, include/crypto12381/miracl_core_interface.hpp, defined in
+ * src/miracl_core_interface.cpp) binds to; each declaration cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative C12381_E* code otherwise; nothing throws; the caller owns
+ *     every buffer; there is NO CPU fallback: without a CUDA device every compute entry returns C12381_ENODEV.
+ *   - "host" entries take host pointers and include the host<->device copies; "_dev" entries take device
+ *     pointers plus a cudaStream_t (passed as void*) and enqueue work only.
+ *   - canonical byte formats (the reference's own wire formats):
+ *       scalar      32 B big-endian integer in [0, r)
+ *       G1 affine   96 B  = x || y, 48 B big-endian each; identity = 96 zero bytes
+ *       G2 affine   192 B = x.b || x.a || y.b || y.a (imaginary part first, FP2_toBytes order); identity = zeros
+ *       G1 compressed 49 B = (0x02 | parity(y)) || x   (ECP_toOctet, ecp_BLS12381.cpp:445-491); identity = zeros
+ *       G2 compressed 97 B = (0x02 | FP2_sign(y)) || x.b || x.a (ECP2_toOctet, ecp2_BLS12381.cpp:184-222)
+ *       GT          576 B FP12_toOctet order (fp12_BLS12381.cpp:923-929)
+ *   - "_miracl" entries take the reference's in-memory PODs (big = int64[7] 58-bit limbs; fp = big + int32 xes,
+ *     Montgomery residue with R = 2^406; point1 192 B, point2 384 B, fp12 776 B) so the forwarding
+ *     translation unit can pass its arguments through unchanged.
+ *   - inputs are expected in the r-torsion subgroups (as produced by the reference), scalars reduced mod r.
+ */
+#ifndef C12381_CUDA_H
+#define C12381_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define C12381_API __attribute__((visibility("default")))
+#else
+#define C12381_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C12381_OK 0
+#define C12381_ENODEV (-1)   /* no CUDA device / context not initialised */
+#define C12381_ECUDA (-2)    /* a CUDA runtime call failed (see c12381_last_error) */
+#define C12381_EINPUT (-3)   /* malformed input: non-canonical coordinate, point off curve, scalar >= r */
+#define C12381_EARG (-4)     /* bad argument (null pointer, k out of range, ...) */
+
+#define C12381_MAX_PAIRS 8   /* pairs per pairing product instance */
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+/* Bind this process to CUDA device `device` (one process per GPU) and create the stream + scratch pool. */
+C12381_API int c12381_init(int device);
+C12381_API void c12381_shutdown(void);
+C12381_API const char* c12381_last_error(void);
+C12381_API int c12381_device(void);              /* bound device or -1 */
+/* The "_dev" entries only enqueue work, so malformed input (C12381_EINPUT) cannot be reported by their return value:
+ * this call synchronises `stream` (NULL = the context stream) and returns C12381_EINPUT if any kernel enqueued since
+ * the last check flagged a non-canonical coordinate, an off-curve point or a scalar >= r (then clears the flag).
+ * The host-pointer entries do this themselves.  The reference reports parse failures the same way: by status
+ * (from_bytes returns 0, src/miracl_core_interface.cpp:109-112), never by a different result. */
+C12381_API int c12381_sync_status(void* stream);
+/* testing/tuning knob: force the MSM window width (0 = automatic) */
+C12381_API void c12381_set_msm_window(int c);
+
+/* ---- multi-scalar multiplication ------------------------------------------------------------------------- */
+/* out = sum_i scalars[i] * points[i] over G1.
+ * Replaces sum_of_products(point1&, int, point1*, const big*) -> ECP_muln
+ * (miracl_core_interface.hpp:143; src/miracl_core_interface.cpp:134-137) and the live DSL MSM loop
+ * product(type_identity<G1Pow>, range) of double_multiply calls (g1_point.hpp:371-404). */
+C12381_API int c12381_g1_msm(const uint8_t* points96, const uint8_t* scalars32, size_t n, uint8_t out49[49]);
+C12381_API int c12381_g1_msm_dev(const uint8_t* d_points96, const uint8_t* d_scalars32, size_t n, uint8_t* d_out49, void* stream);
+/* same sum, result as AFFINE 96 B (the per-rank partial of a sharded MSM) */
+C12381_API int c12381_g1_msm_partial_dev(const uint8_t* d_points96, const uint8_t* d_scalars32, size_t n, uint8_t* d_out96, void* stream);
+/* out = sum_i points[i] (combining the all-gathered per-rank partials in rank order); compressed result.
+ * Replaces the add(point1&, point1&) loop (src/miracl_core_interface.cpp:129-132) used to merge partials. */
+C12381_API int c12381_g1_sum_dev(const uint8_t* d_points96, size_t n, uint8_t* d_out49, void* stream);
+
+/* out = sum_i scalars[i] * points[i] over G2.  The reference has no G2 MSM entry: it replaces the per-term
+ * multiply(point2&, const big&) -> PAIR_G2mul + add(point2&, point2&) loop (g2_point.hpp:202-236;
+ * src/miracl_core_interface.cpp:202-205,212-215). */
+C12381_API int c12381_g2_msm(const uint8_t* points192, const uint8_t* scalars32, size_t n, uint8_t out97[97]);
+C12381_API int c12381_g2_msm_dev(const uint8_t* d_points192, const uint8_t* d_scalars32, size_t n, uint8_t* d_out97, void* stream);
+C12381_API int c12381_g2_msm_partial_dev(const uint8_t* d_points192, const uint8_t* d_scalars32, size_t n, uint8_t* d_out192, void* stream);
+C12381_API int c12381_g2_sum_dev(const uint8_t* d_points192, size_t n, uint8_t* d_out97, void* stream);
+
+/* ---- batched scalar multiplication ------------------------------------------------------------------------ */
+/* out[i] = scalars[i] * points[i], compressed.  Replaces multiply(point1&, const big&) -> PAIR_G1mul
+ * (src/miracl_core_interface.cpp:174-177) / multiply(point2&, const big&) -> PAIR_G2mul (:202-205). */
+C12381_API int c12381_g1_mul_batch(const uint8_t* points96, const uint8_t* scalars32, size_t n, uint8_t* out49);
+C12381_API int c12381_g2_mul_batch(const uint8_t* points192, const uint8_t* scalars32, size_t n, uint8_t* out97);
+C12381_API int c12381_g1_mul_batch_dev(const uint8_t* d_points96, const uint8_t* d_scalars32, size_t n, uint8_t* d_out49, void* stream);
+C12381_API int c12381_g2_mul_batch_dev(const uint8_t* d_points192, const uint8_t* d_scalars32, size_t n, uint8_t* d_out97, void* stream);
+/* out[i] = scalars[i] * generator, AFFINE.  Replaces the `select` path g^x: get_default_generator + multiply
+ * (g1_point.hpp:355-369, g2_point.hpp:129-143; src/miracl_core_interface.cpp:169-177,233-236). */
+C12381_API int c12381_g1_fixed_base_mul_batch(const uint8_t* scalars32, size_t n, uint8_t* out96);
+C12381_API int c12381_g2_fixed_base_mul_batch(const uint8_t* scalars32, size_t n, uint8_t* out192);
+C12381_API int c12381_g1_fixed_base_mul_batch_dev(const uint8_t* d_scalars32, size_t n, uint8_t* d_out96, void* stream);
+C12381_API int c12381_g2_fixed_base_mul_batch_dev(const uint8_t* d_scalars32, size_t n, uint8_t* d_out192, void* stream);
+
+/* ---- pairings --------------------------------------------------------------------------------------------- */
+/* B instances, k pairs each (1 <= k <= C12381_MAX_PAIRS): g1s = B*k*96 B, g2s = B*k*192 B, instance-major.
+ * miller: out[b] = conj-adjusted product of Miller loops, NOT exponentiated (576 B raw Fp12).
+ *   Replaces pair_ate -> PAIR_ate (src/miracl_core_interface.cpp:276-279), pair_double_ate -> PAIR_double_ate
+ *   (:286-289) and their products via multiply(fp12&, fp12&) (:256-259; liner_pair.hpp:219-230,291-303).
+ * final_exp: out[b] = in[b]^(3 (p^12-1)/r).  Replaces pair_final_exponentiation -> PAIR_fexp (:281-284).
+ * pairing_product = final_exp(miller).  pairing_check: verdict[b] = 1 iff the product is the GT identity
+ *   (operator== on pair/Miller operands, liner_pair.hpp:336-357). */
+C12381_API int c12381_miller_batch(const uint8_t* g1s, const uint8_t* g2s, size_t B, int k, uint8_t* out576);
+C12381_API int c12381_final_exp_batch(const uint8_t* in576, size_t B, uint8_t* out576);
+C12381_API int c12381_pairing_product_batch(const uint8_t* g1s, const uint8_t* g2s, size_t B, int k, uint8_t* out576);
+C12381_API int c12381_pairing_check_batch(const uint8_t* g1s, const uint8_t* g2s, size_t B, int k, uint8_t* verdicts);
+C12381_API int c12381_miller_batch_dev(const uint8_t* d_g1s, const uint8_t* d_g2s, size_t B, int k, uint8_t* d_out576, void* stream);
+C12381_API int c12381_final_exp_batch_dev(const uint8_t* d_in576, size_t B, uint8_t* d_out576, void* stream);
+C12381_API int c12381_pairing_product_batch_dev(const uint8_t* d_g1s, const uint8_t* d_g2s, size_t B, int k, uint8_t* d_out576, void* stream);
+C12381_API int c12381_pairing_check_batch_dev(const uint8_t* d_g1s, const uint8_t* d_g2s, size_t B, int k, uint8_t* d_verdicts, void* stream);
+
+/* ---- GT helpers ------------------------------------------------------------------------------------------- */
+/* out[b] = a[b] * b[b].  Replaces multiply(fp12&, fp12&) -> FP12_mul (src/miracl_core_interface.cpp:256-259). */
+C12381_API int c12381_gt_mul_batch(const uint8_t* a576, const uint8_t* b576, size_t B, uint8_t* out576);
+/* out[b] = a[b]^scalars[b] for unitary a.  Replaces pow(fp12&, fp12&, const big&) -> FP12_pow (:261-264). */
+C12381_API int c12381_gt_pow_batch(const uint8_t* a576, const uint8_t* scalars32, size_t B, uint8_t* out576);
+C12381_API int c12381_gt_mul_batch_dev(const uint8_t* d_a576, const uint8_t* d_b576, size_t B, uint8_t* d_out576, void* stream);
+C12381_API int c12381_gt_pow_batch_dev(const uint8_t* d_a576, const uint8_t* d_scalars32, size_t B, uint8_t* d_out576, void* stream);
+
+/* ---- drop-in entries on the reference's PODs (batch of 1 per call; host pointers) --------------------------- */
+/* void sum_of_products(point1& result, int n, point1* points, const big* numbers)  (miracl_core_interface.hpp:143) */
+C12381_API int c12381_sum_of_products_miracl(void* result_point1, int n, const void* points_point1, const void* numbers_big);
+/* void multiply(point1& object, const big& value)  (:165) */
+C12381_API int c12381_multiply_point1_miracl(void* object_point1, const void* value_big);
+/* void double_multiply(point1& p1, point1& p2, big& v1, big& v2): p1 = v1*p1 + v2*p2  (:167) */
+C12381_API int c12381_double_multiply_miracl(void* p1_point1, const void* p2_point1, const void* v1_big, const void* v2_big);
+/* void multiply(point2& object, const big& value)  (:139-141 region; src :202) */
+C12381_API int c12381_multiply_point2_miracl(void* object_point2, const void* value_big);
+/* batched G2 sum of products on PODs (new entry the lazy G2Pow of SURVEY "next" N2 would call) */
+C12381_API int c12381_sum_of_products2_miracl(void* result_point2, int n, const void* points_point2, const void* numbers_big);
+/* void pair_ate(fp12& result, point2& p2, point1& p1)  (:199) */
+C12381_API int c12381_pair_ate_miracl(void* result_fp12, const void* p2_point2, const void* p1_point1);
+/* void pair_double_ate(fp12& result, point2& p2, point1& p1, point2& q2, point1& q1)  (:203) */
+C12381_API int c12381_pair_double_ate_miracl(void* result_fp12, const void* p2, const void* p1, const void* q2, const void* q1);
+/* void pair_final_exponentiation(fp12& object)  (:201) */
+C12381_API int c12381_pair_final_exponentiation_miracl(void* object_fp12);
+/* void multiply(fp12& result, fp12& value): result *= value  (:189) */
+C12381_API int c12381_fp12_multiply_miracl(void* result_fp12, const void* value_fp12);
+/* void pow(fp12& result, fp12& base, const big& exponent)  (:191) */
+C12381_API int c12381_fp12_pow_miracl(void* result_fp12, const void* base_fp12, const void* exponent_big);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------------- */
+/* Integer-multiply roofline probes: run `iters` dependent-chain iterations of the named
+ * instruction mix on every SM and return achieved giga-ops/s in *out_gops (ops as documented per kind):
+ *   kind 0: mad.lo.u32 (IMAD)            ops = 32-bit multiply-adds
+ *   kind 1: mad.lo.cc / madc.hi.cc pairs ops = 32-bit multiply-add instructions
+ *   kind 2: mad.wide.u32 (IMAD.WIDE)     ops = 32x32->64 multiply-adds
+ *   kind 3: full Fp Montgomery product   ops = Fp multiplications
+ *   kind 4: full Fp Montgomery squaring  ops = Fp squarings */
+C12381_API int c12381_probe(int kind, int iters, double* out_gops, double* out_ms);
+/* number of kernels launched by this library since init (bench.py's gpu_launches) */
+C12381_API unsigned long long c12381_launch_count(void);
+/* CUDA-event time (ms) of the dominant MSM kernel (bucket accumulation) in the most recent MSM call, and the
+ * number of bucket additions it performed */
+C12381_API int c12381_last_msm_stats(double* accumulate_ms, double* total_ms, unsigned long long* bucket_adds, int* window_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -10,6 +10,7 @@
 #include "../../crypto12381_b200/csrc/msm_core.cuh"
 #include "../../crypto12381_b200/csrc/scalar_mul.cuh"
 #include "../../crypto12381_b200/csrc/pairing.cuh"
+#include "../../crypto12381_b200/csrc/miracl_pod.cuh"
 
 using namespace c12;
 
@@ -41,18 +42,24 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n, ui
     size_t N = (size_t)n * pl.windows;
     std::vector<uint32_t> keys(N), vals(N);
     for (uint32_t i = 0; i < n; ++i) msm_recode_body(pl, i, sc, keys.data(), vals.data());
+    // segmented stable sort: window w owns [w*n, (w+1)*n), keys are window-local (as the device sort does)
     std::vector<uint32_t> order(N);
     for (size_t i = 0; i < N; ++i) order[i] = (uint32_t)i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    for (uint32_t w = 0; w < pl.windows; ++w)
+        std::stable_sort(order.begin() + (size_t)w * n, order.begin() + (size_t)(w + 1) * n,
+                         [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
     std::vector<uint32_t> sk(N), sv(N);
     for (size_t i = 0; i < N; ++i) { sk[i] = keys[order[i]]; sv[i] = vals[order[i]]; }
     std::vector<uint32_t> start(pl.total, 0), end(pl.total, 0);
-    for (size_t i = 0; i < N; ++i) {
-        uint32_t k = sk[i];
-        if (k >= pl.total) continue;
-        if (i == 0 || sk[i - 1] != k) start[k] = (uint32_t)i;
-        if (i + 1 == N || sk[i + 1] != k) end[k] = (uint32_t)i + 1;
-    }
+    for (uint32_t w = 0; w < pl.windows; ++w)
+        for (size_t i = 0; i < n; ++i) {
+            size_t g = (size_t)w * n + i;
+            uint32_t k = sk[g];
+            if (k >= pl.half) continue;
+            size_t b = (size_t)w * pl.half + k;
+            if (i == 0 || sk[g - 1] != k) start[b] = (uint32_t)g;
+            if (i + 1 == n || sk[g + 1] != k) end[b] = (uint32_t)g + 1;
+        }
     std::vector<Proj<F>> buckets(pl.total);
     for (uint32_t b = 0; b < pl.total; ++b) buckets[b] = msm_accumulate_body<F>(b, start.data(), end.data(), sv.data(), P.data());
     std::vector<Proj<F>> wsum(pl.windows);
@@ -127,5 +134,48 @@ void hm_gt_mul(const uint8_t* a, const uint8_t* b, uint32_t B, uint8_t* out576)
 void hm_gt_pow(const uint8_t* a, const uint8_t* s32, uint32_t B, uint8_t* out576)
 {
     for (uint32_t i = 0; i < B; ++i) gt_pow_body(a + 576 * (size_t)i, s32 + 32 * (size_t)i, out576 + 576 * (size_t)i);
+}
+
+// reference PODs <-> wire formats (bodies of the k_pod_* kernels)
+int hm_pod_points_to_wire(int g2, const uint8_t* pods, uint32_t n, uint8_t* wire)
+{
+    bool ok = true;
+    for (uint32_t i = 0; i < n; ++i)
+        ok = (g2 ? pod_point_to_wire<Fp2>(pods + (size_t)POD_P2 * i, wire + 192 * (size_t)i)
+                 : pod_point_to_wire<Fp>(pods + (size_t)POD_P1 * i, wire + 96 * (size_t)i)) && ok;
+    return ok ? 0 : -1;
+}
+int hm_wire_to_pod_points(int g2, const uint8_t* wire, uint32_t n, uint8_t* pods)
+{
+    bool ok = true;
+    for (uint32_t i = 0; i < n; ++i)
+        ok = (g2 ? wire_to_pod_point<Fp2>(wire + 192 * (size_t)i, pods + (size_t)POD_P2 * i)
+                 : wire_to_pod_point<Fp>(wire + 96 * (size_t)i, pods + (size_t)POD_P1 * i)) && ok;
+    return ok ? 0 : -1;
+}
+int hm_pod_bigs_to_scalars(const uint8_t* bigs, uint32_t n, uint8_t* out32)
+{
+    bool ok = true;
+    for (uint32_t i = 0; i < n; ++i) ok = pod_big_to_scalar(bigs + (size_t)POD_BIG * i, out32 + 32 * (size_t)i) && ok;
+    return ok ? 0 : -1;
+}
+int hm_pod_fp12_to_wire(const uint8_t* pods, uint32_t n, uint8_t* wire)
+{
+    bool ok = true;
+    for (uint32_t e = 0; e < n; ++e)
+        for (uint32_t j = 0; j < 12; ++j) ok = pod_fp12_coeff_to_wire(pods + (size_t)POD_FP12 * e, j, wire + 576 * (size_t)e) && ok;
+    return ok ? 0 : -1;
+}
+void hm_wire_to_pod_fp12(const uint8_t* wire, uint32_t n, uint8_t* pods)
+{
+    for (uint32_t e = 0; e < n; ++e)
+        for (uint32_t j = 0; j < 12; ++j) wire_to_pod_fp12_coeff(wire + 576 * (size_t)e, j, pods + (size_t)POD_FP12 * e);
+}
+uint32_t hm_choose_window(uint64_t n) { return msm_choose_window(n); }
+// auto plan (what the device entry uses): window from msm_choose_window, segments from msm_make_plan
+int hm_g1_msm_auto(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint8_t* out49)
+{
+    MsmPlan pl = msm_make_plan(n ? n : 1, c ? c : msm_choose_window(n));
+    return msm<Fp>(p, s, n, pl.c, pl.seg_len, out49);
 }
 }

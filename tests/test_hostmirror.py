@@ -1,0 +1,124 @@
+"""CPU: the product's kernel BODIES (crypto12381_b200/csrc/*.cuh compiled for the host by tests/hostmirror) against
+the golden vectors of the reference.  What this cannot cover — the inline-PTX field primitives (emulated
+instruction by instruction in tools/gen_fp_ptx.py), the radix-sort kernels and the launch plumbing — is covered by
+the `-m gpu` tests through the C ABI."""
+import ctypes
+import random
+import subprocess
+import sys
+import os
+
+import pytest
+
+import hostmirror_lib as hm
+import parity_suite as ps
+from conftest import chunks
+from oracle import ref
+
+P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+
+
+class MirrorBackend:
+    fixed_base1 = staticmethod(hm.g1_fixed_base)
+    fixed_base2 = staticmethod(hm.g2_fixed_base)
+    mul1 = staticmethod(hm.g1_mul)
+    mul2 = staticmethod(hm.g2_mul)
+    final_exp = staticmethod(hm.final_exp)
+    gt_mul = staticmethod(hm.gt_mul)
+    gt_pow = staticmethod(hm.gt_pow)
+
+    @staticmethod
+    def msm1(points, scalars, c=0):
+        n = len(scalars) // 32
+        out = ctypes.create_string_buffer(49)
+        assert hm.lib().hm_g1_msm_auto(points, scalars, n, c, out) == 0
+        return out.raw
+
+    @staticmethod
+    def msm2(points, scalars, c=0):
+        return hm.g2_msm(points, scalars, c or max(4, hm.lib().hm_choose_window(len(scalars) // 32)))
+
+    @staticmethod
+    def miller(g1, g2, k):
+        return hm.pairing_product(g1, g2, k, 0)
+
+    @staticmethod
+    def product(g1, g2, k):
+        return hm.pairing_product(g1, g2, k, 1)
+
+
+def test_ptx_generator_emulation():
+    """The inline-PTX Fp primitives, instruction list emulated against big-integer arithmetic."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_fp_ptx.py"), "--check-only"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    assert "emulation OK" in out.stdout
+
+
+def test_fp_ops():
+    rnd = random.Random(7)
+    vals = [0, 1, 2, P - 1, P - 2, (P + 1) // 2] + [rnd.randrange(P) for _ in range(40)]
+    b48 = lambda v: v.to_bytes(48, "big")
+    for a in vals:
+        b = rnd.choice(vals)
+        assert hm.fp_op(0, b48(a), b48(b)) == b48(a * b % P)
+        assert hm.fp_op(1, b48(a), b48(b)) == b48((a + b) % P)
+        assert hm.fp_op(2, b48(a), b48(b)) == b48((a - b) % P)
+        assert hm.fp_op(4, b48(a)) == b48(-a % P)
+        assert hm.fp_op(3, b48(a)) == b48(pow(a, P - 2, P))
+        s = int.from_bytes(hm.fp_op(5, b48(a * a % P)), "big")
+        assert s in (a, P - a)
+
+
+def test_points_golden():
+    ps.check_points(MirrorBackend)
+
+
+def test_msm_golden():
+    ps.check_msm(MirrorBackend, max_n=300, windows=(0, 2, 5, 8))
+
+
+def test_msm_1024_auto_window():
+    ps.check_msm(MirrorBackend, windows=(0,))
+
+
+def test_window_choice():
+    l = hm.lib()
+    assert [l.hm_choose_window(n) for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24)] == sorted(
+        l.hm_choose_window(n) for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24))
+    assert l.hm_choose_window(1 << 20) == 16 and 4 <= l.hm_choose_window(1) <= 8
+
+
+def test_pairing_golden():
+    ps.check_pairing(MirrorBackend)
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+def test_pod_conversions_against_reference_structs():
+    """MIRACL structs (R = 2^406 residues, 58-bit digits, lazily reduced) <-> wire formats."""
+    l = hm.lib()
+    sc = ref.random_scalars("pod conversion seed", 6)
+    a1, a2 = ref.g1_fixed_base_mul(sc), ref.g2_fixed_base_mul(sc)
+    a1 += bytes(96)
+    a2 += bytes(192)
+    for unnorm in (False, True):
+        p1, p2 = ref.make_point1(a1, unnorm), ref.make_point2(a2, unnorm)
+        w1, w2 = ctypes.create_string_buffer(96 * 7), ctypes.create_string_buffer(192 * 7)
+        assert l.hm_pod_points_to_wire(0, p1, 7, w1) == 0 and w1.raw == a1
+        assert l.hm_pod_points_to_wire(1, p2, 7, w2) == 0 and w2.raw == a2
+    # and back: the structs we write are accepted by the reference and mean the same points
+    q1, q2 = ctypes.create_string_buffer(192 * 7), ctypes.create_string_buffer(384 * 7)
+    assert l.hm_wire_to_pod_points(0, a1, 7, q1) == 0 and l.hm_wire_to_pod_points(1, a2, 7, q2) == 0
+    assert ref.point1_to_c49(q1, 6) == ref.g1_compress(a1[:96 * 6])
+    assert ref.point2_to_c97(q2, 6) == ref.g2_compress(a2[:192 * 6])
+    bigs = ref.make_big(sc)
+    s32 = ctypes.create_string_buffer(32 * 6)
+    assert l.hm_pod_bigs_to_scalars(bigs, 6, s32) == 0 and s32.raw == sc
+    # fp12: wire -> struct -> reference serialiser, and struct -> wire
+    gt = ref.pairing_product_batch(a1[:96 * 2], a2[:192 * 2], 1, 1)
+    pods = ctypes.create_string_buffer(776 * 2)
+    l.hm_wire_to_pod_fp12(gt, 2, pods)
+    assert ref.fp12_to_bytes(pods, 2) == gt
+    back = ctypes.create_string_buffer(576 * 2)
+    assert l.hm_pod_fp12_to_wire(pods, 2, back) == 0 and back.raw == gt
