@@ -92,5 +92,5 @@ using namespace c12;
 extern "C" int c12381_sync_status(void* stream)
 {
     C12_REQUIRE_CTX();
-    return flags_collect(stream ? (cudaStream_t)stream : ctx().stream);
+    return flags_collect((cudaStream_t)stream);
 }

@@ -309,7 +309,9 @@ int with_staged(const void* const* host_in, const size_t* in_bytes, int n_in, vo
 // ---- entry-point bodies shared by the G1 and G2 translation units --------------------------------------------
 namespace c12 {
 
-static inline cudaStream_t pick_stream(void* stream) { return stream ? (cudaStream_t)stream : ctx().stream; }
+// `_dev` entries run on exactly the stream they are given; NULL is CUDA's default stream (what torch uses unless
+// told otherwise), NOT the context's private stream — the caller's other work on that stream stays ordered with ours.
+static inline cudaStream_t pick_stream(void* stream) { return (cudaStream_t)stream; }
 
 template <class F> int entry_msm_dev(const uint8_t* d_points, const uint8_t* d_scalars, size_t n, uint8_t* d_out, int out_mode, void* stream)
 {

@@ -6,8 +6,9 @@
  * Conventions
  *   - every function returns 0 on success, a negative C12381_E* code otherwise; nothing throws; the caller owns
  *     every buffer; there is NO CPU fallback: without a CUDA device every compute entry returns C12381_ENODEV.
- *   - "host" entries take host pointers and include the host<->device copies; "_dev" entries take device
- *     pointers plus a cudaStream_t (passed as void*) and enqueue work only.
+ *   - "host" entries take host pointers and include the host<->device copies (on the context's own stream, and
+ *     return when the result is in the caller's buffer); "_dev" entries take device pointers plus a cudaStream_t
+ *     (passed as void*; NULL = CUDA's default stream) and enqueue work on exactly that stream.
  *   - canonical byte formats (the reference's own wire formats):
  *       scalar      32 B big-endian integer in [0, r)
  *       G1 affine   96 B  = x || y, 48 B big-endian each; identity = 96 zero bytes
@@ -51,7 +52,7 @@ C12381_API void c12381_shutdown(void);
 C12381_API const char* c12381_last_error(void);
 C12381_API int c12381_device(void);              /* bound device or -1 */
 /* The "_dev" entries only enqueue work, so malformed input (C12381_EINPUT) cannot be reported by their return value:
- * this call synchronises `stream` (NULL = the context stream) and returns C12381_EINPUT if any kernel enqueued since
+ * this call synchronises `stream` (NULL = the default stream) and returns C12381_EINPUT if any kernel enqueued since
  * the last check flagged a non-canonical coordinate, an off-curve point or a scalar >= r (then clears the flag).
  * The host-pointer entries do this themselves.  The reference reports parse failures the same way: by status
  * (from_bytes returns 0, src/miracl_core_interface.cpp:109-112), never by a different result. */
