@@ -17,7 +17,7 @@ def main(obj, out):
             continue
         sym = parts[2]
         dem = subprocess.run(["c++filt", sym], capture_output=True, text=True, check=True).stdout.strip()
-        name = dem.split("miracl_core::")[-1]
+        name = dem.split("miracl_core::", 1)[1]
         hot = name.startswith(HOT_PREFIXES)
         if name.startswith("multiply("):
             first = name[len("multiply("):].split(",")[0]
