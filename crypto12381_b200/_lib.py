@@ -8,7 +8,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libc12381_cuda.so")
+_VARIANT = os.environ.get("C12381_LIB_VARIANT", "")   # experimental twin builds (crypto12381_b200/build.py), measurements only
+LIB_PATH = os.path.join(HERE, f"libc12381_cuda_{_VARIANT}.so" if _VARIANT else "libc12381_cuda.so")
 
 OK, ENODEV, ECUDA, EINPUT, EARG = 0, -1, -2, -3, -4
 MAX_PAIRS = 8

@@ -61,20 +61,35 @@ def _compile(unit: str, digest: str, force: bool) -> bool:
     return True
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
-    os.makedirs(OBJ, exist_ok=True)
-    digest = _headers_digest()
-    with concurrent.futures.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
-        rebuilt = list(ex.map(lambda u: _compile(u, digest, force), UNITS))
-    if any(rebuilt) or not os.path.exists(LIB):
-        objs = [os.path.join(OBJ, u + ".o") for u in UNITS]
-        subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs, check=True, timeout=600)
-        if verbose:
-            print(f"built {LIB} ({sum(rebuilt)} unit(s) recompiled)")
-    elif verbose:
-        print(f"{LIB} is up to date")
-    return LIB
+def build(force: bool = False, verbose: bool = True, variant: str = "", defines=()) -> str:
+    """variant/defines: build an experimental twin `libc12381_cuda_<variant>.so` with extra -D flags (A/B measurements;
+    selected at load time with the environment variable C12381_LIB_VARIANT)."""
+    global OBJ, NVCC_FLAGS
+    lib = LIB if not variant else LIB.replace(".so", f"_{variant}.so")
+    obj_dir, flags = OBJ, NVCC_FLAGS
+    if variant:
+        OBJ = os.path.join(CSRC, "_obj_" + variant)
+        NVCC_FLAGS = NVCC_FLAGS + [f"-D{d}" for d in defines]
+    try:
+        os.makedirs(OBJ, exist_ok=True)
+        digest = _headers_digest()
+        with concurrent.futures.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
+            rebuilt = list(ex.map(lambda u: _compile(u, digest, force), UNITS))
+        if any(rebuilt) or not os.path.exists(lib):
+            objs = [os.path.join(OBJ, u + ".o") for u in UNITS]
+            subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib] + objs, check=True, timeout=600)
+            if verbose:
+                print(f"built {lib} ({sum(rebuilt)} unit(s) recompiled)")
+        elif verbose:
+            print(f"{lib} is up to date")
+    finally:
+        OBJ, NVCC_FLAGS = obj_dir, flags
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        build(force="--force" in sys.argv, variant=sys.argv[i + 1], defines=sys.argv[i + 2].split(","))
+    else:
+        build(force="--force" in sys.argv)

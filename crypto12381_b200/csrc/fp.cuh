@@ -90,10 +90,31 @@ inline void mont_mul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t 
 } // namespace host
 #endif
 
+// Build-time variant C12_FP_CALL: the Montgomery product / squaring are REAL calls (operands and result travel in
+// registers: the ABI passes these 48-byte structs by value without touching local memory), which divides the SASS
+// footprint of every kernel by ~10 at the price of ~36 register moves per product and no scheduling across
+// products.  Used to measure instruction-cache pressure against straight-line code (profiles/).
+#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
+__device__ __noinline__ Fp fp_mul_call(Fp a, Fp b)
+{
+    Fp r;
+    fp_mul_ptx(r.v, a.v, b.v);
+    return r;
+}
+__device__ __noinline__ Fp fp_sqr_call(Fp a)
+{
+    Fp r;
+    fp_sqr_ptx(r.v, a.v);
+    return r;
+}
+#endif
+
 C12_HD Fp fp_mul(const Fp& a, const Fp& b)
 {
     Fp r;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
+    r = fp_mul_call(a, b);
+#elif defined(__CUDA_ARCH__)
     fp_mul_ptx(r.v, a.v, b.v);
 #else
     host::mont_mul(r.v, a.v, b.v);
@@ -104,7 +125,9 @@ C12_HD Fp fp_mul(const Fp& a, const Fp& b)
 C12_HD Fp fp_sqr(const Fp& a)
 {
     Fp r;
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
+    r = fp_sqr_call(a);
+#elif defined(__CUDA_ARCH__)
     fp_sqr_ptx(r.v, a.v);
 #else
     host::mont_mul(r.v, a.v, a.v);
@@ -232,31 +255,96 @@ C12_HD Fp fp_one() { return fp_one_m(); }
 C12_HD Fp fp_to_mont(const Fp& a) { return fp_mul(fp_r2(), a); }  // a may be any 384-bit value (2nd operand)
 C12_HD Fp fp_from_mont(const Fp& a) { return fp_redc(a); }
 
-// a^(p-2) by a fixed 4-bit window over the bits of p-2 (Fermat).  Replaces FP_inv
-// (3rd-party/miracl-core/fp_BLS12381.cpp:817); inversions are amortised by Montgomery's trick wherever a
-// batch exists.  inv(0) = 0.
+// ---- inversion ---------------------------------------------------------------------------------------------
+// Binary extended Euclid on the plain 384-bit integers (Replaces FP_inv, 3rd-party/miracl-core/fp_BLS12381.cpp:817,
+// which is Fermat a^(p-2) through FP_progen).  About 2*381 shift/subtract steps of 12-limb add/sub instead of
+// ~480 Montgomery products: an order of magnitude fewer instructions, which matters most where ONE thread
+// normalises a final result (the serial tail of an MSM).  Not constant time — all inputs here are public.
+// inv(0) = 0.  Inversions are still amortised by Montgomery's trick wherever a batch exists.
+namespace detail {
+C12_HD bool limbs_is_one(const uint32_t (&a)[12])
+{
+    uint32_t z = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < 12; ++i) z |= a[i];
+    return z == 0;
+}
+C12_HD bool limbs_ge(const uint32_t (&a)[12], const uint32_t (&b)[12])
+{
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        uint64_t d = (uint64_t)a[i] - b[i] - borrow;
+        borrow = (d >> 32) & 1u;
+    }
+    return borrow == 0;
+}
+C12_HD void limbs_sub(uint32_t (&a)[12], const uint32_t (&b)[12])  // a -= b, a >= b
+{
+    uint64_t borrow = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        uint64_t d = (uint64_t)a[i] - b[i] - borrow;
+        a[i] = (uint32_t)d;
+        borrow = (d >> 32) & 1u;
+    }
+}
+// x = x / 2 mod p for x < p: (x even ? x : x + p) >> 1
+C12_HD void limbs_half_mod_p(uint32_t (&x)[12])
+{
+    const uint32_t pl[12] = C12_P_LIMBS;
+    const uint32_t mask = 0u - (x[0] & 1u);
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        uint64_t t = (uint64_t)x[i] + (pl[i] & mask) + c;
+        x[i] = (uint32_t)t;
+        c = t >> 32;
+    }
+#pragma unroll
+    for (int i = 0; i < 11; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[11] = (x[11] >> 1) | ((uint32_t)c << 31);
+}
+C12_HD void limbs_shr1(uint32_t (&x)[12])
+{
+#pragma unroll
+    for (int i = 0; i < 11; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+    x[11] >>= 1;
+}
+} // namespace detail
+
 C12_HD_NOINLINE Fp fp_inv(const Fp& a)
 {
-    const uint32_t e[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
-                            0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
-    Fp tab[16];
-    tab[0] = fp_one();
-    tab[1] = a;
+    if (fp_is_zero(a)) return fp_zero();
+    const uint32_t pl[12] = C12_P_LIMBS;
+    Fp u = a, v, x1 = fp_zero(), x2 = fp_zero();   // u = a R (as a plain integer), v = p
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v.v[i] = pl[i];
+    x1.v[0] = 1;
 #pragma unroll 1
-    for (int i = 2; i < 16; ++i) tab[i] = fp_mul(tab[i - 1], a);
-    Fp r = fp_one();
+    while (!detail::limbs_is_one(u.v) && !detail::limbs_is_one(v.v)) {
 #pragma unroll 1
-    for (int i = 95; i >= 0; --i) {
-        if (i != 95) {
-            r = fp_sqr(r);
-            r = fp_sqr(r);
-            r = fp_sqr(r);
-            r = fp_sqr(r);
+        while (!(u.v[0] & 1u)) {
+            detail::limbs_shr1(u.v);
+            detail::limbs_half_mod_p(x1.v);
         }
-        uint32_t d = (e[i >> 3] >> ((i & 7) * 4)) & 15u;
-        if (d) r = fp_mul(r, tab[d]);
+#pragma unroll 1
+        while (!(v.v[0] & 1u)) {
+            detail::limbs_shr1(v.v);
+            detail::limbs_half_mod_p(x2.v);
+        }
+        if (detail::limbs_ge(u.v, v.v)) {
+            detail::limbs_sub(u.v, v.v);
+            x1 = fp_sub(x1, x2);
+        } else {
+            detail::limbs_sub(v.v, u.v);
+            x2 = fp_sub(x2, x1);
+        }
     }
-    return r;
+    // (a R)^-1; times R^3 / R  ->  a^-1 R
+    const Fp r3 = {{0xd94ca1e0u, 0xed48ac6bu, 0x03a7adf8u, 0x315f831eu, 0x615e29ddu, 0x9a53352au, 0x921e1761u, 0x34c04e5eu, 0x65724728u,
+                    0x2512d435u, 0x91755d4du, 0x0aa63460u}};
+    return fp_mul(detail::limbs_is_one(u.v) ? x1 : x2, r3);
 }
 
 // a^((p+1)/4): the square root when a is a residue (p = 3 mod 4).  Replaces FP_sqrt

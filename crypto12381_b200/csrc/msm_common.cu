@@ -31,6 +31,41 @@ int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* star
     return C12381_OK;
 }
 
+__global__ void k_bucket_size_keys(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ ids)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    uint32_t sz = end[b] - start[b];
+    keys[b] = 255u - (sz > 255u ? 255u : sz);   // ascending key = descending size
+    ids[b] = b;
+}
+
+size_t bucket_order_scratch_words(const MsmPlan& pl)
+{
+    size_t tile_words = 0;
+    size_t hist = sort_scratch_words(pl.total, 1, &tile_words);
+    return 4 * (size_t)pl.total + hist + tile_words + 64;
+}
+
+int launch_bucket_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** order, cudaStream_t s)
+{
+    size_t tile_words = 0;
+    size_t hist_words = sort_scratch_words(pl.total, 1, &tile_words);
+    uint32_t* keys = scratch;
+    uint32_t* ids = keys + pl.total;
+    uint32_t* keys2 = ids + pl.total;
+    uint32_t* ids2 = keys2 + pl.total;
+    uint32_t* hist = ids2 + pl.total;
+    uint32_t* tiles = hist + hist_words;
+    k_bucket_size_keys<<<cdiv(pl.total, 256), 256, 0, s>>>(pl.total, start, end, keys, ids);
+    C12_LAUNCHED();
+    int rc = sort_pairs_segmented(keys, ids, keys2, ids2, pl.total, 1, 8, hist, tiles, s);
+    if (rc) return rc;
+    *order = ids;
+    return C12381_OK;
+}
+
 size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words)
 {
     size_t nblk = cdiv(n, SORT_TILE);

@@ -68,14 +68,20 @@ __global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict_
 // defined once in msm_common.cu (kernels there are launched through these host functions)
 int launch_recode(const MsmPlan& pl, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s);
 int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s);
+// order[] = bucket ids sorted by decreasing size (one 8-bit radix pass on min(size, 255)); scratch: 4 * total + hist words
+int launch_bucket_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** order, cudaStream_t s);
+size_t bucket_order_scratch_words(const MsmPlan& pl);
 
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
                                                     const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
-                                                    Proj<F>* __restrict__ buckets)
+                                                    const uint32_t* __restrict__ order, Proj<F>* __restrict__ buckets)
 {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total) return;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    // buckets are visited in order of decreasing size (launch_bucket_order), so the 32 lanes of a warp run loops of
+    // (nearly) equal length and the heaviest buckets start first
+    uint32_t b = order[t];
     buckets[b] = msm_accumulate_body<F>(b, start, end, vals, pts);
 }
 
@@ -165,6 +171,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
     b += 4 * align_up(4 * N);
     b += align_up(4 * hist_words) + align_up(4 * tile_words);
     b += 2 * align_up(4 * (size_t)pl.total);
+    b += align_up(4 * bucket_order_scratch_words(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.windows);
@@ -211,6 +218,7 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
     uint32_t* tiles = (uint32_t*)arena_take(4 * tile_words);
     uint32_t* start = (uint32_t*)arena_take(4 * (size_t)pl.total);
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)pl.total);
+    uint32_t* order_scratch = (uint32_t*)arena_take(4 * bucket_order_scratch_words(pl));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
     Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
     Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows);
@@ -225,8 +233,11 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
     if (rc) return rc;
     rc = launch_bucket_bounds(pl, keys, start, end, s);
     if (rc) return rc;
+    uint32_t* order = nullptr;
+    rc = launch_bucket_order(pl, start, end, order_scratch, &order, s);
+    if (rc) return rc;
     C12_CUDA(cudaEventRecord(c.ev[1], s));
-    k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, buckets);
+    k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, buckets);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     k_reduce1<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);

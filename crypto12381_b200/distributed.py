@@ -36,13 +36,22 @@ def sharded_msm(points, scalars, point_bytes: int, partial_fn: Callable, sum_fn:
     return sum_fn(gathered)
 
 
+def _single(group) -> bool:
+    import torch.distributed as dist
+    return not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1
+
+
 def g1_msm_sharded(points, scalars, group=None):
     from . import device
+    if _single(group):   # nothing to merge: one pipeline, one normalisation
+        return device.g1_msm(points, scalars)
     return sharded_msm(points, scalars, device.G1_AFFINE, device.g1_msm_partial, device.g1_sum, group)
 
 
 def g2_msm_sharded(points, scalars, group=None):
     from . import device
+    if _single(group):
+        return device.g2_msm(points, scalars)
     return sharded_msm(points, scalars, device.G2_AFFINE, device.g2_msm_partial, device.g2_sum, group)
 
 
