@@ -23,7 +23,9 @@
 namespace c12 {
 
 struct MsmPlan {
-    uint32_t n;           // terms
+    uint32_t n;           // terms fed to the bucket pipeline (2 * n_in when the GLV split is on)
+    uint32_t n_in;        // caller's terms
+    uint32_t glv;         // 1: every scalar was split into two ~127-bit halves (G1), windows cover 128 bits
     uint32_t c;           // window bits
     uint32_t windows;     // W
     uint32_t half;        // 2^(c-1) buckets per window
@@ -32,15 +34,16 @@ struct MsmPlan {
     uint32_t segs;        // segments per window = ceil(half / seg_len)
 };
 
-// Window width for n terms: minimises  W * (10 n + 45 * 2^(c-1))  Fp products (10 per mixed bucket addition,
-// ~45 per bucket for the two-level reduction), c in [4, 16] so window-local keys always fit two 8-bit radix
-// passes.  W c >= 256 and scalars < r < 2^255 guarantee the signed recoding never carries out of the top window.
-inline uint32_t msm_choose_window(uint64_t n)
+// Window width for n terms of `bits`-bit scalars: minimises  W * (10 n + 45 * 2^(c-1))  Fp products (10 per mixed
+// bucket addition, ~45 per bucket for the two-level reduction), c in [4, 16] so window-local keys always fit two
+// 8-bit radix passes.  W c >= bits and magnitudes < 2^(bits-1) guarantee the signed recoding never carries out of
+// the top window (scalars < r < 2^255; GLV halves < 2^127).
+inline uint32_t msm_choose_window(uint64_t n, uint32_t bits = 256)
 {
     uint32_t best = 4;
     double best_cost = 1e300;
     for (uint32_t c = 4; c <= 16; ++c) {
-        double W = (double)((256 + c - 1) / c);
+        double W = (double)((bits + c - 1) / c);
         double cost = W * (10.0 * (double)n + 45.0 * (double)(1u << (c - 1)));
         if (cost < best_cost) {
             best_cost = cost;
@@ -50,12 +53,15 @@ inline uint32_t msm_choose_window(uint64_t n)
     return best;
 }
 
-inline MsmPlan msm_make_plan(uint32_t n, uint32_t c)
+// n_in caller terms; glv = true doubles the term count and halves the scalar width
+inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, bool glv = false)
 {
     MsmPlan pl;
-    pl.n = n;
+    pl.n_in = n_in;
+    pl.glv = glv ? 1u : 0u;
+    pl.n = glv ? 2 * n_in : n_in;
     pl.c = c;
-    pl.windows = (256 + c - 1) / c;
+    pl.windows = ((glv ? 128u : 256u) + c - 1) / c;
     pl.half = 1u << (c - 1);
     pl.total = pl.windows * pl.half;
     // reduce-1 segment length: aim for >= 64 Ki threads, between 4 and 64 buckets per thread
@@ -97,11 +103,182 @@ C12_HD uint32_t scalar_bits(const Scalar256& s, uint32_t pos, uint32_t c)
     return (uint32_t)(x & ((1ull << c) - 1ull));
 }
 
+// same on an L-limb magnitude
+template <int L> C12_HD uint32_t limbs_bits(const uint32_t (&v)[L], uint32_t pos, uint32_t c)
+{
+    uint32_t limb = pos >> 5, off = pos & 31u;
+    if (limb >= (uint32_t)L) return 0;
+    uint64_t lo = v[limb];
+    uint64_t hi = (limb + 1 < (uint32_t)L) ? v[limb + 1] : 0;
+    uint64_t x = (lo | (hi << 32)) >> off;
+    return (uint32_t)(x & ((1ull << c) - 1ull));
+}
+
+// ---- GLV split for G1 (replaces MIRACL's glv(), 3rd-party/miracl-core/pair_BLS12381.cpp:759-810) -----------------
+// mu = x^2 (128 bits) acts on G1 as  mu * (X, Y) = (beta X, -Y)  with beta = CRu (rom_field_BLS12381.cpp:58), and
+// mu^2 = mu - 1 (mod r) because r = x^4 - x^2 + 1.  k = k0 + k1 mu is rebalanced to |k0|, |k1| <= mu/2 + 1 < 2^127:
+//   k0 > mu/2:  k0 -= mu, k1 += 1;      k1 > mu/2:  k1 -= mu - 1, k0 -= 1      (second step uses mu^2 = mu - 1)
+// so that eight 16-bit signed windows cover each half with no carry out of the top window.
+struct GlvHalves {
+    uint32_t a0[4], a1[4];   // magnitudes
+    uint32_t neg0, neg1;     // signs
+};
+
+namespace detail {
+C12_HD bool u128_gt(const uint32_t (&a)[4], const uint32_t (&b)[4])
+{
+    for (int i = 3; i >= 0; --i)
+        if (a[i] != b[i]) return a[i] > b[i];
+    return false;
+}
+C12_HD void u128_sub(uint32_t (&r)[4], const uint32_t (&a)[4], const uint32_t (&b)[4])  // a >= b
+{
+    uint64_t borrow = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t d = (uint64_t)a[i] - b[i] - borrow;
+        r[i] = (uint32_t)d;
+        borrow = (d >> 32) & 1u;
+    }
+}
+C12_HD void u128_inc(uint32_t (&a)[4])
+{
+    for (int i = 0; i < 4; ++i)
+        if (++a[i] != 0) return;
+}
+C12_HD void u128_dec(uint32_t (&a)[4])  // a > 0
+{
+    for (int i = 0; i < 4; ++i)
+        if (a[i]-- != 0) return;
+}
+C12_HD bool u128_is_zero(const uint32_t (&a)[4]) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
+} // namespace detail
+
+C12_HD GlvHalves glv_split(const Scalar256& k)
+{
+    const uint32_t mu[4] = C12_X2_LIMBS, rc[5] = C12_X2_RECIP_LIMBS;
+    // q = floor(k * floor(2^256 / mu) / 2^256)  (<= floor(k / mu), short by at most 2)
+    uint32_t prod[13];
+    for (int i = 0; i < 13; ++i) prod[i] = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 5; ++j) {
+            uint64_t t = (uint64_t)k.v[i] * rc[j] + prod[i + j] + carry;
+            prod[i + j] = (uint32_t)t;
+            carry = t >> 32;
+        }
+        prod[i + 5] = (uint32_t)carry;
+    }
+    uint32_t q[5];
+    for (int i = 0; i < 5; ++i) q[i] = prod[8 + i];
+    // rem = k - q * mu  (fits 5 limbs: < 3 mu)
+    uint32_t t[9];
+    for (int i = 0; i < 9; ++i) t[i] = 0;
+    for (int i = 0; i < 5; ++i) {
+        uint64_t carry = 0;
+        for (int j = 0; j < 4; ++j) {
+            uint64_t x = (uint64_t)q[i] * mu[j] + t[i + j] + carry;
+            t[i + j] = (uint32_t)x;
+            carry = x >> 32;
+        }
+        if (i + 4 < 9) t[i + 4] = (uint32_t)carry;
+    }
+    uint32_t rem[5];
+    {
+        uint64_t borrow = 0;
+        for (int i = 0; i < 5; ++i) {
+            uint64_t d = (uint64_t)k.v[i] - t[i] - borrow;
+            rem[i] = (uint32_t)d;
+            borrow = (d >> 32) & 1u;
+        }
+    }
+    for (int guard = 0; guard < 4; ++guard) {  // while rem >= mu
+        bool ge = rem[4] != 0;
+        if (!ge) {
+            uint32_t r4[4] = {rem[0], rem[1], rem[2], rem[3]};
+            ge = !detail::u128_gt(mu, r4);
+        }
+        if (!ge) break;
+        uint64_t borrow = 0;
+        for (int i = 0; i < 5; ++i) {
+            uint64_t d = (uint64_t)rem[i] - (i < 4 ? mu[i] : 0u) - borrow;
+            rem[i] = (uint32_t)d;
+            borrow = (d >> 32) & 1u;
+        }
+        for (int i = 0; i < 5; ++i)
+            if (++q[i] != 0) break;
+    }
+    GlvHalves h;
+    uint32_t half[4];  // mu / 2
+    for (int i = 0; i < 4; ++i) half[i] = (mu[i] >> 1) | (i < 3 ? (mu[i + 1] << 31) : 0u);
+    uint32_t k0[4] = {rem[0], rem[1], rem[2], rem[3]};
+    uint32_t k1[4] = {q[0], q[1], q[2], q[3]};   // q < mu: r / mu < mu
+    h.neg0 = 0;
+    if (detail::u128_gt(k0, half)) {
+        detail::u128_sub(k0, mu, k0);   // k0 - mu = -(mu - k0)
+        h.neg0 = 1;
+        detail::u128_inc(k1);
+    }
+    h.neg1 = 0;
+    if (detail::u128_gt(k1, half)) {
+        // k1 <- k1 - (mu - 1),  k0 <- k0 - 1
+        uint32_t m1[4] = {mu[0], mu[1], mu[2], mu[3]};
+        detail::u128_dec(m1);
+        if (detail::u128_gt(k1, m1)) {
+            detail::u128_sub(k1, k1, m1);
+        } else {
+            detail::u128_sub(k1, m1, k1);
+            h.neg1 = detail::u128_is_zero(k1) ? 0u : 1u;
+        }
+        if (h.neg0) {
+            detail::u128_inc(k0);
+        } else if (detail::u128_is_zero(k0)) {
+            k0[0] = 1;
+            h.neg0 = 1;
+        } else {
+            detail::u128_dec(k0);
+        }
+    }
+    for (int i = 0; i < 4; ++i) {
+        h.a0[i] = k0[i];
+        h.a1[i] = k1[i];
+    }
+    return h;
+}
+
 // Body of the recode kernel for term i: writes W (key, value) pairs at out index w * n + i.
 // The w-major layout keeps each window's entries in term order before the (stable) sort.
+// With the GLV split on, term i yields two pipeline terms: i (point P_i, half k0) and n_in + i (point mu*P_i, half k1).
 C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalars_be32, uint32_t* keys, uint32_t* vals)
 {
     Scalar256 s = scalar_from_be32(scalars_be32 + 32ull * i);
+    if (pl.glv) {
+        GlvHalves h = glv_split(s);
+        for (uint32_t part = 0; part < 2; ++part) {
+            const uint32_t(&mag)[4] = part ? h.a1 : h.a0;
+            const uint32_t sgn = part ? h.neg1 : h.neg0;
+            const uint32_t idx = i + part * pl.n_in;
+            uint32_t carry = 0;
+            for (uint32_t w = 0; w < pl.windows; ++w) {
+                uint32_t d = limbs_bits<4>(mag, w * pl.c, pl.c) + carry;
+                uint32_t neg = 0;
+                carry = 0;
+                if (d > pl.half) {
+                    d = (1u << pl.c) - d;
+                    neg = 1;
+                    carry = 1;
+                }
+                uint64_t o = (uint64_t)w * pl.n + idx;
+                if (d == 0) {
+                    keys[o] = msm_invalid_key(pl);
+                    vals[o] = idx;
+                } else {
+                    keys[o] = d - 1;
+                    vals[o] = idx | ((neg ^ sgn) << 31);
+                }
+            }
+        }
+        return;
+    }
     uint32_t carry = 0;
     for (uint32_t w = 0; w < pl.windows; ++w) {
         uint32_t d = scalar_bits(s, w * pl.c, pl.c) + carry;

@@ -54,8 +54,18 @@ template <class F> __device__ Proj<F> block_sum_256(Proj<F> acc)
     return acc;
 }
 
+// GLV (G1 only): the pipeline also needs mu * P = (beta X, -Y) for every input point (msm_core.cuh, glv_split)
+template <class F> struct MsmTraits {
+    static constexpr bool GLV = false;
+    static __device__ Affine<F> endo(const Affine<F>& p) { return p; }
+};
+template <> struct MsmTraits<Fp> {
+    static constexpr bool GLV = true;
+    static __device__ Affine<Fp> endo(const Affine<Fp>& p) { return Affine<Fp>{fp_mul(p.x, fp_beta_m()), fp_neg(p.y)}; }
+};
+
 template <class F>
-__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t n, Affine<F>* __restrict__ pts,
+__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t n, uint32_t glv, Affine<F>* __restrict__ pts,
                                                       int* flags)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,6 +73,7 @@ __global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict_
     Affine<F> p;
     if (!Wire<F>::parse(p, bytes + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
     pts[i] = p;
+    if (glv) pts[n + i] = MsmTraits<F>::endo(p);   // the identity (0, 0) maps to itself
 }
 
 // defined once in msm_common.cu (kernels there are launched through these host functions)
@@ -181,10 +192,11 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
 // scratch bound for an n-term MSM under the current window setting (callers arena_begin with at least this much)
 template <class F> size_t msm_scratch_for(size_t n)
 {
-    if (n == 0 || n > (1ull << 27)) return 0;
-    uint32_t cbits = ctx().forced_window ? (uint32_t)ctx().forced_window : msm_choose_window(n);
+    if (n == 0 || n > (1ull << 26)) return 0;
+    constexpr bool glv = MsmTraits<F>::GLV;
+    uint32_t cbits = ctx().forced_window ? (uint32_t)ctx().forced_window : msm_choose_window(glv ? 2 * n : n, glv ? 128 : 256);
     if (cbits < 2 || cbits > 16) return 0;
-    return msm_scratch_bytes<F>(msm_make_plan((uint32_t)n, cbits));
+    return msm_scratch_bytes<F>(msm_make_plan((uint32_t)n, cbits, glv));
 }
 
 // The caller has arena_begin()'d at least msm_scratch_for<F>(n) bytes beyond what it took itself.
@@ -199,17 +211,18 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
         C12_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, s));
         return C12381_OK;
     }
-    if (n_sz > (1ull << 27)) return set_error(C12381_EARG, "msm: n > 2^27 terms per call is not supported");
+    if (n_sz > (1ull << 26)) return set_error(C12381_EARG, "msm: n > 2^26 terms per call is not supported");
     const uint32_t n = (uint32_t)n_sz;
-    uint32_t cbits = c.forced_window ? (uint32_t)c.forced_window : msm_choose_window(n);
+    constexpr bool glv = MsmTraits<F>::GLV;
+    uint32_t cbits = c.forced_window ? (uint32_t)c.forced_window : msm_choose_window(glv ? 2 * (uint64_t)n : n, glv ? 128 : 256);
     if (cbits < 2 || cbits > 16) return set_error(C12381_EARG, "msm: window width must be in [2, 16]");
-    const MsmPlan pl = msm_make_plan(n, cbits);
-    const size_t N = (size_t)n * pl.windows;
+    const MsmPlan pl = msm_make_plan(n, cbits, glv);
+    const size_t N = (size_t)pl.n * pl.windows;
 
     int rc;
     size_t tile_words = 0;
-    size_t hist_words = sort_scratch_words(n, pl.windows, &tile_words);
-    Affine<F>* pts = (Affine<F>*)arena_take(sizeof(Affine<F>) * (size_t)n);
+    size_t hist_words = sort_scratch_words(pl.n, pl.windows, &tile_words);
+    Affine<F>* pts = (Affine<F>*)arena_take(sizeof(Affine<F>) * (size_t)pl.n);
     uint32_t* keys = (uint32_t*)arena_take(4 * N);
     uint32_t* vals = (uint32_t*)arena_take(4 * N);
     uint32_t* keys2 = (uint32_t*)arena_take(4 * N);
@@ -225,11 +238,11 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
     if (!wsum) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
-    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pts, c.d_flags);
+    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.glv, pts, c.d_flags);
     C12_LAUNCHED();
     rc = launch_recode(pl, d_scalars, keys, vals, c.d_flags, s);
     if (rc) return rc;
-    rc = sort_pairs_segmented(keys, vals, keys2, vals2, n, pl.windows, pl.c, hist, tiles, s);
+    rc = sort_pairs_segmented(keys, vals, keys2, vals2, pl.n, pl.windows, pl.c, hist, tiles, s);
     if (rc) return rc;
     rc = launch_bucket_bounds(pl, keys, start, end, s);
     if (rc) return rc;

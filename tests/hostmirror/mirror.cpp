@@ -15,33 +15,36 @@
 using namespace c12;
 
 namespace {
-MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len)
+MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, bool glv)
 {
-    MsmPlan pl;
-    pl.n = n;
-    pl.c = c;
-    pl.windows = (256 + c - 1) / c;
-    pl.half = 1u << (c - 1);
-    pl.total = pl.windows * pl.half;
-    pl.seg_len = seg_len;
-    pl.segs = (pl.half + seg_len - 1) / seg_len;
+    MsmPlan pl = msm_make_plan(n, c, glv);
+    if (seg_len) {
+        pl.seg_len = seg_len > pl.half ? pl.half : seg_len;
+        pl.segs = (pl.half + pl.seg_len - 1) / pl.seg_len;
+    }
     return pl;
 }
 
-template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n, uint32_t c, uint32_t seg_len, uint8_t* out)
+Affine<Fp> endo(const Affine<Fp>& p) { return Affine<Fp>{fp_mul(p.x, fp_beta_m()), fp_neg(p.y)}; }   // MsmTraits<Fp>::endo
+Affine<Fp2> endo(const Affine<Fp2>& p) { return p; }
+
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, bool glv = false)
 {
     using W = Wire<F>;
-    if (n == 0) {
+    if (n_in == 0) {
         W::compress(out, affine_inf<F>());
         return 0;
     }
-    MsmPlan pl = make_plan(n, c, seg_len);
+    MsmPlan pl = make_plan(n_in, c, seg_len, glv);
+    const uint32_t n = pl.n;
     std::vector<Affine<F>> P(n);
-    for (uint32_t i = 0; i < n; ++i)
+    for (uint32_t i = 0; i < n_in; ++i) {
         if (!W::parse(P[i], pts + (size_t)W::AFFINE * i)) return -1;
+        if (glv) P[n_in + i] = endo(P[i]);
+    }
     size_t N = (size_t)n * pl.windows;
     std::vector<uint32_t> keys(N), vals(N);
-    for (uint32_t i = 0; i < n; ++i) msm_recode_body(pl, i, sc, keys.data(), vals.data());
+    for (uint32_t i = 0; i < n_in; ++i) msm_recode_body(pl, i, sc, keys.data(), vals.data());
     // segmented stable sort: window w owns [w*n, (w+1)*n), keys are window-local (as the device sort does)
     std::vector<uint32_t> order(N);
     for (size_t i = 0; i < N; ++i) order[i] = (uint32_t)i;
@@ -172,10 +175,23 @@ void hm_wire_to_pod_fp12(const uint8_t* wire, uint32_t n, uint8_t* pods)
         for (uint32_t j = 0; j < 12; ++j) wire_to_pod_fp12_coeff(wire + 576 * (size_t)e, j, pods + (size_t)POD_FP12 * e);
 }
 uint32_t hm_choose_window(uint64_t n) { return msm_choose_window(n); }
+uint32_t hm_choose_window_glv(uint64_t n) { return msm_choose_window(2 * n, 128); }
+// k (32 B BE) -> |k0|, |k1| (16 B BE each) and signs, k = +-k0 +- k1 * x^2 (mod r)
+void hm_glv_split(const uint8_t* k32, uint8_t* a0, uint8_t* a1, uint32_t* signs)
+{
+    GlvHalves h = glv_split(scalar_from_be32(k32));
+    for (int i = 0; i < 4; ++i)
+        for (int b = 0; b < 4; ++b) {
+            a0[15 - (4 * i + b)] = (uint8_t)(h.a0[i] >> (8 * b));
+            a1[15 - (4 * i + b)] = (uint8_t)(h.a1[i] >> (8 * b));
+        }
+    signs[0] = h.neg0;
+    signs[1] = h.neg1;
+}
 // auto plan (what the device entry uses): window from msm_choose_window, segments from msm_make_plan
 int hm_g1_msm_auto(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint8_t* out49)
 {
-    MsmPlan pl = msm_make_plan(n ? n : 1, c ? c : msm_choose_window(n));
-    return msm<Fp>(p, s, n, pl.c, pl.seg_len, out49);
+    // exactly the device entry's plan: GLV split on, window from msm_choose_window(2n, 128)
+    return msm<Fp>(p, s, n, c ? c : msm_choose_window(2 * (uint64_t)n, 128), 0, out49, true);
 }
 }

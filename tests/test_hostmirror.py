@@ -88,6 +88,24 @@ def test_window_choice():
     assert [l.hm_choose_window(n) for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24)] == sorted(
         l.hm_choose_window(n) for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24))
     assert l.hm_choose_window(1 << 20) == 16 and 4 <= l.hm_choose_window(1) <= 8
+    assert l.hm_choose_window_glv(1 << 20) == 16
+
+
+def test_glv_split():
+    """k = +-k0 +- k1 x^2 (mod r), both halves below 2^127 (so 8 signed 16-bit windows never overflow)."""
+    l = hm.lib()
+    X2 = 0xD201000000010000 ** 2
+    rnd = random.Random(11)
+    edge = [0, 1, 2, ps.R - 1, ps.R - 2, X2, X2 - 1, X2 + 1, X2 // 2, X2 // 2 + 1, X2 // 2 - 1, X2 * (X2 // 2), X2 * (X2 // 2 + 1),
+            X2 * (X2 // 2) + X2 // 2 + 1, X2 * (X2 - 1), (X2 - 2) * X2 + X2 // 2 + 5, 1 << 127, (1 << 128) - 1, 1 << 254]
+    for k in edge + [rnd.randrange(ps.R) for _ in range(3000)]:
+        k %= ps.R
+        a0, a1 = ctypes.create_string_buffer(16), ctypes.create_string_buffer(16)
+        sg = (ctypes.c_uint32 * 2)()
+        l.hm_glv_split(k.to_bytes(32, "big"), a0, a1, sg)
+        k0, k1 = int.from_bytes(a0.raw, "big"), int.from_bytes(a1.raw, "big")
+        assert k0 < 1 << 127 and k1 < 1 << 127, hex(k)
+        assert ((-k0 if sg[0] else k0) + (-k1 if sg[1] else k1) * X2 - k) % ps.R == 0, hex(k)
 
 
 def test_pairing_golden():
