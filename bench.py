@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20)
-    ap.add_argument("--pairing-instances", type=int, default=1 << 14)
+    ap.add_argument("--pairing-instances", type=int, default=1 << 16)
     ap.add_argument("--cpu-sample-log-n", type=int, default=15)
     ap.add_argument("--no-secondary", action="store_true")
     return ap.parse_args()
@@ -245,11 +245,14 @@ def run_ours(args):
             hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        W = (256 + stats["window_bits"] - 1) // stats["window_bits"]
         passes = (stats["window_bits"] + 7) // 8
-        sort_ms = statistics.mean(tot_ms) - acc   # everything that is not accumulation (upper bound for the scatter phase)
-        roofline["hbm_phase"] = {"what": "recode + segmented radix sort (keys+indices)", "algorithmic_bytes": n * W * 8 * 2 * passes,
-                                 "upper_bound_ms": sort_ms, "peak_gbs": hbm, "peak_source": hbm_src}
+        ph = stats["phases_ms"]
+        sort_bytes = adds * 8 * 2 * passes      # (key, index) pairs read and written once per radix pass
+        roofline["phases_ms"] = ph
+        roofline["hbm_phase"] = {"what": "segmented radix sort of the (bucket key, term index) pairs: bucket scatter", "algorithmic_bytes": sort_bytes,
+                                 "ms": ph["sort"], "achieved_gbs": sort_bytes / (ph["sort"] * 1e-3) / 1e9 if ph["sort"] > 0 else None,
+                                 "peak_gbs": hbm, "frac": (sort_bytes / (ph["sort"] * 1e-3) / 1e9 / hbm) if ph["sort"] > 0 else None,
+                                 "peak_source": hbm_src, "radix_passes": passes}
         cpu = None
         try:
             from oracle import ref

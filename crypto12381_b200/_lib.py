@@ -68,6 +68,7 @@ SIGNATURES = {
     "c12381_launch_count": (ctypes.c_ulonglong, []),
     "c12381_last_msm_stats": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(_i)]),
+    "c12381_last_msm_phases": (_i, [ctypes.POINTER(ctypes.c_double)]),
 }
 
 

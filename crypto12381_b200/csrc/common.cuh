@@ -14,6 +14,7 @@ namespace c12 {
 
 struct MsmStats {
     double accumulate_ms = 0, total_ms = 0;
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // parse, recode, sort, bounds+order, accumulate, reduce1, reduce2, finish
     unsigned long long bucket_adds = 0;
     int window_bits = 0;
 };
@@ -33,6 +34,7 @@ struct Ctx {
     int forced_window = 0;
     MsmStats stats;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // MSM phase boundaries
 };
 
 Ctx& ctx();

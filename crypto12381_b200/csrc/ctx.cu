@@ -130,13 +130,13 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_fp(uint32_t* out, int i
     Fp c = fp_add(a, b), d = fp_sub(a, b);
     if (square) {
         for (int i = 0; i < iters; ++i) {
-            c = fp_sqr(c);
-            d = fp_sqr(d);
+            c = fp_sqr_inl(c);
+            d = fp_sqr_inl(d);
         }
     } else {
         for (int i = 0; i < iters; ++i) {
-            c = fp_mul(c, a);
-            d = fp_mul(d, b);
+            c = fp_mul_inl(c, a);
+            d = fp_mul_inl(d, b);
         }
     }
     uint32_t x = 0;
@@ -167,6 +167,7 @@ int c12381_init(int device)
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
     C12_CUDA(cudaMalloc(&c.d_flags, 64 * sizeof(int)));
     for (auto& ev : c.ev) C12_CUDA(cudaEventCreate(&ev));
+    for (auto& ev : c.pev) C12_CUDA(cudaEventCreate(&ev));
     c.device = device;
     c.launches = 0;
     return C12381_OK;
@@ -182,6 +183,8 @@ void c12381_shutdown(void)
     if (c.d_flags) cudaFree(c.d_flags);
     if (c.h_flags) cudaFreeHost(c.h_flags);
     for (auto& ev : c.ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c.pev)
         if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(c.stream);
     c = Ctx();
@@ -202,11 +205,25 @@ int c12381_last_msm_stats(double* accumulate_ms, double* total_ms, unsigned long
         C12_CUDA(cudaEventElapsedTime(&t, ctx().ev[0], ctx().ev[3]));
         s.accumulate_ms = a;
         s.total_ms = t;
+        for (int i = 0; i < 8; ++i) {
+            float p = 0;
+            C12_CUDA(cudaEventElapsedTime(&p, ctx().pev[i], ctx().pev[i + 1]));
+            s.phase_ms[i] = p;
+        }
     }
     if (accumulate_ms) *accumulate_ms = s.accumulate_ms;
     if (total_ms) *total_ms = s.total_ms;
     if (bucket_adds) *bucket_adds = s.bucket_adds;
     if (window_bits) *window_bits = s.window_bits;
+    return C12381_OK;
+}
+
+int c12381_last_msm_phases(double* phase_ms8)
+{
+    int rc = c12381_last_msm_stats(nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (!phase_ms8) return set_error(C12381_EARG, "last_msm_phases: null pointer");
+    for (int i = 0; i < 8; ++i) phase_ms8[i] = ctx().stats.phase_ms[i];
     return C12381_OK;
 }
 

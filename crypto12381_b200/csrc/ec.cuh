@@ -168,8 +168,8 @@ template <class F> C12_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q)
         acc.zzz = FieldOps<F>::one();
         return;
     }
-    F u2 = mul(q.x, acc.zz);
-    F s2 = mul(q.y, acc.zzz);
+    F u2 = mul_hot(q.x, acc.zz);
+    F s2 = mul_hot(q.y, acc.zzz);
     F pp = sub(u2, acc.x);
     F rr = sub(s2, acc.y);
     if (is_zero(pp)) {
@@ -179,14 +179,14 @@ template <class F> C12_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q)
             acc = xyzz_inf<F>();       // opposite points
         return;
     }
-    F p2 = sqr(pp);
-    F p3 = mul(pp, p2);
-    F qq = mul(acc.x, p2);
-    F x3 = sub(sub(sqr(rr), p3), dbl(qq));
-    acc.y = sub(mul(rr, sub(qq, x3)), mul(acc.y, p3));
+    F p2 = sqr_hot(pp);
+    F p3 = mul_hot(pp, p2);
+    F qq = mul_hot(acc.x, p2);
+    F x3 = sub(sub(sqr_hot(rr), p3), dbl(qq));
+    acc.y = sub(mul_hot(rr, sub(qq, x3)), mul_hot(acc.y, p3));
     acc.x = x3;
-    acc.zz = mul(acc.zz, p2);
-    acc.zzz = mul(acc.zzz, p3);
+    acc.zz = mul_hot(acc.zz, p2);
+    acc.zzz = mul_hot(acc.zzz, p3);
 }
 
 // XYZZ -> homogeneous projective: (X*ZZZ : Y*ZZ : ZZ*ZZZ)

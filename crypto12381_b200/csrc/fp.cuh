@@ -90,11 +90,14 @@ inline void mont_mul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t 
 } // namespace host
 #endif
 
-// Build-time variant C12_FP_CALL: the Montgomery product / squaring are REAL calls (operands and result travel in
-// registers: the ABI passes these 48-byte structs by value without touching local memory), which divides the SASS
-// footprint of every kernel by ~10 at the price of ~36 register moves per product and no scheduling across
-// products.  Used to measure instruction-cache pressure against straight-line code (profiles/).
-#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
+// On the device the Montgomery product / squaring are REAL calls by default (operands and result travel in
+// registers: the ABI passes these 48-byte structs by value without touching local memory).  That divides the SASS
+// footprint of every kernel by ~10 at the price of ~36 register moves per product; measured (profiles/r01c): the
+// instruction-cache misses of fully inlined tower / curve code cost more than the calls (pairings 1.19 M/s against
+// 0.91 M/s, MSM tail 5.2 ms against 6.0 ms).  The one loop where straight-line code wins - the bucket accumulation's
+// XYZZ addition - uses fp_mul_inl / fp_sqr_inl explicitly.  -DC12_FP_INLINE_ALL restores inlining everywhere (A/B).
+#if defined(__CUDA_ARCH__) && !defined(C12_FP_INLINE_ALL)
+#define C12_FP_CALL 1
 __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b)
 {
     Fp r;
@@ -109,30 +112,44 @@ __device__ __noinline__ Fp fp_sqr_call(Fp a)
 }
 #endif
 
-C12_HD Fp fp_mul(const Fp& a, const Fp& b)
+// always-inline product / squaring (hot loops only)
+C12_HD Fp fp_mul_inl(const Fp& a, const Fp& b)
 {
     Fp r;
-#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
-    r = fp_mul_call(a, b);
-#elif defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__)
     fp_mul_ptx(r.v, a.v, b.v);
 #else
     host::mont_mul(r.v, a.v, b.v);
 #endif
     return r;
 }
-
-C12_HD Fp fp_sqr(const Fp& a)
+C12_HD Fp fp_sqr_inl(const Fp& a)
 {
     Fp r;
-#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
-    r = fp_sqr_call(a);
-#elif defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__)
     fp_sqr_ptx(r.v, a.v);
 #else
     host::mont_mul(r.v, a.v, a.v);
 #endif
     return r;
+}
+
+C12_HD Fp fp_mul(const Fp& a, const Fp& b)
+{
+#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
+    return fp_mul_call(a, b);
+#else
+    return fp_mul_inl(a, b);
+#endif
+}
+
+C12_HD Fp fp_sqr(const Fp& a)
+{
+#if defined(__CUDA_ARCH__) && defined(C12_FP_CALL)
+    return fp_sqr_call(a);
+#else
+    return fp_sqr_inl(a);
+#endif
 }
 
 C12_HD Fp fp_add(const Fp& a, const Fp& b)

@@ -52,6 +52,12 @@ C12_HD_NOINLINE Fp2 sqr(const Fp2& x)
     return Fp2{t0, fp_dbl(t1)};
 }
 
+// products of the bucket-accumulation hot loop (ec.cuh xyzz_madd): straight-line code over Fp, the regular call over Fp2
+C12_HD Fp mul_hot(const Fp& a, const Fp& b) { return fp_mul_inl(a, b); }
+C12_HD Fp sqr_hot(const Fp& a) { return fp_sqr_inl(a); }
+C12_HD Fp2 mul_hot(const Fp2& x, const Fp2& y) { return mul(x, y); }
+C12_HD Fp2 sqr_hot(const Fp2& x) { return sqr(x); }
+
 C12_HD Fp2 mul_fp(const Fp2& x, const Fp& s) { return Fp2{fp_mul(x.a, s), fp_mul(x.b, s)}; }
 
 // x * (1+i): the non-residue of the tower (QNRI = 0)

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) k_accumulate(uint32_t total, const uint32
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) k_reduce1(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ partial)
+__global__ void __launch_bounds__(128, 3) k_reduce1(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ partial)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= pl.segs) return;
@@ -105,14 +105,81 @@ __global__ void __launch_bounds__(128) k_reduce1(MsmPlan pl, const Proj<F>* __re
     partial[(size_t)w * pl.segs + t] = msm_reduce1_body<F>(pl, w, t, buckets);
 }
 
+// ---- lane-cooperative point arithmetic (the serial tail of an MSM) -------------------------------------------------
+// One thread's dependent chain of Montgomery products is latency-bound (~0.5 us per product), and the Horner
+// combination of the window sums is c (W - 1) sequential doublings.  The RCB formulas have two layers of independent
+// products (4 + 4 for a doubling, 6 + 6 for an addition): lane i of the warp computes the i-th product of a layer and
+// the results are broadcast back with shuffles, so a doubling costs two product latencies instead of eight.
+// Every lane holds the same point before and after each call (all 32 lanes must call these together).
+template <class T> __device__ __forceinline__ T shfl_bcast_obj(const T& x, int src)
+{
+    static_assert(sizeof(T) % 4 == 0, "word-sized objects only");
+    T r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&x);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) d[i] = __shfl_sync(0xffffffffu, s[i], src);
+    return r;
+}
+
+// out[i] = a[i] * b[i], product i computed by lane i
+template <class F, int N> __device__ __forceinline__ void coop_mul(F (&out)[N], const F (&a)[N], const F (&b)[N])
+{
+    const int lane = threadIdx.x & 31;
+    F x = a[0], y = b[0];
+#pragma unroll
+    for (int i = 1; i < N; ++i) {
+        x = select(lane == i, a[i], x);
+        y = select(lane == i, b[i], y);
+    }
+    F m = mul(x, y);
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = shfl_bcast_obj(m, i);
+}
+
+// proj_dbl (RCB15 Algorithm 9), same value
+template <class F> __device__ Proj<F> coop_dbl(const Proj<F>& p)
+{
+    F a1[4] = {p.y, p.y, p.z, p.x}, b1[4] = {p.y, p.z, p.z, p.y}, m[4];
+    coop_mul<F, 4>(m, a1, b1);                      // t0 = Y^2, t1 = YZ, t2 = Z^2, XY
+    F z3 = mul8(m[0]);
+    F t2 = FieldOps<F>::mul_b3(m[2]);
+    F y3 = add(m[0], t2);
+    F t0 = sub(m[0], mul3(t2));
+    F a2[4] = {t2, z3, y3, t0}, b2[4] = {z3, m[1], t0, m[3]}, n[4];
+    coop_mul<F, 4>(n, a2, b2);                      // x3, Z3, y3 t0, t0 XY
+    return Proj<F>{dbl(n[3]), add(n[2], n[0]), n[1]};
+}
+
+// proj_add (RCB15 Algorithm 7), same value
+template <class F> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& q)
+{
+    F a1[6] = {p.x, p.y, p.z, add(p.x, p.y), add(p.y, p.z), add(p.x, p.z)};
+    F b1[6] = {q.x, q.y, q.z, add(q.x, q.y), add(q.y, q.z), add(q.x, q.z)}, m[6];
+    coop_mul<F, 6>(m, a1, b1);
+    F t3 = sub(m[3], add(m[0], m[1]));
+    F t4 = sub(m[4], add(m[1], m[2]));
+    F y3 = FieldOps<F>::mul_b3(sub(m[5], add(m[0], m[2])));
+    F t0 = mul3(m[0]);
+    F t2 = FieldOps<F>::mul_b3(m[2]);
+    F z3 = add(m[1], t2);
+    F t1 = sub(m[1], t2);
+    F a2[6] = {y3, t3, y3, t1, t0, z3}, b2[6] = {t4, t1, t0, z3, t3, t4}, n[6];
+    coop_mul<F, 6>(n, a2, b2);
+    return Proj<F>{sub(n[1], n[0]), add(n[2], n[3]), add(n[5], n[4])};
+}
+
+constexpr int REDUCE2_SPLIT = 8;   // blocks per window in reduce-2 (their partials are merged by k_finish)
+
 template <class F>
-__global__ void __launch_bounds__(256) k_reduce2(MsmPlan pl, const Proj<F>* __restrict__ partial, Proj<F>* __restrict__ wsum)
+__global__ void __launch_bounds__(256) k_reduce2(MsmPlan pl, const Proj<F>* __restrict__ partial, Proj<F>* __restrict__ wpart)
 {
     uint32_t w = blockIdx.x;
     Proj<F> acc = proj_inf<F>();
-    for (uint32_t t = threadIdx.x; t < pl.segs; t += 256) acc = proj_add(acc, partial[(size_t)w * pl.segs + t]);
+    for (uint32_t t = blockIdx.y * 256 + threadIdx.x; t < pl.segs; t += 256 * REDUCE2_SPLIT)
+        acc = proj_add(acc, partial[(size_t)w * pl.segs + t]);
     acc = block_sum_256(acc);
-    if (threadIdx.x == 0) wsum[w] = acc;
+    if (threadIdx.x == 0) wpart[(size_t)w * REDUCE2_SPLIT + blockIdx.y] = acc;
 }
 
 template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, int out_mode)
@@ -124,10 +191,32 @@ template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, i
         Wire<F>::compress(out, a);
 }
 
-template <class F> __global__ void k_finish(MsmPlan pl, const Proj<F>* __restrict__ wsum, uint8_t* out, int out_mode)
+// One block of 8 warps: warp v merges the REDUCE2_SPLIT partials of windows v, v + 8, ... (shuffle tree), then warp 0
+// runs the Horner combination  acc = 2^c acc + S_w  with lane-cooperative doublings, normalises and encodes.
+template <class F> __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __restrict__ wpart, uint8_t* out, int out_mode)
 {
-    if (threadIdx.x || blockIdx.x) return;
-    write_point<F>(out, msm_horner_body<F>(pl, wsum), out_mode);
+    extern __shared__ __align__(16) unsigned char finish_smem[];
+    Proj<F>* wsum = reinterpret_cast<Proj<F>*>(finish_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t w = warp; w < pl.windows; w += 8) {
+        Proj<F> acc = lane < REDUCE2_SPLIT ? wpart[(size_t)w * REDUCE2_SPLIT + lane] : proj_inf<F>();
+#pragma unroll 1
+        for (int off = REDUCE2_SPLIT / 2; off >= 1; off >>= 1) {
+            Proj<F> o = shfl_down_obj(acc, off);
+            acc = proj_add(acc, o);
+        }
+        if (lane == 0) wsum[w] = acc;
+    }
+    __syncthreads();
+    if (warp) return;
+    Proj<F> acc = wsum[pl.windows - 1];
+#pragma unroll 1
+    for (uint32_t w = pl.windows - 1; w > 0; --w) {
+#pragma unroll 1
+        for (uint32_t k = 0; k < pl.c; ++k) acc = coop_dbl(acc);
+        acc = coop_add(acc, wsum[w - 1]);
+    }
+    if (lane == 0) write_point<F>(out, acc, out_mode);
 }
 
 // sum of n wire-format points (merging all-gathered per-rank partials; also a general point-sum entry)
@@ -185,7 +274,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
     b += align_up(4 * bucket_order_scratch_words(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
-    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows);
+    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * REDUCE2_SPLIT);
     return b + 65536;
 }
 
@@ -234,31 +323,40 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
     uint32_t* order_scratch = (uint32_t*)arena_take(4 * bucket_order_scratch_words(pl));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
     Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
-    Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows);
+    Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * REDUCE2_SPLIT);
     if (!wsum) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
+    C12_CUDA(cudaEventRecord(c.pev[0], s));
     k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.glv, pts, c.d_flags);
     C12_LAUNCHED();
+    C12_CUDA(cudaEventRecord(c.pev[1], s));
     rc = launch_recode(pl, d_scalars, keys, vals, c.d_flags, s);
     if (rc) return rc;
+    C12_CUDA(cudaEventRecord(c.pev[2], s));
     rc = sort_pairs_segmented(keys, vals, keys2, vals2, pl.n, pl.windows, pl.c, hist, tiles, s);
     if (rc) return rc;
+    C12_CUDA(cudaEventRecord(c.pev[3], s));
     rc = launch_bucket_bounds(pl, keys, start, end, s);
     if (rc) return rc;
     uint32_t* order = nullptr;
     rc = launch_bucket_order(pl, start, end, order_scratch, &order, s);
     if (rc) return rc;
     C12_CUDA(cudaEventRecord(c.ev[1], s));
+    C12_CUDA(cudaEventRecord(c.pev[4], s));
     k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, buckets);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
+    C12_CUDA(cudaEventRecord(c.pev[5], s));
     k_reduce1<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);
     C12_LAUNCHED();
-    k_reduce2<F><<<pl.windows, 256, 0, s>>>(pl, partial, wsum);
+    C12_CUDA(cudaEventRecord(c.pev[6], s));
+    k_reduce2<F><<<dim3(pl.windows, REDUCE2_SPLIT), 256, 0, s>>>(pl, partial, wsum);
     C12_LAUNCHED();
-    k_finish<F><<<1, 32, 0, s>>>(pl, wsum, d_out, out_mode);
+    C12_CUDA(cudaEventRecord(c.pev[7], s));
+    k_finish<F><<<1, 256, sizeof(Proj<F>) * pl.windows, s>>>(pl, wsum, d_out, out_mode);
     C12_LAUNCHED();
+    C12_CUDA(cudaEventRecord(c.pev[8], s));
     C12_CUDA(cudaEventRecord(c.ev[3], s));
     c.stats.window_bits = (int)pl.c;
     c.stats.bucket_adds = N;
