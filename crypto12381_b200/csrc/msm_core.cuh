@@ -22,6 +22,12 @@
 
 namespace c12 {
 
+constexpr uint32_t MSM_MAX_LEVELS = 8;
+constexpr uint32_t MSM_LEVEL_LEN = 8;      // segment length of reduction levels >= 1 (a power of two)
+constexpr uint32_t MSM_LEVEL_LOG = 3;
+constexpr uint32_t MSM_REDUCE2_SPLIT = 8;  // tree-sum jobs per window over the level-0 sums
+constexpr uint32_t MSM_WPART_SLOTS = MSM_REDUCE2_SPLIT + MSM_MAX_LEVELS;
+
 struct MsmPlan {
     uint32_t n;           // terms fed to the bucket pipeline (2 * n_in when the GLV split is on)
     uint32_t n_in;        // caller's terms
@@ -30,8 +36,11 @@ struct MsmPlan {
     uint32_t windows;     // W
     uint32_t half;        // 2^(c-1) buckets per window
     uint32_t total;       // W * half
-    uint32_t seg_len;     // buckets per reduce-1 thread
-    uint32_t segs;        // segments per window = ceil(half / seg_len)
+    uint32_t seg_len;     // buckets per level-0 reduction thread (a power of two)
+    uint32_t segs;        // segments per window = ceil(half / seg_len) = count[1]
+    // multi-level bucket reduction: level k turns count[k] entries per window into count[k+1] (sum, total) pairs
+    uint32_t levels;
+    uint32_t count[MSM_MAX_LEVELS + 1];
 };
 
 // Window width for n terms of `bits`-bit scalars: minimises  W * (10 n + 45 * 2^(c-1))  Fp products (10 per mixed
@@ -53,6 +62,21 @@ inline uint32_t msm_choose_window(uint64_t n, uint32_t bits = 256)
     return best;
 }
 
+// fills seg_len / segs / levels / count[] for a level-0 segment length (a power of two <= half)
+inline void msm_plan_levels(MsmPlan& pl, uint32_t seg_len)
+{
+    pl.seg_len = seg_len;
+    pl.segs = (pl.half + seg_len - 1) / seg_len;
+    for (uint32_t k = 0; k <= MSM_MAX_LEVELS; ++k) pl.count[k] = 1;
+    pl.count[0] = pl.half;
+    pl.count[1] = pl.segs;
+    pl.levels = 1;
+    while (pl.count[pl.levels] > 1 && pl.levels < MSM_MAX_LEVELS) {
+        pl.count[pl.levels + 1] = (pl.count[pl.levels] + MSM_LEVEL_LEN - 1) / MSM_LEVEL_LEN;
+        ++pl.levels;
+    }
+}
+
 // n_in caller terms; glv = true doubles the term count and halves the scalar width
 inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, bool glv = false)
 {
@@ -64,13 +88,11 @@ inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, bool glv = false)
     pl.windows = ((glv ? 128u : 256u) + c - 1) / c;
     pl.half = 1u << (c - 1);
     pl.total = pl.windows * pl.half;
-    // reduce-1 segment length: aim for >= 64 Ki threads, between 4 and 64 buckets per thread
-    uint32_t seg = pl.total / 65536u;
-    if (seg < 4) seg = 4;
-    if (seg > 64) seg = 64;
+    // level-0 segment length: a power of two in [4, 64] that keeps the level-0 grid within one wave (~48 Ki threads)
+    uint32_t seg = 4;
+    while (seg < 64 && pl.total / seg > 49152u) seg <<= 1;
     if (seg > pl.half) seg = pl.half;
-    pl.seg_len = seg;
-    pl.segs = (pl.half + seg - 1) / seg;
+    msm_plan_levels(pl, seg);
     return pl;
 }
 
@@ -318,25 +340,54 @@ C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint
     return xyzz_to_proj(acc);
 }
 
-// Body of reduce-1 for (window w, segment t): buckets with digit value k in [t*L+1, min((t+1)*L, half)]
-// (array index k-1).  Returns sum_k k * B_k over the segment.
-template <class F>
-C12_HD Proj<F> msm_reduce1_body(const MsmPlan& pl, uint32_t w, uint32_t t, const Proj<F>* buckets)
+// ---- bucket reduction:  S_w = sum_j (j + 1) B[j]  over the half buckets of window w ----------------------------------
+// Level 0 cuts the buckets into segments of L_0 = seg_len: segment t yields sum0_t = sum_i (i + 1) B[t L_0 + i] and the
+// plain total R1[t], so  S_w = sum_t sum0_t + L_0 sum_t t R1[t].  The second term is the same problem on the (8 x shorter)
+// array R1 with weights starting at 0; level k >= 1 cuts R_k into segments of 8 and yields sum_k,u = sum_i i R_k[8u + i]
+// and totals R_(k+1)[u].  With s_k = sum over the segments of level k:
+//     S_w = s_0 + L_0 (s_1 + 8 (s_2 + 8 (s_3 + ...)))
+// i.e. two additions per entry per level, no scalar multiplications, and only doublings to recombine.
+// Offsets (in points) of the per-level arrays inside the reduction scratch: sums of level k hold W * count[k+1] points,
+// totals feeding level k >= 1 hold W * count[k].
+C12_HD size_t msm_sums_offset(const MsmPlan& pl, uint32_t k)
 {
-    uint32_t lo = t * pl.seg_len;                       // first array index of the segment
-    uint32_t hi = lo + pl.seg_len;
-    if (hi > pl.half) hi = pl.half;
-    const Proj<F>* B = buckets + (uint64_t)w * pl.half;
-    Proj<F> run = proj_inf<F>();
-    Proj<F> sum = proj_inf<F>();
+    size_t o = 0;
+    for (uint32_t j = 0; j < k; ++j) o += (size_t)pl.windows * pl.count[j + 1];
+    return o;
+}
+C12_HD size_t msm_runs_offset(const MsmPlan& pl, uint32_t k)   // k >= 1
+{
+    size_t o = msm_sums_offset(pl, pl.levels);
+    for (uint32_t j = 1; j < k; ++j) o += (size_t)pl.windows * pl.count[j];
+    return o;
+}
+C12_HD size_t msm_reduce_scratch_points(const MsmPlan& pl) { return msm_runs_offset(pl, pl.levels + 1); }
+
+// one segment [lo, hi) of one level: sum = sum_i (i + w0) in[lo + i]  (w0 = 1 at level 0, 0 above), run = sum_i in[lo + i]
+template <class F>
+C12_HD void msm_reduce_level_body(const Proj<F>* in, uint32_t lo, uint32_t hi, uint32_t w0, Proj<F>& sum, Proj<F>& run)
+{
+    run = proj_inf<F>();
+    sum = proj_inf<F>();
 #pragma unroll 1
     for (uint32_t j = hi; j > lo; --j) {
-        run = proj_add(run, B[j - 1]);
-        sum = proj_add(sum, run);
+        run = proj_add(run, in[j - 1]);
+        if (w0 || j - 1 > lo) sum = proj_add(sum, run);
     }
-    // sum = sum_j (j - lo) * B[j-1] (digit value = j); add lo * run
-    if (lo) sum = proj_add(sum, proj_mul_small(run, lo));
-    return sum;
+}
+
+// S_w from the per-level sums s_0 .. s_(levels-1) of one window
+template <class F> C12_HD Proj<F> msm_combine_levels_body(const MsmPlan& pl, const Proj<F>* s)
+{
+    Proj<F> acc = s[pl.levels - 1];
+#pragma unroll 1
+    for (uint32_t k = pl.levels - 1; k > 0; --k) {
+        uint32_t len = k - 1 == 0 ? pl.seg_len : MSM_LEVEL_LEN;   // L_(k-1)
+#pragma unroll 1
+        for (; len > 1; len >>= 1) acc = proj_dbl(acc);
+        acc = proj_add(acc, s[k - 1]);
+    }
+    return acc;
 }
 
 // Horner over window sums S_w (w = W-1 .. 0): acc = 2^c acc + S_w

@@ -31,6 +31,17 @@ template <class T> __device__ __forceinline__ T shfl_down_obj(const T& x, int de
     return r;
 }
 
+template <class T> __device__ __forceinline__ T shfl_bcast_obj(const T& x, int src)
+{
+    static_assert(sizeof(T) % 4 == 0, "word-sized objects only");
+    T r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&x);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) d[i] = __shfl_sync(0xffffffffu, s[i], src);
+    return r;
+}
+
 // Sum of one value per thread over a 256-thread block (fixed tree: deterministic).  Result valid in thread 0.
 template <class F> __device__ Proj<F> block_sum_256(Proj<F> acc)
 {
@@ -96,13 +107,19 @@ __global__ void __launch_bounds__(128) k_accumulate(uint32_t total, const uint32
     buckets[b] = msm_accumulate_body<F>(b, start, end, vals, pts);
 }
 
+// level 0 of the bucket reduction: one thread per (window, segment of seg_len buckets)
 template <class F>
-__global__ void __launch_bounds__(128, 3) k_reduce1(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ partial)
+__global__ void __launch_bounds__(128, 3) k_reduce_level0(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ scratch)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= pl.segs) return;
     uint32_t w = blockIdx.y;
-    partial[(size_t)w * pl.segs + t] = msm_reduce1_body<F>(pl, w, t, buckets);
+    uint32_t lo = t * pl.seg_len, hi = lo + pl.seg_len;
+    if (hi > pl.half) hi = pl.half;
+    Proj<F> sum, run;
+    msm_reduce_level_body<F>(buckets + (size_t)w * pl.half, lo, hi, 1u, sum, run);
+    scratch[msm_sums_offset(pl, 0) + (size_t)w * pl.segs + t] = sum;
+    scratch[msm_runs_offset(pl, 1) + (size_t)w * pl.segs + t] = run;
 }
 
 // ---- lane-cooperative point arithmetic (the serial tail of an MSM) -------------------------------------------------
@@ -111,21 +128,23 @@ __global__ void __launch_bounds__(128, 3) k_reduce1(MsmPlan pl, const Proj<F>* _
 // products (4 + 4 for a doubling, 6 + 6 for an addition): lane i of the warp computes the i-th product of a layer and
 // the results are broadcast back with shuffles, so a doubling costs two product latencies instead of eight.
 // Every lane holds the same point before and after each call (all 32 lanes must call these together).
-template <class T> __device__ __forceinline__ T shfl_bcast_obj(const T& x, int src)
+// Groups of 8 lanes: every lane of a group holds the same point before and after each call; `mask` names the lanes of
+// the calling group(s) (all of them must call together).
+template <class T> __device__ __forceinline__ T group_bcast_obj(const T& x, int src, uint32_t mask)
 {
     static_assert(sizeof(T) % 4 == 0, "word-sized objects only");
     T r;
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&x);
     uint32_t* d = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) d[i] = __shfl_sync(0xffffffffu, s[i], src);
+    for (int i = 0; i < (int)(sizeof(T) / 4); ++i) d[i] = __shfl_sync(mask, s[i], src, 8);
     return r;
 }
 
-// out[i] = a[i] * b[i], product i computed by lane i
-template <class F, int N> __device__ __forceinline__ void coop_mul(F (&out)[N], const F (&a)[N], const F (&b)[N])
+// out[i] = a[i] * b[i], product i computed by lane i of the group (N <= 8)
+template <class F, int N> __device__ __forceinline__ void coop_mul(F (&out)[N], const F (&a)[N], const F (&b)[N], uint32_t mask)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 7;
     F x = a[0], y = b[0];
 #pragma unroll
     for (int i = 1; i < N; ++i) {
@@ -134,29 +153,29 @@ template <class F, int N> __device__ __forceinline__ void coop_mul(F (&out)[N], 
     }
     F m = mul(x, y);
 #pragma unroll
-    for (int i = 0; i < N; ++i) out[i] = shfl_bcast_obj(m, i);
+    for (int i = 0; i < N; ++i) out[i] = group_bcast_obj(m, i, mask);
 }
 
 // proj_dbl (RCB15 Algorithm 9), same value
-template <class F> __device__ Proj<F> coop_dbl(const Proj<F>& p)
+template <class F> __device__ Proj<F> coop_dbl(const Proj<F>& p, uint32_t mask)
 {
     F a1[4] = {p.y, p.y, p.z, p.x}, b1[4] = {p.y, p.z, p.z, p.y}, m[4];
-    coop_mul<F, 4>(m, a1, b1);                      // t0 = Y^2, t1 = YZ, t2 = Z^2, XY
+    coop_mul<F, 4>(m, a1, b1, mask);                // t0 = Y^2, t1 = YZ, t2 = Z^2, XY
     F z3 = mul8(m[0]);
     F t2 = FieldOps<F>::mul_b3(m[2]);
     F y3 = add(m[0], t2);
     F t0 = sub(m[0], mul3(t2));
     F a2[4] = {t2, z3, y3, t0}, b2[4] = {z3, m[1], t0, m[3]}, n[4];
-    coop_mul<F, 4>(n, a2, b2);                      // x3, Z3, y3 t0, t0 XY
+    coop_mul<F, 4>(n, a2, b2, mask);                // x3, Z3, y3 t0, t0 XY
     return Proj<F>{dbl(n[3]), add(n[2], n[0]), n[1]};
 }
 
 // proj_add (RCB15 Algorithm 7), same value
-template <class F> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& q)
+template <class F> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& q, uint32_t mask)
 {
     F a1[6] = {p.x, p.y, p.z, add(p.x, p.y), add(p.y, p.z), add(p.x, p.z)};
     F b1[6] = {q.x, q.y, q.z, add(q.x, q.y), add(q.y, q.z), add(q.x, q.z)}, m[6];
-    coop_mul<F, 6>(m, a1, b1);
+    coop_mul<F, 6>(m, a1, b1, mask);
     F t3 = sub(m[3], add(m[0], m[1]));
     F t4 = sub(m[4], add(m[1], m[2]));
     F y3 = FieldOps<F>::mul_b3(sub(m[5], add(m[0], m[2])));
@@ -165,21 +184,56 @@ template <class F> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& 
     F z3 = add(m[1], t2);
     F t1 = sub(m[1], t2);
     F a2[6] = {y3, t3, y3, t1, t0, z3}, b2[6] = {t4, t1, t0, z3, t3, t4}, n[6];
-    coop_mul<F, 6>(n, a2, b2);
+    coop_mul<F, 6>(n, a2, b2, mask);
     return Proj<F>{sub(n[1], n[0]), add(n[2], n[3]), add(n[5], n[4])};
 }
 
-constexpr int REDUCE2_SPLIT = 8;   // blocks per window in reduce-2 (their partials are merged by k_finish)
-
+// levels >= 1 of the bucket reduction: a group of 8 lanes per (window, segment of 8 totals) - these levels are short
+// dependent chains over few items, so latency (not throughput) is what counts
 template <class F>
-__global__ void __launch_bounds__(256) k_reduce2(MsmPlan pl, const Proj<F>* __restrict__ partial, Proj<F>* __restrict__ wpart)
+__global__ void __launch_bounds__(128) k_reduce_level(MsmPlan pl, uint32_t k, Proj<F>* __restrict__ scratch)
 {
-    uint32_t w = blockIdx.x;
+    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const uint32_t count = pl.count[k], next = pl.count[k + 1];
+    if (g >= next) return;
+    const uint32_t w = blockIdx.y;
+    const uint32_t mask = 0xffu << (threadIdx.x & 24);
+    const Proj<F>* in = scratch + msm_runs_offset(pl, k) + (size_t)w * count;
+    uint32_t lo = g * MSM_LEVEL_LEN, hi = lo + MSM_LEVEL_LEN;
+    if (hi > count) hi = count;
+    Proj<F> run = proj_inf<F>(), sum = proj_inf<F>();
+#pragma unroll 1
+    for (uint32_t j = hi; j > lo; --j) {
+        run = coop_add(run, in[j - 1], mask);
+        if (j - 1 > lo) sum = coop_add(sum, run, mask);
+    }
+    if ((threadIdx.x & 7) == 0) {
+        scratch[msm_sums_offset(pl, k) + (size_t)w * next + g] = sum;
+        scratch[msm_runs_offset(pl, k + 1) + (size_t)w * next + g] = run;
+    }
+}
+
+// tree sums of the per-level sums: block (w, y) -> wpart[w][y].  y < MSM_REDUCE2_SPLIT: a slice of the level-0 sums;
+// y = MSM_REDUCE2_SPLIT + k - 1: all sums of level k >= 1.
+template <class F>
+__global__ void __launch_bounds__(256) k_reduce2(MsmPlan pl, const Proj<F>* __restrict__ scratch, Proj<F>* __restrict__ wpart)
+{
+    const uint32_t w = blockIdx.x, y = blockIdx.y;
+    uint32_t k = 0, lo = 0, hi;
+    if (y < MSM_REDUCE2_SPLIT) {
+        uint32_t chunk = (pl.count[1] + MSM_REDUCE2_SPLIT - 1) / MSM_REDUCE2_SPLIT;
+        lo = y * chunk;
+        hi = lo + chunk;
+        if (hi > pl.count[1]) hi = pl.count[1];
+    } else {
+        k = y - MSM_REDUCE2_SPLIT + 1;
+        hi = pl.count[k + 1];
+    }
+    const Proj<F>* in = scratch + msm_sums_offset(pl, k) + (size_t)w * pl.count[k + 1];
     Proj<F> acc = proj_inf<F>();
-    for (uint32_t t = blockIdx.y * 256 + threadIdx.x; t < pl.segs; t += 256 * REDUCE2_SPLIT)
-        acc = proj_add(acc, partial[(size_t)w * pl.segs + t]);
+    for (uint32_t t = lo + threadIdx.x; t < hi; t += 256) acc = proj_add(acc, in[t]);
     acc = block_sum_256(acc);
-    if (threadIdx.x == 0) wpart[(size_t)w * REDUCE2_SPLIT + blockIdx.y] = acc;
+    if (threadIdx.x == 0) wpart[(size_t)w * MSM_WPART_SLOTS + y] = acc;
 }
 
 template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, int out_mode)
@@ -191,19 +245,34 @@ template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, i
         Wire<F>::compress(out, a);
 }
 
-// One block of 8 warps: warp v merges the REDUCE2_SPLIT partials of windows v, v + 8, ... (shuffle tree), then warp 0
-// runs the Horner combination  acc = 2^c acc + S_w  with lane-cooperative doublings, normalises and encodes.
+// One block of 8 warps.  Warp v, for windows v, v + 8, ...: merges the level-0 slices (shuffle tree) and recombines the
+// levels  S_w = s_0 + L_0 (s_1 + 8 (s_2 + ...))  with lane-cooperative doublings.  Then warp 0 runs the Horner
+// combination over windows  acc = 2^c acc + S_w, normalises and encodes.
 template <class F> __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __restrict__ wpart, uint8_t* out, int out_mode)
 {
     extern __shared__ __align__(16) unsigned char finish_smem[];
     Proj<F>* wsum = reinterpret_cast<Proj<F>*>(finish_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t full = 0xffffffffu;
     for (uint32_t w = warp; w < pl.windows; w += 8) {
-        Proj<F> acc = lane < REDUCE2_SPLIT ? wpart[(size_t)w * REDUCE2_SPLIT + lane] : proj_inf<F>();
+        const Proj<F>* slot = wpart + (size_t)w * MSM_WPART_SLOTS;
+        Proj<F> s0 = lane < (int)MSM_REDUCE2_SPLIT ? slot[lane] : proj_inf<F>();
 #pragma unroll 1
-        for (int off = REDUCE2_SPLIT / 2; off >= 1; off >>= 1) {
-            Proj<F> o = shfl_down_obj(acc, off);
-            acc = proj_add(acc, o);
+        for (int off = MSM_REDUCE2_SPLIT / 2; off >= 1; off >>= 1) {
+            Proj<F> o = shfl_down_obj(s0, off);
+            s0 = proj_add(s0, o);
+        }
+        s0 = shfl_bcast_obj(s0, 0);
+        Proj<F> acc = s0;
+        if (pl.levels > 1) {
+            acc = slot[MSM_REDUCE2_SPLIT + pl.levels - 2];
+#pragma unroll 1
+            for (uint32_t k = pl.levels - 1; k > 0; --k) {
+                uint32_t len = k - 1 == 0 ? pl.seg_len : MSM_LEVEL_LEN;
+#pragma unroll 1
+                for (; len > 1; len >>= 1) acc = coop_dbl(acc, full);
+                acc = coop_add(acc, k - 1 == 0 ? s0 : slot[MSM_REDUCE2_SPLIT + k - 2], full);
+            }
         }
         if (lane == 0) wsum[w] = acc;
     }
@@ -213,8 +282,8 @@ template <class F> __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, c
 #pragma unroll 1
     for (uint32_t w = pl.windows - 1; w > 0; --w) {
 #pragma unroll 1
-        for (uint32_t k = 0; k < pl.c; ++k) acc = coop_dbl(acc);
-        acc = coop_add(acc, wsum[w - 1]);
+        for (uint32_t k = 0; k < pl.c; ++k) acc = coop_dbl(acc, full);
+        acc = coop_add(acc, wsum[w - 1], full);
     }
     if (lane == 0) write_point<F>(out, acc, out_mode);
 }
@@ -273,8 +342,8 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
     b += 2 * align_up(4 * (size_t)pl.total);
     b += align_up(4 * bucket_order_scratch_words(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
-    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
-    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * REDUCE2_SPLIT);
+    b += align_up(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
+    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
     return b + 65536;
 }
 
@@ -322,8 +391,8 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)pl.total);
     uint32_t* order_scratch = (uint32_t*)arena_take(4 * bucket_order_scratch_words(pl));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
-    Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * pl.segs);
-    Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * REDUCE2_SPLIT);
+    Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
+    Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
     if (!wsum) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
@@ -348,10 +417,14 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));
-    k_reduce1<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);
+    k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);
     C12_LAUNCHED();
+    for (uint32_t k = 1; k < pl.levels; ++k) {
+        k_reduce_level<F><<<dim3(cdiv((size_t)pl.count[k + 1] * 8, 128), pl.windows), 128, 0, s>>>(pl, k, partial);
+        C12_LAUNCHED();
+    }
     C12_CUDA(cudaEventRecord(c.pev[6], s));
-    k_reduce2<F><<<dim3(pl.windows, REDUCE2_SPLIT), 256, 0, s>>>(pl, partial, wsum);
+    k_reduce2<F><<<dim3(pl.windows, MSM_REDUCE2_SPLIT + pl.levels - 1), 256, 0, s>>>(pl, partial, wsum);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.pev[7], s));
     k_finish<F><<<1, 256, sizeof(Proj<F>) * pl.windows, s>>>(pl, wsum, d_out, out_mode);

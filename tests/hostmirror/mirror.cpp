@@ -18,10 +18,7 @@ namespace {
 MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, bool glv)
 {
     MsmPlan pl = msm_make_plan(n, c, glv);
-    if (seg_len) {
-        pl.seg_len = seg_len > pl.half ? pl.half : seg_len;
-        pl.segs = (pl.half + pl.seg_len - 1) / pl.seg_len;
-    }
+    if (seg_len) msm_plan_levels(pl, seg_len > pl.half ? pl.half : seg_len);   // a power of two
     return pl;
 }
 
@@ -67,9 +64,24 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
     for (uint32_t b = 0; b < pl.total; ++b) buckets[b] = msm_accumulate_body<F>(b, start.data(), end.data(), sv.data(), P.data());
     std::vector<Proj<F>> wsum(pl.windows);
     for (uint32_t w = 0; w < pl.windows; ++w) {
-        Proj<F> acc = proj_inf<F>();
-        for (uint32_t t = 0; t < pl.segs; ++t) acc = proj_add(acc, msm_reduce1_body<F>(pl, w, t, buckets.data()));
-        wsum[w] = acc;
+        // the multi-level reduction of msm_core.cuh, level by level (k_reduce_level0 / k_reduce_level / k_reduce2 / k_finish)
+        std::vector<Proj<F>> cur(buckets.begin() + (size_t)w * pl.half, buckets.begin() + (size_t)(w + 1) * pl.half);
+        std::vector<Proj<F>> s(pl.levels);
+        for (uint32_t k = 0; k < pl.levels; ++k) {
+            uint32_t len = k == 0 ? pl.seg_len : MSM_LEVEL_LEN, next = pl.count[k + 1];
+            if (cur.size() != pl.count[k]) return -2;
+            std::vector<Proj<F>> runs(next);
+            Proj<F> tot = proj_inf<F>();
+            for (uint32_t t = 0; t < next; ++t) {
+                uint32_t lo = t * len, hi = lo + len > pl.count[k] ? pl.count[k] : lo + len;
+                Proj<F> sum;
+                msm_reduce_level_body<F>(cur.data(), lo, hi, k == 0 ? 1u : 0u, sum, runs[t]);
+                tot = proj_add(tot, sum);
+            }
+            s[k] = tot;
+            cur.swap(runs);
+        }
+        wsum[w] = msm_combine_levels_body<F>(pl, s.data());
     }
     Proj<F> r = msm_horner_body<F>(pl, wsum.data());
     W::compress(out, proj_to_affine(r));
