@@ -14,7 +14,7 @@ namespace c12 {
 
 struct MsmStats {
     double accumulate_ms = 0, total_ms = 0;
-    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // parse, recode, sort, bounds+order, accumulate, reduce1, reduce2, finish
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // recode, sort, bounds+order, parse, accumulate, reduce levels, reduce2, finish
     unsigned long long bucket_adds = 0;
     int window_bits = 0;
 };
@@ -22,6 +22,8 @@ struct MsmStats {
 struct Ctx {
     int device = -1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host entries: input uploads that overlap the first pipeline stages
+    cudaEvent_t copy_ev[3] = {nullptr, nullptr, nullptr};
     std::string err;
     unsigned long long launches = 0;
     // scratch arena: one allocation, bump-allocated per call, grown (after a stream sync) when too small

@@ -26,6 +26,7 @@ int arena_begin(size_t total, cudaStream_t s)
         // growing: earlier work may still read the old arena
         C12_CUDA(cudaStreamSynchronize(s));
         if (s != c.stream) C12_CUDA(cudaStreamSynchronize(c.stream));
+        if (c.copy_stream) C12_CUDA(cudaStreamSynchronize(c.copy_stream));
         if (c.arena) C12_CUDA(cudaFree(c.arena));
         c.arena = nullptr;
         c.arena_bytes = 0;
@@ -164,6 +165,8 @@ int c12381_init(int device)
     if (c.device >= 0) c12381_shutdown();
     C12_CUDA(cudaSetDevice(device));
     C12_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    C12_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    for (auto& ev : c.copy_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
     C12_CUDA(cudaMalloc(&c.d_flags, 64 * sizeof(int)));
     for (auto& ev : c.ev) C12_CUDA(cudaEventCreate(&ev));
@@ -186,6 +189,12 @@ void c12381_shutdown(void)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : c.pev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c.copy_ev)
+        if (ev) cudaEventDestroy(ev);
+    if (c.copy_stream) {
+        cudaStreamSynchronize(c.copy_stream);
+        cudaStreamDestroy(c.copy_stream);
+    }
     cudaStreamDestroy(c.stream);
     c = Ctx();
 }

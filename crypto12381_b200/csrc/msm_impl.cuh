@@ -361,7 +361,11 @@ template <class F> size_t msm_scratch_for(size_t n)
 // d_points: n wire-format affine points; d_scalars: n x 32 B big-endian; d_out: Wire<F>::COMPRESSED or ::AFFINE bytes.
 // Everything is enqueued on `s`; malformed input is reported through the context flag word (c12381_sync_status /
 // the host entry's return code), never by a different code path.
-template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint8_t* d_out, int out_mode, cudaStream_t s)
+// points_ready: optional event after which d_points is valid (host entries upload the points on a second stream while
+// the scalar-only stages - recode, sort, bucket bounds - already run).
+template <class F>
+int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint8_t* d_out, int out_mode, cudaStream_t s,
+            cudaEvent_t points_ready = nullptr)
 {
     Ctx& c = ctx();
     const int out_bytes = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
@@ -397,20 +401,21 @@ template <class F> int msm_run(const uint8_t* d_points, const uint8_t* d_scalars
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
     C12_CUDA(cudaEventRecord(c.pev[0], s));
-    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.glv, pts, c.d_flags);
-    C12_LAUNCHED();
-    C12_CUDA(cudaEventRecord(c.pev[1], s));
     rc = launch_recode(pl, d_scalars, keys, vals, c.d_flags, s);
     if (rc) return rc;
-    C12_CUDA(cudaEventRecord(c.pev[2], s));
+    C12_CUDA(cudaEventRecord(c.pev[1], s));
     rc = sort_pairs_segmented(keys, vals, keys2, vals2, pl.n, pl.windows, pl.c, hist, tiles, s);
     if (rc) return rc;
-    C12_CUDA(cudaEventRecord(c.pev[3], s));
+    C12_CUDA(cudaEventRecord(c.pev[2], s));
     rc = launch_bucket_bounds(pl, keys, start, end, s);
     if (rc) return rc;
     uint32_t* order = nullptr;
     rc = launch_bucket_order(pl, start, end, order_scratch, &order, s);
     if (rc) return rc;
+    if (points_ready) C12_CUDA(cudaStreamWaitEvent(s, points_ready, 0));
+    C12_CUDA(cudaEventRecord(c.pev[3], s));
+    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.glv, pts, c.d_flags);
+    C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
     k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, buckets);
@@ -522,11 +527,35 @@ template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scal
 {
     C12_REQUIRE_CTX();
     if (!out || (n && (!points || !scalars))) return set_error(C12381_EARG, "msm: null pointer");
-    const void* in[2] = {points, scalars};
-    size_t sz[2] = {n * Wire<F>::AFFINE, n * 32};
-    return with_staged(in, sz, 2, out, Wire<F>::COMPRESSED, msm_scratch_for<F>(n), [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
-        return msm_run<F>(d_in[0], d_in[1], n, d_out, OUT_COMPRESSED, s);
-    });
+    // scalars go up on the context stream (the first stages need only them); the points - three quarters of the bytes -
+    // follow on the copy stream and are awaited right before k_parse_points
+    Ctx& c = ctx();
+    cudaStream_t s = c.stream;
+    const size_t pb = n * Wire<F>::AFFINE, sb = n * 32;
+    int rc = arena_begin(msm_scratch_for<F>(n) + align_up(pb) + align_up(sb) + 8192, s);
+    if (rc) return rc;
+    uint8_t* d_pts = (uint8_t*)arena_take(pb ? pb : 4);
+    uint8_t* d_sc = (uint8_t*)arena_take(sb ? sb : 4);
+    uint8_t* d_out = (uint8_t*)arena_take(Wire<F>::COMPRESSED);
+    rc = flags_reset(s);
+    if (rc) return rc;
+    cudaEvent_t ready = nullptr;
+    if (n) {
+        C12_CUDA(cudaMemcpyAsync(d_sc, scalars, sb, cudaMemcpyHostToDevice, s));
+        C12_CUDA(cudaEventRecord(c.copy_ev[0], s));                        // the arena is ours from here on
+        C12_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_ev[0], 0));
+        C12_CUDA(cudaMemcpyAsync(d_pts, points, pb, cudaMemcpyHostToDevice, c.copy_stream));
+        C12_CUDA(cudaEventRecord(c.copy_ev[1], c.copy_stream));
+        ready = c.copy_ev[1];
+    }
+    rc = msm_run<F>(d_pts, d_sc, n, d_out, OUT_COMPRESSED, s, ready);
+    if (rc) {
+        cudaStreamSynchronize(c.copy_stream);
+        cudaStreamSynchronize(s);
+        return rc;
+    }
+    C12_CUDA(cudaMemcpyAsync(out, d_out, Wire<F>::COMPRESSED, cudaMemcpyDeviceToHost, s));
+    return flags_collect(s);
 }
 
 template <class F> int entry_sum_dev(const uint8_t* d_points, size_t n, uint8_t* d_out, void* stream)

@@ -8,9 +8,12 @@
 namespace c12 {
 
 constexpr int PAIR_THREADS = 64;
+#ifndef C12_PAIR_MIN_BLOCKS
+#define C12_PAIR_MIN_BLOCKS 1      // blocks per SM the register allocation is bounded for (A/B knob, profiles/)
+#endif
 
 // mode 0: raw Miller product (576 B); mode 1: final-exponentiated GT value (576 B); mode 2: verdict byte (GT == 1)
-__global__ void __launch_bounds__(PAIR_THREADS) k_pairing(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, uint32_t B,
+__global__ void __launch_bounds__(PAIR_THREADS, C12_PAIR_MIN_BLOCKS) k_pairing(const uint8_t* __restrict__ g1, const uint8_t* __restrict__ g2, uint32_t B,
                                                           uint32_t k, int mode, uint8_t* __restrict__ out, int* flags)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -188,7 +188,7 @@ def last_msm_stats() -> dict:
     check(lib().c12381_last_msm_stats(ctypes.byref(a), ctypes.byref(t), ctypes.byref(adds), ctypes.byref(c)))
     ph = (ctypes.c_double * 8)()
     check(lib().c12381_last_msm_phases(ph))
-    names = ["parse", "recode", "sort", "bounds_order", "accumulate", "reduce1", "reduce2", "finish"]
+    names = ["recode", "sort", "bounds_order", "parse", "accumulate", "reduce1", "reduce2", "finish"]
     return {"accumulate_ms": a.value, "total_ms": t.value, "bucket_adds": adds.value, "window_bits": c.value,
             "phases_ms": dict(zip(names, list(ph)))}
 

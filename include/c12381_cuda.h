@@ -156,8 +156,8 @@ C12381_API unsigned long long c12381_launch_count(void);
 /* CUDA-event time (ms) of the dominant MSM kernel (bucket accumulation) in the most recent MSM call, and the
  * number of bucket additions it performed */
 C12381_API int c12381_last_msm_stats(double* accumulate_ms, double* total_ms, unsigned long long* bucket_adds, int* window_bits);
-/* CUDA-event times (ms) of the eight phases of the most recent MSM call: parse, recode, sort, bucket bounds + order,
- * accumulate, reduce-1, reduce-2, finish */
+/* CUDA-event times (ms) of the eight phases of the most recent MSM call: recode, sort, bucket bounds + order, parse
+ * (includes waiting for the point upload in the host entry), accumulate, reduction levels, reduce-2, finish */
 C12381_API int c12381_last_msm_phases(double* phase_ms8);
 
 #ifdef __cplusplus

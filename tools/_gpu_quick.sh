@@ -1,8 +1,13 @@
-SKIP_NCU=1 bash tools/gpu_round.sh r01f
-python - <<'PY'
-import json
-d=json.load(open("gpurun_out/r01f/bench.json"))
-print("phases", d["roofline"].get("phases_ms"))
-print("hbm", d["roofline"].get("hbm_phase"))
-print("secondary", {k:v for k,v in d["secondary"].items() if k!="cpu_baseline"})
+TAG=${TAG:-r01g}
+SKIP_NCU=1 VARIANTS="${VARIANTS}" bash tools/gpu_round.sh $TAG
+python - <<PY
+import json,glob
+for f in sorted(glob.glob("gpurun_out/$TAG/bench*.json")):
+    d=json.load(open(f))
+    if "roofline" not in d: continue
+    print(f)
+    print(" phases", {k: round(v,3) for k,v in d["roofline"].get("phases_ms",{}).items()})
+    print(" e2e ms", d["e2e"].get("ms_per_step"), " hbm", d["roofline"].get("hbm_phase",{}).get("achieved_gbs"))
+    s=d.get("secondary",{})
+    print(" pairings/s", s.get("value"), "ms", s.get("ms"), "frac", s.get("frac_of_int32_mad_peak"))
 PY
