@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--pairing-instances", type=int, default=1 << 16)
     ap.add_argument("--cpu-sample-log-n", type=int, default=15)
+    ap.add_argument("--g2-log-n", type=int, default=18)
     ap.add_argument("--no-secondary", action="store_true")
     return ap.parse_args()
 
@@ -309,6 +310,46 @@ def run_ours(args):
             except Exception as e:
                 sec["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
             line["secondary"] = sec
+    # secondary 2: G2 MSM (BASELINE configs[2]), n = 2^18 per GPU, partial -> all-gather -> merge as for G1
+    if not args.no_secondary:
+        from crypto12381_b200.distributed import g2_msm_sharded
+        n2 = 1 << args.g2_log_n
+        k2 = torch.from_numpy(rand_scalars(n2, 5000 + rank)).reshape(-1).to(dev)
+        s2 = torch.from_numpy(rand_scalars(n2, 6000 + rank)).reshape(-1).to(dev)
+        p2 = dv.g2_fixed_base_mul_batch(k2)
+        for _ in range(2):
+            r2 = g2_msm_sharded(p2, s2)
+        barrier()
+        reps = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush.fill_(1)
+        e0.record()
+        for _ in range(reps):
+            r2 = g2_msm_sharded(p2, s2)
+        e1.record()
+        barrier()
+        st2 = dv.last_msm_stats()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            ms = float(t.item())
+            g2 = {"metric": "g2_msm_points_per_s", "value": n2 * world / (ms * 1e-3), "unit": "points/s", "n_per_gpu": n2, "ms": ms,
+                  "window_bits": st2["window_bits"], "phases_ms": st2["phases_ms"], "result_hex": bytes(r2.cpu().numpy()).hex()}
+            try:
+                from oracle import ref
+                if ref.available():
+                    m = 1 << 11
+                    tc = time.perf_counter()
+                    want = ref.g2_msm(bytes(p2[:192 * m].cpu().numpy()), bytes(s2[:32 * m].cpu().numpy()), ref.hardware_threads())
+                    dtc = time.perf_counter() - tc
+                    got = bytes(dv.g2_msm(p2[:192 * m], s2[:32 * m]).cpu().numpy())
+                    g2["cpu_baseline"] = {"value": m / dtc, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                          "sample": f"first 2^11 terms: per-term PAIR_G2mul + ECP2_add loop (g2_point.hpp:202-236) over {ref.hardware_threads()} host threads",
+                                          "bit_exact_vs_gpu_on_sample": want == got}
+            except Exception as e:
+                g2["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+            line["secondary_g2_msm"] = g2
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

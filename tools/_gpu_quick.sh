@@ -1,5 +1,5 @@
 TAG=${TAG:-r01g}
-SKIP_NCU=1 VARIANTS="${VARIANTS}" bash tools/gpu_round.sh $TAG
+VARIANTS="${VARIANTS}" bash tools/gpu_round.sh $TAG
 python - <<PY
 import json,glob
 for f in sorted(glob.glob("gpurun_out/$TAG/bench*.json")):
@@ -10,4 +10,5 @@ for f in sorted(glob.glob("gpurun_out/$TAG/bench*.json")):
     print(" e2e ms", d["e2e"].get("ms_per_step"), " hbm", d["roofline"].get("hbm_phase",{}).get("achieved_gbs"))
     s=d.get("secondary",{})
     print(" pairings/s", s.get("value"), "ms", s.get("ms"), "frac", s.get("frac_of_int32_mad_peak"))
+    print(" g2", d.get("secondary_g2_msm"))
 PY
