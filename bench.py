@@ -234,8 +234,17 @@ def run_ours(args):
         adds = stats["bucket_adds"]
         acc = statistics.mean(acc_ms)
         achieved = adds * FP_MUL_PER_BUCKET_ADD * MAC_PER_FP_MUL / (acc * 1e-3) / 1e9
+        traffic, traffic_src = None, None
+        try:   # DRAM bytes of one k_accumulate launch from the committed ncu --set full capture (same n, same plan)
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                tr = json.load(f)["k_accumulate<Fp>"]
+            if args.log_n == 20:
+                traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
+        except Exception:
+            pass
         roofline = {"bound": "int32_mad", "kernel": "k_accumulate<Fp>", "achieved": achieved, "peak": peak_gmacs, "unit": "GMAC/s (32x32->64 multiply-adds)",
-                    "frac": achieved / peak_gmacs, "traffic": None,
+                    "frac": achieved / peak_gmacs, "traffic": traffic, "traffic_unit": "DRAM bytes per launch", "traffic_source": traffic_src,
+                    "gather_bytes_algorithmic": adds * 96,
                     "peak_source": "measured live: c12381_probe kind 2 (mad.wide.u32 chains) / kind 1 (mad.lo.cc+madc.hi.cc pairs), same GPU, same run",
                     "algorithmic": f"{adds} bucket additions/launch x {FP_MUL_PER_BUCKET_ADD} Fp-mul x {MAC_PER_FP_MUL} MAC",
                     "kernel_ms": acc, "kernel_share_of_step": acc / statistics.mean(tot_ms), "window_bits": stats["window_bits"],
