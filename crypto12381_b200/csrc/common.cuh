@@ -30,6 +30,7 @@ struct Ctx {
     uint8_t* arena = nullptr;
     size_t arena_bytes = 0;
     size_t arena_used = 0;
+    int arena_depth = 0;   // > 0 while a host entry runs its pipeline: nested arena_begin calls carve from the same reservation
     // pinned staging for small results / flags
     int* h_flags = nullptr;
     int* d_flags = nullptr;

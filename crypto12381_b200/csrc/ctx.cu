@@ -22,6 +22,10 @@ int arena_begin(size_t total, cudaStream_t s)
 {
     Ctx& c = g_ctx;
     total = align_up(total + 4096);
+    if (c.arena_depth > 0) {   // an entry point called from inside a host entry: its scratch was reserved by the outer call
+        if (c.arena_used + total > c.arena_bytes) return set_error(C12381_ECUDA, "nested scratch reservation too small");
+        return C12381_OK;
+    }
     if (total > c.arena_bytes) {
         // growing: earlier work may still read the old arena
         C12_CUDA(cudaStreamSynchronize(s));

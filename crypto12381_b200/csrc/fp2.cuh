@@ -35,22 +35,32 @@ C12_HD Fp2 select(bool c, const Fp2& x, const Fp2& y)
 }
 
 // Karatsuba: 3 Fp products.  A real call on the device: the towers above it (Fp4/Fp12, G2 curve formulas)
-// would otherwise inline ~2,000 SASS instructions per use and thrash the instruction cache.
-C12_HD_NOINLINE Fp2 mul(const Fp2& x, const Fp2& y)
+// would otherwise inline ~2,000 SASS instructions per use and thrash the instruction cache.  Operands and result
+// travel BY VALUE (in registers): by-reference parameters of a non-inlined function would force every caller to
+// park both operands in local memory first.
+C12_HD Fp2 fp2_mul_body(const Fp2& x, const Fp2& y)
 {
     Fp t0 = fp_mul(x.a, y.a);
     Fp t1 = fp_mul(x.b, y.b);
     Fp t2 = fp_mul(fp_add(x.a, x.b), fp_add(y.a, y.b));
     return Fp2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
 }
-
 // (a+b)(a-b) + 2ab i : 2 Fp products
-C12_HD_NOINLINE Fp2 sqr(const Fp2& x)
+C12_HD Fp2 fp2_sqr_body(const Fp2& x)
 {
     Fp t0 = fp_mul(fp_add(x.a, x.b), fp_sub(x.a, x.b));
     Fp t1 = fp_mul(x.a, x.b);
     return Fp2{t0, fp_dbl(t1)};
 }
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ Fp2 fp2_mul_call(Fp2 x, Fp2 y) { return fp2_mul_body(x, y); }
+__device__ __noinline__ Fp2 fp2_sqr_call(Fp2 x) { return fp2_sqr_body(x); }
+C12_HD Fp2 mul(const Fp2& x, const Fp2& y) { return fp2_mul_call(x, y); }
+C12_HD Fp2 sqr(const Fp2& x) { return fp2_sqr_call(x); }
+#else
+C12_HD Fp2 mul(const Fp2& x, const Fp2& y) { return fp2_mul_body(x, y); }
+C12_HD Fp2 sqr(const Fp2& x) { return fp2_sqr_body(x); }
+#endif
 
 // products of the bucket-accumulation hot loop (ec.cuh xyzz_madd): straight-line code over Fp, the regular call over Fp2
 C12_HD Fp mul_hot(const Fp& a, const Fp& b) { return fp_mul_inl(a, b); }

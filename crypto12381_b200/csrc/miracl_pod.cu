@@ -144,7 +144,7 @@ int pod_miller(void* result_fp12, const void* const* p2s, const void* const* p1s
     }
     const void* in[2] = {h1, h2};
     size_t sz[2] = {(size_t)POD_P1 * k, (size_t)POD_P2 * k};
-    return with_staged(in, sz, 2, result_fp12, POD_FP12, 8192, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+    return with_staged(in, sz, 2, result_fp12, POD_FP12, 65536, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
         uint8_t* w1 = (uint8_t*)arena_take(96 * 2);
         uint8_t* w2 = (uint8_t*)arena_take(192 * 2);
         uint8_t* f = (uint8_t*)arena_take(576);
@@ -201,7 +201,7 @@ int c12381_pair_final_exponentiation_miracl(void* object_fp12)
     if (!object_fp12) return set_error(C12381_EARG, "pair_final_exponentiation: null pointer");
     const void* in[1] = {object_fp12};
     size_t sz[1] = {POD_FP12};
-    return with_staged(in, sz, 1, object_fp12, POD_FP12, 4096, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+    return with_staged(in, sz, 1, object_fp12, POD_FP12, 65536, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
         uint8_t* f = (uint8_t*)arena_take(576);
         uint8_t* g = (uint8_t*)arena_take(576);
         int rc = fp12_to_wire(d_in[0], 1, f, s);
@@ -217,7 +217,7 @@ int c12381_fp12_multiply_miracl(void* result_fp12, const void* value_fp12)
     if (!result_fp12 || !value_fp12) return set_error(C12381_EARG, "multiply(fp12): null pointer");
     const void* in[2] = {result_fp12, value_fp12};
     size_t sz[2] = {POD_FP12, POD_FP12};
-    return with_staged(in, sz, 2, result_fp12, POD_FP12, 4096, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+    return with_staged(in, sz, 2, result_fp12, POD_FP12, 65536, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
         uint8_t* a = (uint8_t*)arena_take(576);
         uint8_t* b = (uint8_t*)arena_take(576);
         uint8_t* g = (uint8_t*)arena_take(576);
@@ -235,7 +235,7 @@ int c12381_fp12_pow_miracl(void* result_fp12, const void* base_fp12, const void*
     if (!result_fp12 || !base_fp12 || !exponent_big) return set_error(C12381_EARG, "pow(fp12): null pointer");
     const void* in[2] = {base_fp12, exponent_big};
     size_t sz[2] = {POD_FP12, POD_BIG};
-    return with_staged(in, sz, 2, result_fp12, POD_FP12, 4096, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+    return with_staged(in, sz, 2, result_fp12, POD_FP12, 65536, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
         uint8_t* a = (uint8_t*)arena_take(576);
         uint8_t* e = (uint8_t*)arena_take(32);
         uint8_t* g = (uint8_t*)arena_take(576);

@@ -29,9 +29,9 @@ constexpr uint32_t MSM_REDUCE2_SPLIT = 8;  // tree-sum jobs per window over the 
 constexpr uint32_t MSM_WPART_SLOTS = MSM_REDUCE2_SPLIT + MSM_MAX_LEVELS;
 
 struct MsmPlan {
-    uint32_t n;           // terms fed to the bucket pipeline (2 * n_in when the GLV split is on)
+    uint32_t n;           // terms fed to the bucket pipeline = parts * n_in
     uint32_t n_in;        // caller's terms
-    uint32_t glv;         // 1: every scalar was split into two ~127-bit halves (G1), windows cover 128 bits
+    uint32_t parts;       // 1: none; 2: GLV halves of < 2^127 (G1); 4: GLS quarters of < 2^63 (G2).  Windows cover 256 / parts bits
     uint32_t c;           // window bits
     uint32_t windows;     // W
     uint32_t half;        // 2^(c-1) buckets per window
@@ -77,15 +77,15 @@ inline void msm_plan_levels(MsmPlan& pl, uint32_t seg_len)
     }
 }
 
-// n_in caller terms; glv = true doubles the term count and halves the scalar width
-inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, bool glv = false)
+// n_in caller terms; every scalar is split into `parts` (1, 2 or 4) signed pieces of 256 / parts bits
+inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, uint32_t parts = 1)
 {
     MsmPlan pl;
     pl.n_in = n_in;
-    pl.glv = glv ? 1u : 0u;
-    pl.n = glv ? 2 * n_in : n_in;
+    pl.parts = parts;
+    pl.n = parts * n_in;
     pl.c = c;
-    pl.windows = ((glv ? 128u : 256u) + c - 1) / c;
+    pl.windows = (256u / parts + c - 1) / c;
     pl.half = 1u << (c - 1);
     pl.total = pl.windows * pl.half;
     // level-0 segment length: a power of two in [4, 64] that keeps the level-0 grid within one wave (~48 Ki threads)
@@ -175,7 +175,8 @@ C12_HD void u128_dec(uint32_t (&a)[4])  // a > 0
 C12_HD bool u128_is_zero(const uint32_t (&a)[4]) { return (a[0] | a[1] | a[2] | a[3]) == 0; }
 } // namespace detail
 
-C12_HD GlvHalves glv_split(const Scalar256& k)
+// k = q mu + rem, 0 <= rem < mu = x^2 (q < mu because r < mu^2)
+C12_HD void divmod_mu(const Scalar256& k, uint32_t (&q_out)[4], uint32_t (&rem_out)[4])
 {
     const uint32_t mu[4] = C12_X2_LIMBS, rc[5] = C12_X2_RECIP_LIMBS;
     // q = floor(k * floor(2^256 / mu) / 2^256)  (<= floor(k / mu), short by at most 2)
@@ -229,11 +230,20 @@ C12_HD GlvHalves glv_split(const Scalar256& k)
         for (int i = 0; i < 5; ++i)
             if (++q[i] != 0) break;
     }
+    for (int i = 0; i < 4; ++i) {
+        q_out[i] = q[i];
+        rem_out[i] = rem[i];
+    }
+}
+
+C12_HD GlvHalves glv_split(const Scalar256& k)
+{
+    const uint32_t mu[4] = C12_X2_LIMBS;
+    uint32_t k0[4], k1[4];
+    divmod_mu(k, k1, k0);
     GlvHalves h;
     uint32_t half[4];  // mu / 2
     for (int i = 0; i < 4; ++i) half[i] = (mu[i] >> 1) | (i < 3 ? (mu[i + 1] << 31) : 0u);
-    uint32_t k0[4] = {rem[0], rem[1], rem[2], rem[3]};
-    uint32_t k1[4] = {q[0], q[1], q[2], q[3]};   // q < mu: r / mu < mu
     h.neg0 = 0;
     if (detail::u128_gt(k0, half)) {
         detail::u128_sub(k0, mu, k0);   // k0 - mu = -(mu - k0)
@@ -267,21 +277,99 @@ C12_HD GlvHalves glv_split(const Scalar256& k)
     return h;
 }
 
+// ---- GLS split for G2 (replaces MIRACL's gs(), 3rd-party/miracl-core/pair_BLS12381.cpp:814-873) --------------------
+// On G2 the endomorphism psi (conjugate the coordinates, scale by f^-2 / f^-3; ECP2_frob, ecp2_BLS12381.cpp:579-590)
+// acts as multiplication by p = x = -z (mod r), z = |x| (64 bits).  k = k0 + k1 z + k2 z^2 + k3 z^3 (digits < z, since
+// r < z^4) is rebalanced to |k_i| <= z/2 + 1 < 2^63:  k_i > z/2: k_i -= z, k_(i+1) += 1;  for the top digit the carry is
+// z^4 = z^2 - 1 (mod r): k2 += 1, k0 -= 1.  Then  k P = sum_i k_i [z^i]P  with  [z^i]P = (-1)^i psi^i(P), so four signed
+// 16-bit windows cover each quarter and the Horner recombination needs 48 doublings instead of 240.
+struct ScalarParts {
+    uint32_t mag[4][4];   // magnitudes, little-endian limbs (upper limbs zero for the shorter pieces)
+    uint32_t neg[4];      // signs
+};
+
+C12_HD void gls_split(const Scalar256& k, ScalarParts& out)
+{
+    uint32_t hi[4], lo[4];
+    divmod_mu(k, hi, lo);                     // k = hi z^2 + lo, both < z^2
+    const unsigned __int128 z = (unsigned __int128)C12_X_ABS;
+    const unsigned __int128 L = ((unsigned __int128)lo[3] << 96) | ((unsigned __int128)lo[2] << 64) | ((unsigned __int128)lo[1] << 32) | lo[0];
+    const unsigned __int128 H = ((unsigned __int128)hi[3] << 96) | ((unsigned __int128)hi[2] << 64) | ((unsigned __int128)hi[1] << 32) | hi[0];
+    __int128 d[4] = {(__int128)(L % z), (__int128)(L / z), (__int128)(H % z), (__int128)(H / z)};
+    const __int128 zi = (__int128)z, half = zi >> 1;
+    for (int i = 0; i < 3; ++i)
+        if (d[i] > half) {
+            d[i] -= zi;
+            d[i + 1] += 1;
+        }
+    if (d[3] > half) {
+        d[3] -= zi;
+        d[2] += 1;
+        d[0] -= 1;
+    }
+    for (int i = 0; i < 4; ++i) {
+        const bool ng = d[i] < 0;
+        const uint64_t m = (uint64_t)(ng ? -d[i] : d[i]);
+        out.mag[i][0] = (uint32_t)m;
+        out.mag[i][1] = (uint32_t)(m >> 32);
+        out.mag[i][2] = 0;
+        out.mag[i][3] = 0;
+        out.neg[i] = ng ? 1u : 0u;
+    }
+}
+
+// the `parts` signed pieces of k (parts = 2: GLV halves, 4: GLS quarters)
+C12_HD void msm_split(const Scalar256& k, uint32_t parts, ScalarParts& out)
+{
+    if (parts == 4) {
+        gls_split(k, out);
+        return;
+    }
+    GlvHalves h = glv_split(k);
+    for (int i = 0; i < 4; ++i) {
+        out.mag[0][i] = h.a0[i];
+        out.mag[1][i] = h.a1[i];
+        out.mag[2][i] = 0;
+        out.mag[3][i] = 0;
+    }
+    out.neg[0] = h.neg0;
+    out.neg[1] = h.neg1;
+    out.neg[2] = out.neg[3] = 0;
+}
+
+// Scalar splits: the pipeline also needs the endomorphism images of every input point.
+//   G1, 2 pieces (GLV):  [mu]P = (beta X, -Y)
+//   G2, 4 pieces (GLS):  [z^q]P = (-1)^q psi^q(P)
+template <class F> struct MsmTraits;
+template <> struct MsmTraits<Fp> {
+    static constexpr uint32_t PARTS = 2;
+    static C12_HD Affine<Fp> endo(uint32_t, const Affine<Fp>& p) { return Affine<Fp>{fp_mul(p.x, fp_beta_m()), fp_neg(p.y)}; }
+};
+template <> struct MsmTraits<Fp2> {
+    static constexpr uint32_t PARTS = 4;
+    static C12_HD Affine<Fp2> endo(uint32_t q, const Affine<Fp2>& p)
+    {
+        if (q == 2) return Affine<Fp2>{mul_fp(p.x, psi2_x_m()), mul_fp(p.y, psi2_y_m())};
+        Fp2 cx = q == 1 ? psi_x_m() : psi3_x_m(), cy = q == 1 ? psi_y_m() : psi3_y_m();
+        return Affine<Fp2>{mul(conj(p.x), cx), neg(mul(conj(p.y), cy))};   // odd powers carry the sign of x = -z
+    }
+};
+
 // Body of the recode kernel for term i: writes W (key, value) pairs at out index w * n + i.
 // The w-major layout keeps each window's entries in term order before the (stable) sort.
-// With the GLV split on, term i yields two pipeline terms: i (point P_i, half k0) and n_in + i (point mu*P_i, half k1).
+// With a split on, term i yields `parts` pipeline terms: piece q at index q n_in + i (point [mu^q]P_i resp. [z^q]P_i).
 C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalars_be32, uint32_t* keys, uint32_t* vals)
 {
     Scalar256 s = scalar_from_be32(scalars_be32 + 32ull * i);
-    if (pl.glv) {
-        GlvHalves h = glv_split(s);
-        for (uint32_t part = 0; part < 2; ++part) {
-            const uint32_t(&mag)[4] = part ? h.a1 : h.a0;
-            const uint32_t sgn = part ? h.neg1 : h.neg0;
+    if (pl.parts > 1) {
+        ScalarParts sp;
+        msm_split(s, pl.parts, sp);
+        for (uint32_t part = 0; part < pl.parts; ++part) {
+            const uint32_t sgn = sp.neg[part];
             const uint32_t idx = i + part * pl.n_in;
             uint32_t carry = 0;
             for (uint32_t w = 0; w < pl.windows; ++w) {
-                uint32_t d = limbs_bits<4>(mag, w * pl.c, pl.c) + carry;
+                uint32_t d = limbs_bits<4>(sp.mag[part], w * pl.c, pl.c) + carry;
                 uint32_t neg = 0;
                 carry = 0;
                 if (d > pl.half) {

@@ -65,18 +65,8 @@ template <class F> __device__ Proj<F> block_sum_256(Proj<F> acc)
     return acc;
 }
 
-// GLV (G1 only): the pipeline also needs mu * P = (beta X, -Y) for every input point (msm_core.cuh, glv_split)
-template <class F> struct MsmTraits {
-    static constexpr bool GLV = false;
-    static __device__ Affine<F> endo(const Affine<F>& p) { return p; }
-};
-template <> struct MsmTraits<Fp> {
-    static constexpr bool GLV = true;
-    static __device__ Affine<Fp> endo(const Affine<Fp>& p) { return Affine<Fp>{fp_mul(p.x, fp_beta_m()), fp_neg(p.y)}; }
-};
-
 template <class F>
-__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t n, uint32_t glv, Affine<F>* __restrict__ pts,
+__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t n, uint32_t parts, Affine<F>* __restrict__ pts,
                                                       int* flags)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,7 +74,7 @@ __global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict_
     Affine<F> p;
     if (!Wire<F>::parse(p, bytes + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
     pts[i] = p;
-    if (glv) pts[n + i] = MsmTraits<F>::endo(p);   // the identity (0, 0) maps to itself
+    for (uint32_t q = 1; q < parts; ++q) pts[(size_t)q * n + i] = MsmTraits<F>::endo(q, p);   // the identity (0, 0) maps to itself
 }
 
 // defined once in msm_common.cu (kernels there are launched through these host functions)
@@ -350,11 +340,11 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
 // scratch bound for an n-term MSM under the current window setting (callers arena_begin with at least this much)
 template <class F> size_t msm_scratch_for(size_t n)
 {
-    if (n == 0 || n > (1ull << 26)) return 0;
-    constexpr bool glv = MsmTraits<F>::GLV;
-    uint32_t cbits = ctx().forced_window ? (uint32_t)ctx().forced_window : msm_choose_window(glv ? 2 * n : n, glv ? 128 : 256);
+    if (n == 0 || n > (1ull << 26) / MsmTraits<F>::PARTS * 2) return 0;
+    constexpr uint32_t parts = MsmTraits<F>::PARTS;
+    uint32_t cbits = ctx().forced_window ? (uint32_t)ctx().forced_window : msm_choose_window(parts * n, 256 / parts);
     if (cbits < 2 || cbits > 16) return 0;
-    return msm_scratch_bytes<F>(msm_make_plan((uint32_t)n, cbits, glv));
+    return msm_scratch_bytes<F>(msm_make_plan((uint32_t)n, cbits, parts));
 }
 
 // The caller has arena_begin()'d at least msm_scratch_for<F>(n) bytes beyond what it took itself.
@@ -373,12 +363,12 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         C12_CUDA(cudaMemsetAsync(d_out, 0, out_bytes, s));
         return C12381_OK;
     }
-    if (n_sz > (1ull << 26)) return set_error(C12381_EARG, "msm: n > 2^26 terms per call is not supported");
+    if (n_sz > (1ull << 26) / MsmTraits<F>::PARTS * 2) return set_error(C12381_EARG, "msm: too many terms per call (2^26 over G1, 2^25 over G2)");
     const uint32_t n = (uint32_t)n_sz;
-    constexpr bool glv = MsmTraits<F>::GLV;
-    uint32_t cbits = c.forced_window ? (uint32_t)c.forced_window : msm_choose_window(glv ? 2 * (uint64_t)n : n, glv ? 128 : 256);
+    constexpr uint32_t parts = MsmTraits<F>::PARTS;
+    uint32_t cbits = c.forced_window ? (uint32_t)c.forced_window : msm_choose_window((uint64_t)parts * n, 256 / parts);
     if (cbits < 2 || cbits > 16) return set_error(C12381_EARG, "msm: window width must be in [2, 16]");
-    const MsmPlan pl = msm_make_plan(n, cbits, glv);
+    const MsmPlan pl = msm_make_plan(n, cbits, parts);
     const size_t N = (size_t)pl.n * pl.windows;
 
     int rc;
@@ -414,7 +404,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     if (rc) return rc;
     if (points_ready) C12_CUDA(cudaStreamWaitEvent(s, points_ready, 0));
     C12_CUDA(cudaEventRecord(c.pev[3], s));
-    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.glv, pts, c.d_flags);
+    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.parts, pts, c.d_flags);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
@@ -495,7 +485,9 @@ int with_staged(const void* const* host_in, const size_t* in_bytes, int n_in, vo
     uint8_t* d_out = (uint8_t*)arena_take(out_bytes ? out_bytes : 4);
     rc = flags_reset(s);
     if (rc) return rc;
+    c.arena_depth++;
     rc = run(d_in, d_out, s);
+    c.arena_depth--;
     if (rc) {
         cudaStreamSynchronize(s);
         return rc;

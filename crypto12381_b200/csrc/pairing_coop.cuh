@@ -64,7 +64,7 @@ __device__ __forceinline__ Fp4 ld4(const Fp2* base, int i) { return Fp4{ld(base 
 __device__ __forceinline__ Fp2 mul_ip_if(bool e, const Fp2& v) { return select(e, mul_ip(v), v); }
 
 // ---- f *= line (coefficients at ln[0..2]) ----------------------------------------------------------------------------
-__device__ void sparse_mul(const Lane& L, const Fp2* ln, bool keep)
+__device__ __noinline__ void sparse_mul(Lane L, const Fp2* ln, bool keep)
 {
     const int r = L.r;
     Fp2 acc = mul(ld(ln), ld(L.s->f + r));
@@ -78,13 +78,33 @@ __device__ void sparse_mul(const Lane& L, const Fp2* ln, bool keep)
 // ---- dst = a * b, general (dst may alias a or b; uses x[] as the exchange area, so a, b, dst must not live there) ---------
 // Karatsuba over Fp4 (FP12_mul, fp12_BLS12381.cpp:246-298): lane r computes the r-th Fp4 product
 //   v0 = a0 b0, v1 = a1 b1, v2 = a2 b2, m0 = (a1+a2)(b1+b2), m1 = (a0+a1)(b0+b1), m2 = (a0+a2)(b0+b2)
-__device__ __forceinline__ void fp4_operands(const Fp2* a, int r, Fp4& u)
+// Operands are re-read from shared memory where they are needed instead of being held in registers: the live set stays
+// at two operands plus one partial sum, which is what lets three blocks (12 warps) share an SM's register file.
+struct Opnd {           // an Fp4 operand in shared memory: half h = p[h * stride] (+ q[h * stride] when q != nullptr)
+    const Fp2* p;
+    const Fp2* q;
+    int stride;
+};
+__device__ __forceinline__ Fp2 fetch(const Opnd& o, int h)
 {
-    // r: 0,1,2 -> a_r; 3 -> a1+a2; 4 -> a0+a1; 5 -> a0+a2
-    const int i = r < 3 ? r : (r == 3 ? 1 : 0);
-    const int j = r == 5 ? 2 : (r == 4 ? 1 : 2);
-    Fp4 p = ld4(a, i), q = ld4(a, j);
-    u = r < 3 ? p : add(p, q);
+    Fp2 v = ld(o.p + h * o.stride);
+    if (o.q) v = add(v, ld(o.q + h * o.stride));
+    return v;
+}
+// the Fp4 product U V (times two when `twice`) -> x[2 slot], x[2 slot + 1]
+__device__ __forceinline__ void fp4_product_to_x(Lane L, int slot, const Opnd& U, const Opnd& V, bool twice, bool store)
+{
+    Fp2 t0 = mul(fetch(U, 0), fetch(V, 0));
+    Fp2 t1 = mul(fetch(U, 1), fetch(V, 1));
+    Fp2 lo = add(t0, mul_ip(t1));
+    Fp2 s = add(t0, t1);
+    if (twice) lo = dbl(lo);
+    st(L.s->x + 2 * slot, lo, L.on && store);
+    Fp2 ua = add(fetch(U, 0), fetch(U, 1));
+    Fp2 ub = add(fetch(V, 0), fetch(V, 1));
+    Fp2 hi = sub(mul(ua, ub), s);
+    if (twice) hi = dbl(hi);
+    st(L.s->x + 2 * slot + 1, hi, L.on && store);
 }
 __device__ __forceinline__ Fp2 assemble_product(const Fp2* x, int r)
 {
@@ -107,39 +127,39 @@ __device__ __forceinline__ Fp2 assemble_product(const Fp2* x, int r)
     Fp2 t = sub(sub(ld(x + 10 + h), ld(x + h)), ld(x + 4 + h));
     return add(t, ld(x + 2 + h));
 }
-__device__ void full_mul(const Lane& L, Fp2* dst, const Fp2* a, const Fp2* b)
+__device__ __noinline__ void full_mul(Lane L, Fp2* dst, const Fp2* a, const Fp2* b)
 {
-    Fp4 u, v;
-    fp4_operands(a, L.r, u);
-    fp4_operands(b, L.r, v);
-    Fp4 p = mul(u, v);
+    // r: 0,1,2 -> a_r; 3 -> a1+a2; 4 -> a0+a1; 5 -> a0+a2
+    const int r = L.r;
+    const int i = r < 3 ? r : (r == 3 ? 1 : 0);
+    const int j = r < 3 ? -1 : (r == 4 ? 1 : 2);
+    const Opnd U = {a + i, j < 0 ? nullptr : a + j, 3}, V = {b + i, j < 0 ? nullptr : b + j, 3};
+    fp4_product_to_x(L, r, U, V, false, true);
     __syncwarp();
-    st(L.s->x + 2 * L.r, p.a, L.on);
-    st(L.s->x + 2 * L.r + 1, p.b, L.on);
+    Fp2 c = assemble_product(L.s->x, r);
     __syncwarp();
-    Fp2 c = assemble_product(L.s->x, L.r);
-    __syncwarp();
-    st(dst + L.r, c, L.on);
+    st(dst + r, c, L.on);
     __syncwarp();
 }
 
 // ---- dst = a^2, general (Chung-Hasan SQR2, FP12_sqr, fp12_BLS12381.cpp:190): five Fp4 products, lane 5 idles ----------
-//   s0 = a0^2, s1' = a0 a1, s2 = (a0 - a1 + a2)^2, s3' = a1 a2, s4 = a2^2   (s1 = 2 s1', s3 = 2 s3')
+//   s0 = a0^2, s1 = 2 a0 a1, s2 = (a0 - a1 + a2)^2, s3 = 2 a1 a2, s4 = a2^2
 //   a' = s0 + j s3, b' = s1 + j s4, c' = s1 + s2 + s3 - s0 - s4
-__device__ void full_sqr(const Lane& L, Fp2* dst, const Fp2* a)
+// Lane 2 first parks d = a0 - a1 + a2 in x[10], x[11] (free until the partial products land in x[0..9]).
+__device__ __noinline__ void full_sqr(Lane L, Fp2* dst, const Fp2* a)
 {
     const int r = L.r;
-    Fp4 a0 = ld4(a, 0), a1 = ld4(a, 1), a2 = ld4(a, 2);
-    Fp4 d = add(sub(a0, a1), a2);
-    Fp4 u = r == 0 ? a0 : (r == 1 ? a0 : (r == 2 ? d : (r == 3 ? a1 : a2)));
-    Fp4 v = r == 0 ? a0 : (r == 1 ? a1 : (r == 2 ? d : (r == 3 ? a2 : a2)));
-    Fp4 p = mul(u, v);
-    if (r == 1 || r == 3) p = dbl(p);
-    __syncwarp();
-    if (r < 5) {
-        st(L.s->x + 2 * r, p.a, L.on);
-        st(L.s->x + 2 * r + 1, p.b, L.on);
+    if (r == 2) {
+        st(L.s->x + 10, add(sub(ld(a), ld(a + 1)), ld(a + 2)), L.on);
+        st(L.s->x + 11, add(sub(ld(a + 3), ld(a + 4)), ld(a + 5)), L.on);
     }
+    __syncwarp();
+    // operands: coefficients of `a` three apart (lanes 0, 1, 3, 4), or the parked d, halves one apart (lane 2)
+    const int iu = r == 3 ? 1 : (r >= 4 ? 2 : 0);       // 0: a0, 1: a0, 3: a1, 4: a2
+    const int iv = r == 0 ? 0 : (r == 1 ? 1 : 2);       // 0: a0, 1: a1, 3: a2, 4: a2
+    const Opnd U = {r == 2 ? L.s->x + 10 : a + iu, nullptr, r == 2 ? 1 : 3};
+    const Opnd V = {r == 2 ? L.s->x + 10 : a + iv, nullptr, r == 2 ? 1 : 3};
+    fp4_product_to_x(L, r, U, V, r == 1 || r == 3, r < 5);
     __syncwarp();
     const Fp2* x = L.s->x;      // x[2q], x[2q+1] = halves of s_q
     const int h = r >= 3 ? 1 : 0, q = r % 3;
@@ -158,7 +178,7 @@ __device__ void full_sqr(const Lane& L, Fp2* dst, const Fp2* a)
 // ---- s = s^2 on the cyclotomic subgroup (Granger-Scott, FP12_usqr, fp12_BLS12381.cpp:147-187), in place ------------
 //   A = a0^2, B = j a2^2, C = a1^2;  a' = 3A + 2 nconj(a0), b' = 3B + 2 conj(a1), c' = 3C + 2 nconj(a2)
 //   Fp4 square (y0, y1)^2 = (P' - P - xi P, 2 P) with P = y0 y1, P' = (y0 + y1)(y0 + xi y1): one product per lane.
-__device__ void cyclo_sqr(const Lane& L, Fp2* s)
+__device__ __noinline__ void cyclo_sqr(Lane L, Fp2* s)
 {
     const int r = L.r;
     // lanes (0,1) square a0 = (f0, f3); lanes (2,3) square a2 = (f2, f5); lanes (4,5) square a1 = (f1, f4)
@@ -197,18 +217,18 @@ __device__ void cyclo_sqr(const Lane& L, Fp2* s)
 }
 
 // conj (p^6 Frobenius): w -> -w
-__device__ void conj_inplace(const Lane& L, Fp2* s)
+__device__ void conj_inplace(Lane L, Fp2* s)
 {
     if (L.r & 1) st(s + L.r, neg(ld(s + L.r)), L.on);
     __syncwarp();
 }
-__device__ void copy12(const Lane& L, Fp2* dst, const Fp2* src)
+__device__ void copy12(Lane L, Fp2* dst, const Fp2* src)
 {
     st(dst + L.r, ld(src + L.r), L.on);
     __syncwarp();
 }
 // x^p (FP12_frob, fp12_BLS12381.cpp:867-881): f_r -> conj(f_r) * gamma_r, gamma = (1, c1, c2, c3, c1 c3, c2 c3)
-__device__ void frob_inplace(const Lane& L, Fp2* s)
+__device__ __noinline__ void frob_inplace(Lane L, Fp2* s)
 {
     const int r = L.r;
     Fp2 c1 = frob_c1_m(), c2 = frob_c2_m(), c3 = frob_c3_m();
@@ -223,9 +243,9 @@ __device__ void frob_inplace(const Lane& L, Fp2* s)
 }
 
 // dst = 1 / src: lane 0 of the group runs the scalar FP12_inv body once per instance (one of ~2,000 steps)
-__device__ void inv12(const Lane& L, Fp2* dst, const Fp2* src)
+__device__ __noinline__ void inv12(Lane L, Fp2* dst, const Fp2* src)
 {
-    if (L.r == 0) {
+    if (L.r == 0 && L.on) {
         Fp12 v = Fp12{Fp4{ld(src + 0), ld(src + 3)}, Fp4{ld(src + 1), ld(src + 4)}, Fp4{ld(src + 2), ld(src + 5)}};
         v = inv(v);
         st(dst + 0, v.a.a, L.on);
@@ -239,7 +259,7 @@ __device__ void inv12(const Lane& L, Fp2* dst, const Fp2* src)
 }
 
 // acc = base^|x| for unitary base (pow_x_abs in pairing.cuh); acc, base distinct slots outside x[]
-__device__ void pow_x(const Lane& L, Fp2* acc, const Fp2* base)
+__device__ void pow_x(Lane L, Fp2* acc, const Fp2* base)
 {
     const uint64_t e = C12_X_ABS;
     copy12(L, acc, base);
@@ -251,8 +271,8 @@ __device__ void pow_x(const Lane& L, Fp2* acc, const Fp2* base)
 }
 
 // ---- final exponentiation of s->f in place (PAIR_fexp, pair_BLS12381.cpp:629-755; final_exp in pairing.cuh) ---------
-// slots: F = s->f, S1 = s->t[0..5], S2 = s->t[6..11]; g = 576-byte global scratch of this instance (the output buffer)
-__device__ void final_exp_coop(const Lane& L, Fp2* g)
+// slots: F = s->f, S1 = s->t[0..5], S2 = s->t[6..11]; g = this instance's six-coefficient global scratch
+__device__ void final_exp_coop(Lane L, Fp2* g)
 {
     Fp2* F = L.s->f;
     Fp2* S1 = L.s->t;
@@ -301,7 +321,7 @@ __device__ void final_exp_coop(const Lane& L, Fp2* g)
 
 // ---- G2 point steps with line evaluation: lane j < k owns pair j ---------------------------------------------------------
 // PAIR_double + PAIR_line (pair_BLS12381.cpp:40-78,119-144): line through T,T evaluated at P = (px, py), then T <- 2T.
-__device__ void point_double_line(Fp2* T, Fp2* ln, const Fp& px, const Fp& py, bool on)
+__device__ __noinline__ void point_double_line(Fp2* T, Fp2* ln, const Fp& px, const Fp& py, bool on)
 {
     Fp2 Y = ld(T + 1), Z = ld(T + 2);
     Fp2 yz = mul(Y, Z);
@@ -321,16 +341,20 @@ __device__ void point_double_line(Fp2* T, Fp2* ln, const Fp& px, const Fp& py, b
     st(T, dbl(mul(t0, xy)), on);                            // X3
 }
 
-// PAIR_add + PAIR_line (pair_BLS12381.cpp:81-144): line through T and the affine Q (sign applied by the caller), T <- T + Q
-__device__ void point_add_line(Fp2* T, Fp2* ln, const Affine<Fp2>& Q, const Fp& px, const Fp& py, bool on)
+// PAIR_add + PAIR_line (pair_BLS12381.cpp:81-144): line through T and B = +-Q, T <- T + B.  B is what ECP2_affine leaves:
+// (x, y, 1), or (0 : +-1 : 0) for the identity - the reference runs the same formulas on it, so do we.
+__device__ __noinline__ void point_add_line(Fp2* T, Fp2* ln, const Affine<Fp2>& Q, bool negate, const Fp& px, const Fp& py, bool on)
 {
     Proj<Fp2> A = Proj<Fp2>{ld(T), ld(T + 1), ld(T + 2)};
-    Fp2 x1 = sub(A.x, mul(A.z, Q.x));
-    Fp2 y1 = sub(A.y, mul(A.z, Q.y));
+    const bool qinf = affine_is_inf(Q);
+    Fp2 bx = Q.x, by = qinf ? fp2_one() : Q.y;
+    if (negate) by = neg(by);
+    Fp2 x1 = sub(A.x, mul(A.z, bx));
+    Fp2 y1 = sub(A.y, mul(A.z, by));
     st(ln, mul_fp(mul_ip(x1), py), on);
-    st(ln + 1, sub(mul(y1, Q.x), mul(x1, Q.y)), on);
+    st(ln + 1, sub(mul(y1, bx), mul(x1, by)), on);
     st(ln + 2, mul_fp(neg(y1), px), on);
-    Proj<Fp2> R = affine_is_inf(Q) ? A : proj_add_affine_nz(A, Q);
+    Proj<Fp2> R = qinf ? proj_add(A, Proj<Fp2>{bx, by, fp2_zero()}) : proj_add_affine_nz(A, Affine<Fp2>{bx, by});
     st(T, R.x, on);
     st(T + 1, R.y, on);
     st(T + 2, R.z, on);
@@ -343,7 +367,7 @@ struct PairIn {
 };
 
 // Miller product of pairs [0, kk) of this instance into s->f (un-exponentiated, conjugated).  Lanes j < kk own pair j.
-__device__ void miller_coop(const Lane& L, const PairIn* pin, int kk)
+__device__ void miller_coop(Lane L, const PairIn* pin, int kk)
 {
     const int j = L.r;
     const bool mine = j < kk && j < CHUNK;
@@ -376,8 +400,7 @@ __device__ void miller_coop(const Lane& L, const PairIn* pin, int kk)
         if (bt != 0) {
             if (mine) {
                 Affine<Fp2> Q = L.on ? pin[j].Q : affine_inf<Fp2>();
-                if (bt < 0) Q.y = neg(Q.y);
-                point_add_line(s->t + 3 * j, s->x + 3 * j, Q, px, py, L.on);
+                point_add_line(s->t + 3 * j, s->x + 3 * j, Q, bt < 0, px, py, L.on);
             }
             __syncwarp();
 #pragma unroll 1

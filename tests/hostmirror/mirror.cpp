@@ -15,29 +15,27 @@
 using namespace c12;
 
 namespace {
-MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, bool glv)
+MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, uint32_t parts)
 {
-    MsmPlan pl = msm_make_plan(n, c, glv);
+    MsmPlan pl = msm_make_plan(n, c, parts);
     if (seg_len) msm_plan_levels(pl, seg_len > pl.half ? pl.half : seg_len);   // a power of two
     return pl;
 }
 
-Affine<Fp> endo(const Affine<Fp>& p) { return Affine<Fp>{fp_mul(p.x, fp_beta_m()), fp_neg(p.y)}; }   // MsmTraits<Fp>::endo
-Affine<Fp2> endo(const Affine<Fp2>& p) { return p; }
-
-template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, bool glv = false)
+// parts = 1: no split; MsmTraits<F>::PARTS: the split the device entries use
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1)
 {
     using W = Wire<F>;
     if (n_in == 0) {
         W::compress(out, affine_inf<F>());
         return 0;
     }
-    MsmPlan pl = make_plan(n_in, c, seg_len, glv);
+    MsmPlan pl = make_plan(n_in, c, seg_len, parts);
     const uint32_t n = pl.n;
     std::vector<Affine<F>> P(n);
     for (uint32_t i = 0; i < n_in; ++i) {
         if (!W::parse(P[i], pts + (size_t)W::AFFINE * i)) return -1;
-        if (glv) P[n_in + i] = endo(P[i]);
+        for (uint32_t q = 1; q < parts; ++q) P[(size_t)q * n_in + i] = MsmTraits<F>::endo(q, P[i]);
     }
     size_t N = (size_t)n * pl.windows;
     std::vector<uint32_t> keys(N), vals(N);
@@ -204,6 +202,22 @@ void hm_glv_split(const uint8_t* k32, uint8_t* a0, uint8_t* a1, uint32_t* signs)
 int hm_g1_msm_auto(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint8_t* out49)
 {
     // exactly the device entry's plan: GLV split on, window from msm_choose_window(2n, 128)
-    return msm<Fp>(p, s, n, c ? c : msm_choose_window(2 * (uint64_t)n, 128), 0, out49, true);
+    return msm<Fp>(p, s, n, c ? c : msm_choose_window(2 * (uint64_t)n, 128), 0, out49, MsmTraits<Fp>::PARTS);
+}
+// the G2 device entry's plan: GLS split in four, window from msm_choose_window(4n, 64)
+int hm_g2_msm_auto(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint8_t* out97)
+{
+    return msm<Fp2>(p, s, n, c ? c : msm_choose_window(4 * (uint64_t)n, 64), 0, out97, MsmTraits<Fp2>::PARTS);
+}
+// k (32 B BE) -> |k_i| (8 B BE each) and signs, k = sum_i +-k_i z^i (mod r)
+void hm_gls_split(const uint8_t* k32, uint8_t* mags32, uint32_t* signs)
+{
+    ScalarParts sp;
+    gls_split(scalar_from_be32(k32), sp);
+    for (int q = 0; q < 4; ++q) {
+        uint64_t m = (uint64_t)sp.mag[q][0] | ((uint64_t)sp.mag[q][1] << 32);
+        for (int b = 0; b < 8; ++b) mags32[8 * q + 7 - b] = (uint8_t)(m >> (8 * b));
+        signs[q] = sp.neg[q];
+    }
 }
 }

@@ -36,7 +36,12 @@ class MirrorBackend:
 
     @staticmethod
     def msm2(points, scalars, c=0):
-        return hm.g2_msm(points, scalars, c or max(4, hm.lib().hm_choose_window(len(scalars) // 32)))
+        n = len(scalars) // 32
+        out = ctypes.create_string_buffer(97)
+        assert hm.lib().hm_g2_msm_auto(points, scalars, n, c, out) == 0    # the device entry's plan: GLS split in four
+        plain = hm.g2_msm(points, scalars, c or max(4, hm.lib().hm_choose_window(n)))   # and the unsplit pipeline
+        assert plain == out.raw
+        return out.raw
 
     @staticmethod
     def miller(g1, g2, k):
@@ -106,6 +111,23 @@ def test_glv_split():
         k0, k1 = int.from_bytes(a0.raw, "big"), int.from_bytes(a1.raw, "big")
         assert k0 < 1 << 127 and k1 < 1 << 127, hex(k)
         assert ((-k0 if sg[0] else k0) + (-k1 if sg[1] else k1) * X2 - k) % ps.R == 0, hex(k)
+
+
+def test_gls_split():
+    """k = sum_i +-k_i z^i (mod r) with every |k_i| below 2^63 (four signed 16-bit windows never overflow)."""
+    l = hm.lib()
+    Z = 0xD201000000010000
+    rnd = random.Random(12)
+    edge = [0, 1, 2, ps.R - 1, ps.R - 2, Z, Z - 1, Z + 1, Z // 2, Z // 2 + 1, Z * Z, Z ** 3, Z ** 3 * (Z // 2 + 1), Z ** 3 * (Z // 2) + Z * Z * (Z // 2 + 1),
+            (Z // 2 + 1) * (1 + Z + Z * Z + Z ** 3), (Z - 1) * (1 + Z + Z * Z) , 1 << 63, (1 << 64) - 1, 1 << 254]
+    for k in edge + [rnd.randrange(ps.R) for _ in range(3000)]:
+        k %= ps.R
+        mags = ctypes.create_string_buffer(32)
+        sg = (ctypes.c_uint32 * 4)()
+        l.hm_gls_split(k.to_bytes(32, "big"), mags, sg)
+        ks = [int.from_bytes(mags.raw[8 * q:8 * q + 8], "big") for q in range(4)]
+        assert all(m < 1 << 63 for m in ks), hex(k)
+        assert (sum((-m if sg[q] else m) * Z ** q for q, m in enumerate(ks)) - k) % ps.R == 0, hex(k)
 
 
 def test_pairing_golden():
