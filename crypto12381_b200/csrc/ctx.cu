@@ -187,6 +187,8 @@ void c12381_shutdown(void)
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
     if (c.arena) cudaFree(c.arena);
+    for (auto& t : c.fb_table)
+        if (t) cudaFree(t);
     if (c.d_flags) cudaFree(c.d_flags);
     if (c.h_flags) cudaFreeHost(c.h_flags);
     for (auto& ev : c.ev)

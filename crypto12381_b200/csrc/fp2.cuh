@@ -22,10 +22,12 @@ C12_HD Fp inv(const Fp& a) { return fp_inv(a); }
 // ---- Fp2 ------------------------------------------------------------------------------------------------
 C12_HD Fp2 fp2_zero() { return Fp2{fp_zero(), fp_zero()}; }
 C12_HD Fp2 fp2_one() { return Fp2{fp_one(), fp_zero()}; }
+// Additive operations stay inline: as by-value calls they cost ~70 register moves each, no smaller than the inlined
+// carry chains, and the pairing kernels measured 3-5 % slower (profiles/r01n).
 C12_HD Fp2 add(const Fp2& x, const Fp2& y) { return Fp2{fp_add(x.a, y.a), fp_add(x.b, y.b)}; }
 C12_HD Fp2 sub(const Fp2& x, const Fp2& y) { return Fp2{fp_sub(x.a, y.a), fp_sub(x.b, y.b)}; }
 C12_HD Fp2 neg(const Fp2& x) { return Fp2{fp_neg(x.a), fp_neg(x.b)}; }
-C12_HD Fp2 dbl(const Fp2& x) { return Fp2{fp_dbl(x.a), fp_dbl(x.b)}; }
+C12_HD Fp2 dbl(const Fp2& x) { return add(x, x); }
 C12_HD Fp2 conj(const Fp2& x) { return Fp2{x.a, fp_neg(x.b)}; }
 C12_HD bool is_zero(const Fp2& x) { return fp_is_zero(x.a) && fp_is_zero(x.b); }
 C12_HD bool eq(const Fp2& x, const Fp2& y) { return fp_eq(x.a, y.a) && fp_eq(x.b, y.b); }

@@ -305,14 +305,53 @@ __global__ void __launch_bounds__(128) k_scalar_mul(const uint8_t* __restrict__ 
         atomicOr(flags, FLAG_BAD_POINT);
 }
 
+// ---- fixed base g^x (the `select` path, g1_point.hpp:355-369 / g2_point.hpp:129-143) ------------------------------
+// A per-context table  T[w][d-1] = d 2^(8w) G  (w < 32, d = 1..128, affine, Montgomery form) is built once on the
+// device; a scalar is recoded into 32 signed 8-bit digits and g^x is 32 mixed additions - no doublings.
+constexpr uint32_t FB_WINDOWS = 32, FB_HALF = 128;
+
+template <class F> __global__ void __launch_bounds__(128) k_fixed_base_table(Affine<F>* __restrict__ table)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= FB_WINDOWS * FB_HALF) return;
+    const uint32_t w = t / FB_HALF, d = t % FB_HALF + 1;
+    Scalar256 k;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k.v[i] = 0;
+    // d << 8w  (d <= 128 fits 8 bits + 1)
+    const uint32_t bit = 8 * w;
+    k.v[bit >> 5] = d << (bit & 31u);
+    if ((bit & 31u) > 23 && (bit >> 5) + 1 < 8) k.v[(bit >> 5) + 1] = d >> (32 - (bit & 31u));
+    table[t] = proj_to_affine(proj_scalar_mul(generator<F>(), k));
+}
+
 template <class F>
-__global__ void __launch_bounds__(128) k_fixed_base(const uint8_t* __restrict__ scalars, uint32_t n, uint8_t* __restrict__ out, int* flags)
+__global__ void __launch_bounds__(128) k_fixed_base(const uint8_t* __restrict__ scalars, uint32_t n, const Affine<F>* __restrict__ table,
+                                                    uint8_t* __restrict__ out, int* flags)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Scalar256 k = scalar_from_be32(scalars + 32ull * i);
     if (!scalar_is_canonical(k)) atomicOr(flags, FLAG_BAD_SCALAR);
-    fixed_base_body<F>(scalars + 32ull * i, out + (size_t)Wire<F>::AFFINE * i);
+    XYZZ<F> acc = xyzz_inf<F>();
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (uint32_t w = 0; w < FB_WINDOWS; ++w) {
+        uint32_t d = ((k.v[w >> 2] >> ((w & 3u) * 8)) & 255u) + carry;
+        carry = 0;
+        bool ng = false;
+        if (d > FB_HALF) {          // (128, 256] -> d - 256 in (-128, 0]
+            d = 256u - d;
+            ng = true;
+            carry = 1;
+        }
+        if (d == 0) continue;
+        Affine<F> pt = table[w * FB_HALF + d - 1];
+        if (ng) pt.y = neg(pt.y);
+        xyzz_madd(acc, pt);
+    }
+    // scalars are < r < 2^255, so the top digit is at most 0x73 + 1 and never carries out
+    Wire<F>::serialize(out + (size_t)Wire<F>::AFFINE * i, proj_to_affine(xyzz_to_proj(acc)));
 }
 
 // ---- host pipeline ------------------------------------------------------------------------------------------
@@ -452,12 +491,24 @@ int scalar_mul_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n, 
     return C12381_OK;
 }
 
+// per-context device tables (freed by c12381_shutdown)
+template <class F> Affine<F>*& fixed_base_table_slot();
+template <> inline Affine<Fp>*& fixed_base_table_slot<Fp>() { return reinterpret_cast<Affine<Fp>*&>(ctx().fb_table[0]); }
+template <> inline Affine<Fp2>*& fixed_base_table_slot<Fp2>() { return reinterpret_cast<Affine<Fp2>*&>(ctx().fb_table[1]); }
+
 template <class F> int fixed_base_run(const uint8_t* d_scalars, size_t n, uint8_t* d_out, cudaStream_t s)
 {
     Ctx& c = ctx();
     if (n == 0) return C12381_OK;
     if (n > 0x7fffffffull) return set_error(C12381_EARG, "fixed_base: too many terms");
-    k_fixed_base<F><<<cdiv(n, 128), 128, 0, s>>>(d_scalars, (uint32_t)n, d_out, c.d_flags);
+    Affine<F>*& table = fixed_base_table_slot<F>();
+    if (!table) {   // first use on this context: build the window table (4,096 scalar multiplications, once)
+        C12_CUDA(cudaMalloc(&table, sizeof(Affine<F>) * FB_WINDOWS * FB_HALF));
+        k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(table);
+        C12_LAUNCHED();
+        C12_CUDA(cudaStreamSynchronize(s));   // later calls may come on other streams
+    }
+    k_fixed_base<F><<<cdiv(n, 128), 128, 0, s>>>(d_scalars, (uint32_t)n, table, d_out, c.d_flags);
     C12_LAUNCHED();
     return C12381_OK;
 }

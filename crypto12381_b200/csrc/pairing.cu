@@ -198,15 +198,24 @@ __global__ void __launch_bounds__(PC_THREADS, C12_PAIR_BLOCKS) k_gt_pow_coop(con
     pc_emit(L, 1, b, out);
 }
 
-// C12381_PAIRING=scalar selects the thread-per-instance kernels (A/B measurements, debugging)
-static bool use_scalar_kernels()
+// Two implementations of every entry: thread-per-instance (pairing.cuh bodies) and six-lanes-per-instance
+// (pairing_coop.cuh).  At large batch sizes they measure within 5 % of each other (profiles/r01n: 1.88 M against
+// 1.81 M pairings/s at 2^16 x 4), the former slightly ahead; below ~16 instances per SM the cooperative kernels win by
+// having six times the parallelism per instance (a single pairing is ~2.5x faster).  C12381_PAIRING=scalar|coop forces
+// one of them.
+constexpr size_t PAIRING_COOP_BELOW = 148 * 64;
+
+static int g_pairing_kernel = -1;   // 0 automatic, 1 thread-per-instance, 2 cooperative (c12381_set_pairing_kernel)
+
+static bool use_scalar_kernels(size_t B)
 {
-    static int v = -1;
-    if (v < 0) {
+    if (g_pairing_kernel < 0) {
         const char* e = getenv("C12381_PAIRING");
-        v = (e && e[0] == 's') ? 1 : 0;
+        g_pairing_kernel = !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'c' ? 2 : 0));
     }
-    return v == 1;
+    if (g_pairing_kernel == 1) return true;
+    if (g_pairing_kernel == 2) return false;
+    return B >= PAIRING_COOP_BELOW;
 }
 
 static int pc_configure()
@@ -230,7 +239,7 @@ static int pairing_run(const uint8_t* d_g1, const uint8_t* d_g2, size_t B, int k
     if (k < 1 || k > C12381_MAX_PAIRS) return set_error(C12381_EARG, "pairing: k must be in [1, C12381_MAX_PAIRS]");
     if (B == 0) return C12381_OK;
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "pairing: too many instances");
-    if (use_scalar_kernels()) {
+    if (use_scalar_kernels(B)) {
         k_pairing<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(d_g1, d_g2, (uint32_t)B, (uint32_t)k, mode, d_out, ctx().d_flags);
         C12_LAUNCHED();
         return C12381_OK;
@@ -272,7 +281,7 @@ static int final_exp_run(const uint8_t* d_in, size_t B, uint8_t* d_out, cudaStre
 {
     if (B == 0) return C12381_OK;
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "final_exp: too many instances");
-    if (use_scalar_kernels()) {
+    if (use_scalar_kernels(B)) {
         k_final_exp<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(d_in, (uint32_t)B, d_out);
         C12_LAUNCHED();
         return C12381_OK;
@@ -289,7 +298,7 @@ static int gt_mul_run(const uint8_t* a, const uint8_t* b, size_t B, uint8_t* d_o
 {
     if (B == 0) return C12381_OK;
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "gt_mul: too many instances");
-    if (use_scalar_kernels()) {
+    if (use_scalar_kernels(B)) {
         k_gt_mul<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, b, (uint32_t)B, d_out);
         C12_LAUNCHED();
         return C12381_OK;
@@ -304,7 +313,7 @@ static int gt_pow_run(const uint8_t* a, const uint8_t* sc, size_t B, uint8_t* d_
 {
     if (B == 0) return C12381_OK;
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "gt_pow: too many instances");
-    if (use_scalar_kernels()) {
+    if (use_scalar_kernels(B)) {
         k_gt_pow<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, sc, (uint32_t)B, d_out, ctx().d_flags);
         C12_LAUNCHED();
         return C12381_OK;
@@ -321,6 +330,7 @@ static int gt_pow_run(const uint8_t* a, const uint8_t* sc, size_t B, uint8_t* d_
 using namespace c12;
 
 extern "C" {
+void c12381_set_pairing_kernel(int mode) { g_pairing_kernel = mode == 1 || mode == 2 ? mode : 0; }
 int c12381_miller_batch(const uint8_t* g1s, const uint8_t* g2s, size_t B, int k, uint8_t* out576) { return pairing_host(g1s, g2s, B, k, 0, out576); }
 int c12381_pairing_product_batch(const uint8_t* g1s, const uint8_t* g2s, size_t B, int k, uint8_t* out576) { return pairing_host(g1s, g2s, B, k, 1, out576); }
 int c12381_pairing_check_batch(const uint8_t* g1s, const uint8_t* g2s, size_t B, int k, uint8_t* verdicts) { return pairing_host(g1s, g2s, B, k, 2, verdicts); }

@@ -112,6 +112,10 @@ C12381_API int c12381_final_exp_batch_dev(const uint8_t* d_in576, size_t B, uint
 C12381_API int c12381_pairing_product_batch_dev(const uint8_t* d_g1s, const uint8_t* d_g2s, size_t B, int k, uint8_t* d_out576, void* stream);
 C12381_API int c12381_pairing_check_batch_dev(const uint8_t* d_g1s, const uint8_t* d_g2s, size_t B, int k, uint8_t* d_verdicts, void* stream);
 
+/* testing/tuning knob: which kernels serve the pairing / GT entries.  0 = automatic (by batch size), 1 = one thread per
+ * instance, 2 = six cooperating lanes per instance with the state in shared memory.  Same results either way. */
+C12381_API void c12381_set_pairing_kernel(int mode);
+
 /* ---- GT helpers ------------------------------------------------------------------------------------------- */
 /* out[b] = a[b] * b[b].  Replaces multiply(fp12&, fp12&) -> FP12_mul (src/miracl_core_interface.cpp:256-259). */
 C12381_API int c12381_gt_mul_batch(const uint8_t* a576, const uint8_t* b576, size_t B, uint8_t* out576);

@@ -87,7 +87,15 @@ def test_msm_golden_all_windows(cuda):
     ps.check_msm(cuda, windows=(0, 2, 3, 5, 8, 9, 13, 16))
 
 
-def test_pairing_golden(cuda):
+@pytest.fixture(params=[1, 2], ids=["thread-per-instance", "cooperative"])
+def pairing_kernel(request):
+    from crypto12381_b200 import _lib
+    _lib.lib().c12381_set_pairing_kernel(request.param)
+    yield request.param
+    _lib.lib().c12381_set_pairing_kernel(0)
+
+
+def test_pairing_golden(cuda, pairing_kernel):
     ps.check_pairing(cuda)
 
 
@@ -133,7 +141,7 @@ def test_mul_batch_vs_reference(cuda):
 
 @needs_ref
 @pytest.mark.parametrize("k", [1, 2, 3, 4, 8])
-def test_pairing_products_vs_reference(cuda, k):
+def test_pairing_products_vs_reference(cuda, k, pairing_kernel):
     t = ref.hardware_threads()
     B = 16
     a, b = ref.random_scalars(f"pair-g1-{k}", B * k), ref.random_scalars(f"pair-g2-{k}", B * k)
@@ -249,7 +257,7 @@ def test_skewed_scalars_and_repeated_points(cuda):
     assert cuda.msm1(same, ss) == cuda.mul1(pts[:96], be32(sum(ints(ss)) % R))
 
 
-def test_pairing_check_full_batch(cuda):
+def test_pairing_check_full_batch(cuda, pairing_kernel):
     """2^12 instances x 4 pairs with  Π_j e(a_j G1, b_j G2) · e(-(Σ a_j b_j) G1, G2) == 1; flipped instances fail."""
     B, k = 1 << 12, 4
     dv = cuda.device
