@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(128) k_accumulate(uint32_t total, const uint32
 
 // level 0 of the bucket reduction: one thread per (window, segment of seg_len buckets)
 template <class F>
-__global__ void __launch_bounds__(128, 3) k_reduce_level0(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ scratch)
+__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? 3 : 1) k_reduce_level0(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ scratch)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= pl.segs) return;

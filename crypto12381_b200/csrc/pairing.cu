@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(PC_THREADS, C12_PAIR_BLOCKS) k_gt_pow_coop(con
 // 1.81 M pairings/s at 2^16 x 4), the former slightly ahead; below ~16 instances per SM the cooperative kernels win by
 // having six times the parallelism per instance (a single pairing is ~2.5x faster).  C12381_PAIRING=scalar|coop forces
 // one of them.
-constexpr size_t PAIRING_COOP_BELOW = 148 * 64;
+constexpr size_t PAIRING_COOP_BELOW = 16384 + 1;
 
 static int g_pairing_kernel = -1;   // 0 automatic, 1 thread-per-instance, 2 cooperative (c12381_set_pairing_kernel)
 
