@@ -100,6 +100,61 @@ def generator_power2(values: bytes) -> bytes:
     return out.raw[:G2_AFFINE * n]
 
 
+def products_over_bases(bases: bytes, values: bytes) -> bytes:
+    """out[b] = Σ_j values[b][j]·bases[j] over G1 for m shared bases: the per-signature products of the examples,
+    g1 * h0^r * Π[n](h[i]^m[i]) (examples/bbs-plus/src/bbs+.cpp:53,72), for many signatures at once.  Affine 96 B each."""
+    ensure_init()
+    m = _count(bases, G1_AFFINE, "bases")
+    B = _count(values, SCALAR * m, "values") if m else 0
+    out = _out(G1_AFFINE * B)
+    check(lib().c12381_g1_multi_fixed_base_batch(bases, m, values, B, out))
+    return out.raw[:G1_AFFINE * B]
+
+
+def products_over_bases2(bases: bytes, values: bytes) -> bytes:
+    """Same over G2 (e.g. w * g2^x, bbs+.cpp:72): affine 192 B each."""
+    ensure_init()
+    m = _count(bases, G2_AFFINE, "bases")
+    B = _count(values, SCALAR * m, "values") if m else 0
+    out = _out(G2_AFFINE * B)
+    check(lib().c12381_g2_multi_fixed_base_batch(bases, m, values, B, out))
+    return out.raw[:G2_AFFINE * B]
+
+
+# ---- from_bytes / to_bytes (point1, point2) -> ECP_fromOctet / ECP_toOctet, ECP2_* (:109-117,187-195), batched ----------
+def from_bytes(encoded: bytes) -> bytes:
+    """49-byte G1 encodings -> affine 96 B; raises C12381Error(EINPUT) where the reference's from_bytes returns 0."""
+    ensure_init()
+    n = _count(encoded, G1_COMPRESSED, "encoded")
+    out = _out(G1_AFFINE * n)
+    check(lib().c12381_g1_decompress_batch(encoded, n, out))
+    return out.raw[:G1_AFFINE * n]
+
+
+def from_bytes2(encoded: bytes) -> bytes:
+    ensure_init()
+    n = _count(encoded, G2_COMPRESSED, "encoded")
+    out = _out(G2_AFFINE * n)
+    check(lib().c12381_g2_decompress_batch(encoded, n, out))
+    return out.raw[:G2_AFFINE * n]
+
+
+def to_bytes(points: bytes) -> bytes:
+    ensure_init()
+    n = _count(points, G1_AFFINE, "points")
+    out = _out(G1_COMPRESSED * n)
+    check(lib().c12381_g1_compress_batch(points, n, out))
+    return out.raw[:G1_COMPRESSED * n]
+
+
+def to_bytes2(points: bytes) -> bytes:
+    ensure_init()
+    n = _count(points, G2_AFFINE, "points")
+    out = _out(G2_COMPRESSED * n)
+    check(lib().c12381_g2_compress_batch(points, n, out))
+    return out.raw[:G2_COMPRESSED * n]
+
+
 # ---- pairings ------------------------------------------------------------------------------------------------------
 def _pairs(g1s: bytes, g2s: bytes, k: int) -> int:
     if not 1 <= k <= _lib.MAX_PAIRS:

@@ -81,6 +81,39 @@ C12_HD Fp2 inv(const Fp2& x)
     return Fp2{fp_mul(x.a, n), fp_neg(fp_mul(x.b, n))};
 }
 
+// ---- square roots (point decompression; replaces FP_sqrt / FP2_sqrt, fp_BLS12381.cpp:842-876, fp2_BLS12381.cpp:460-520)
+// Any root will do: the callers fix the sign from the encoding's sign bit.
+C12_HD bool fp_sqrt(Fp& r, const Fp& a)
+{
+    r = fp_sqrt_candidate(a);
+    return fp_eq(fp_sqr(r), a);
+}
+// sqrt(a + b i): with s = sqrt(a^2 + b^2), x = sqrt((a +- s) / 2), y = b / (2 x)
+C12_HD bool fp2_sqrt(Fp2& r, const Fp2& z)
+{
+    if (is_zero(z)) {
+        r = fp2_zero();
+        return true;
+    }
+    Fp t;
+    if (fp_is_zero(z.b)) {          // real: -1 is a non-residue, so exactly one of a, -a has a root in Fp
+        if (fp_sqrt(t, z.a)) {
+            r = Fp2{t, fp_zero()};
+            return true;
+        }
+        if (!fp_sqrt(t, fp_neg(z.a))) return false;
+        r = Fp2{fp_zero(), t};
+        return true;
+    }
+    Fp s;
+    if (!fp_sqrt(s, fp_add(fp_sqr(z.a), fp_sqr(z.b)))) return false;   // the norm of a square is a square
+    Fp x;
+    if (!fp_sqrt(x, fp_mul(fp_add(z.a, s), fp_half_m())) && !fp_sqrt(x, fp_mul(fp_sub(z.a, s), fp_half_m()))) return false;
+    Fp y = fp_mul(z.b, fp_inv(fp_dbl(x)));
+    r = Fp2{x, y};
+    return eq(sqr(r), z);
+}
+
 C12_HD Fp2 mul3(const Fp2& x) { return Fp2{fp_mul3(x.a), fp_mul3(x.b)}; }
 C12_HD Fp2 mul4(const Fp2& x) { return Fp2{fp_mul4(x.a), fp_mul4(x.b)}; }
 C12_HD Fp2 mul8(const Fp2& x) { return Fp2{fp_mul8(x.a), fp_mul8(x.b)}; }

@@ -552,6 +552,24 @@ template <> struct Wire<Fp> {
         o[0] = (uint8_t)(0x02 | fp_sign(p.y));
         fp_to_be48(o + 1, fp_from_mont(p.x));
     }
+    // ECP_fromOctet compressed -> ECP_setx (ecp_BLS12381.cpp:495-545,302-323): y = sqrt(x^3 + 4), sign from the tag byte.
+    // 49 zero bytes = identity (the C++ layer's convention, g1_point.hpp:87-106).  false: bad tag, x >= p, or no root.
+    static C12_HD bool decompress(Affine<Fp>& o, const uint8_t* b)
+    {
+        o = affine_inf<Fp>();
+        uint8_t any = 0;
+        for (int i = 0; i < 49; ++i) any |= b[i];
+        if (!any) return true;
+        if ((b[0] & 0xfe) != 0x02) return false;
+        Fp x = fp_from_be48(b + 1);
+        if (!fp_is_canonical(x)) return false;
+        x = fp_to_mont(x);
+        Fp y;
+        if (!fp_sqrt(y, fp_add(fp_mul(fp_sqr(x), x), fp_mul4(fp_one())))) return false;
+        if (fp_sign(y) != (int)(b[0] & 1)) y = fp_neg(y);
+        o = Affine<Fp>{x, y};
+        return true;
+    }
     static C12_HD void serialize(uint8_t* o, const Affine<Fp>& p)
     {
         if (affine_is_inf(p)) {
@@ -575,6 +593,24 @@ template <> struct Wire<Fp2> {
         o[0] = (uint8_t)(0x02 | fp2_sign(p.y));
         fp_to_be48(o + 1, fp_from_mont(p.x.b));
         fp_to_be48(o + 49, fp_from_mont(p.x.a));
+    }
+    // ECP2_fromOctet compressed -> ECP2_setx (ecp2_BLS12381.cpp:225-266,322-344): y = sqrt(x^3 + 4(1+i)), FP2_sign from the tag
+    static C12_HD bool decompress(Affine<Fp2>& o, const uint8_t* b)
+    {
+        o = affine_inf<Fp2>();
+        uint8_t any = 0;
+        for (int i = 0; i < 97; ++i) any |= b[i];
+        if (!any) return true;
+        if ((b[0] & 0xfe) != 0x02) return false;
+        Fp xb = fp_from_be48(b + 1), xa = fp_from_be48(b + 49);
+        if (!fp_is_canonical(xa) || !fp_is_canonical(xb)) return false;
+        Fp2 x = Fp2{fp_to_mont(xa), fp_to_mont(xb)};
+        Fp2 four = Fp2{fp_mul4(fp_one()), fp_zero()};
+        Fp2 y;
+        if (!fp2_sqrt(y, add(mul(sqr(x), x), mul_ip(four)))) return false;
+        if (fp2_sign(y) != (int)(b[0] & 1)) y = neg(y);
+        o = Affine<Fp2>{x, y};
+        return true;
     }
     static C12_HD void serialize(uint8_t* o, const Affine<Fp2>& p)
     {

@@ -11,4 +11,10 @@ int c12381_g1_mul_batch(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o
 int c12381_g1_mul_batch_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_mul_dev<Fp>(p, s, n, o, st); }
 int c12381_g1_fixed_base_mul_batch(const uint8_t* s, size_t n, uint8_t* o) { return entry_fixed_host<Fp>(s, n, o); }
 int c12381_g1_fixed_base_mul_batch_dev(const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_fixed_dev<Fp>(s, n, o, st); }
+int c12381_g1_multi_fixed_base_batch(const uint8_t* bases, size_t m, const uint8_t* s, size_t B, uint8_t* o) { return entry_multi_fixed_host<Fp>(bases, m, s, B, o); }
+int c12381_g1_multi_fixed_base_batch_dev(const uint8_t* bases, size_t m, const uint8_t* s, size_t B, uint8_t* o, void* st) { return entry_multi_fixed_dev<Fp>(bases, m, s, B, o, st); }
+int c12381_g1_decompress_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_convert_host<Fp>(in, n, o, true); }
+int c12381_g1_decompress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp>(in, n, o, true, st); }
+int c12381_g1_compress_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_convert_host<Fp>(in, n, o, false); }
+int c12381_g1_compress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp>(in, n, o, false, st); }
 }

@@ -11,4 +11,10 @@ int c12381_g2_mul_batch(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o
 int c12381_g2_mul_batch_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_mul_dev<Fp2>(p, s, n, o, st); }
 int c12381_g2_fixed_base_mul_batch(const uint8_t* s, size_t n, uint8_t* o) { return entry_fixed_host<Fp2>(s, n, o); }
 int c12381_g2_fixed_base_mul_batch_dev(const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_fixed_dev<Fp2>(s, n, o, st); }
+int c12381_g2_multi_fixed_base_batch(const uint8_t* bases, size_t m, const uint8_t* s, size_t B, uint8_t* o) { return entry_multi_fixed_host<Fp2>(bases, m, s, B, o); }
+int c12381_g2_multi_fixed_base_batch_dev(const uint8_t* bases, size_t m, const uint8_t* s, size_t B, uint8_t* o, void* st) { return entry_multi_fixed_dev<Fp2>(bases, m, s, B, o, st); }
+int c12381_g2_decompress_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_convert_host<Fp2>(in, n, o, true); }
+int c12381_g2_decompress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp2>(in, n, o, true, st); }
+int c12381_g2_compress_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_convert_host<Fp2>(in, n, o, false); }
+int c12381_g2_compress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp2>(in, n, o, false, st); }
 }

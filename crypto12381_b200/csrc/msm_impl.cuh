@@ -310,30 +310,29 @@ __global__ void __launch_bounds__(128) k_scalar_mul(const uint8_t* __restrict__ 
 // device; a scalar is recoded into 32 signed 8-bit digits and g^x is 32 mixed additions - no doublings.
 constexpr uint32_t FB_WINDOWS = 32, FB_HALF = 128;
 
-template <class F> __global__ void __launch_bounds__(128) k_fixed_base_table(Affine<F>* __restrict__ table)
+// bases = nullptr: the default generator (one table); else m wire-format affine bases, table j at [j * 4096]
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_base_table(const uint8_t* __restrict__ bases, uint32_t m, Affine<F>* __restrict__ table, int* flags)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= FB_WINDOWS * FB_HALF) return;
-    const uint32_t w = t / FB_HALF, d = t % FB_HALF + 1;
+    if (t >= m * FB_WINDOWS * FB_HALF) return;
+    const uint32_t j = t / (FB_WINDOWS * FB_HALF), e = t % (FB_WINDOWS * FB_HALF);
+    const uint32_t w = e / FB_HALF, d = e % FB_HALF + 1;
+    Affine<F> base = generator<F>();
+    if (bases && !Wire<F>::parse(base, bases + (size_t)Wire<F>::AFFINE * j)) atomicOr(flags, FLAG_BAD_POINT);
     Scalar256 k;
 #pragma unroll
     for (int i = 0; i < 8; ++i) k.v[i] = 0;
-    // d << 8w  (d <= 128 fits 8 bits + 1)
+    // d << 8w  (d <= 128 needs 8 bits)
     const uint32_t bit = 8 * w;
     k.v[bit >> 5] = d << (bit & 31u);
-    if ((bit & 31u) > 23 && (bit >> 5) + 1 < 8) k.v[(bit >> 5) + 1] = d >> (32 - (bit & 31u));
-    table[t] = proj_to_affine(proj_scalar_mul(generator<F>(), k));
+    if ((bit & 31u) > 24 && (bit >> 5) + 1 < 8) k.v[(bit >> 5) + 1] = d >> (32 - (bit & 31u));
+    table[t] = proj_to_affine(proj_scalar_mul(base, k));
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_fixed_base(const uint8_t* __restrict__ scalars, uint32_t n, const Affine<F>* __restrict__ table,
-                                                    uint8_t* __restrict__ out, int* flags)
+// acc += k * (the base of `table`), k < r as 32 signed 8-bit digits: 32 mixed additions, no doublings
+template <class F> __device__ __forceinline__ void fixed_base_accumulate(XYZZ<F>& acc, const Scalar256& k, const Affine<F>* __restrict__ table)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Scalar256 k = scalar_from_be32(scalars + 32ull * i);
-    if (!scalar_is_canonical(k)) atomicOr(flags, FLAG_BAD_SCALAR);
-    XYZZ<F> acc = xyzz_inf<F>();
     uint32_t carry = 0;
 #pragma unroll 1
     for (uint32_t w = 0; w < FB_WINDOWS; ++w) {
@@ -347,11 +346,48 @@ __global__ void __launch_bounds__(128) k_fixed_base(const uint8_t* __restrict__ 
         }
         if (d == 0) continue;
         Affine<F> pt = table[w * FB_HALF + d - 1];
+        if (affine_is_inf(pt)) continue;     // identity base
         if (ng) pt.y = neg(pt.y);
         xyzz_madd(acc, pt);
     }
     // scalars are < r < 2^255, so the top digit is at most 0x73 + 1 and never carries out
+}
+
+// out[b] = sum_j scalars[b][j] * base_j  (m = 1 with the generator's table: g^x)
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_base(const uint8_t* __restrict__ scalars, uint32_t n, uint32_t m, const Affine<F>* __restrict__ table,
+                                                    uint8_t* __restrict__ out, int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> acc = xyzz_inf<F>();
+#pragma unroll 1
+    for (uint32_t j = 0; j < m; ++j) {
+        Scalar256 k = scalar_from_be32(scalars + 32ull * ((size_t)i * m + j));
+        if (!scalar_is_canonical(k)) atomicOr(flags, FLAG_BAD_SCALAR);
+        fixed_base_accumulate<F>(acc, k, table + (size_t)j * FB_WINDOWS * FB_HALF);
+    }
     Wire<F>::serialize(out + (size_t)Wire<F>::AFFINE * i, proj_to_affine(xyzz_to_proj(acc)));
+}
+
+// ---- wire-format conversions in batch (K13): compressed <-> affine -----------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_decompress(const uint8_t* __restrict__ in, uint32_t n, uint8_t* __restrict__ out, int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p;
+    if (!Wire<F>::decompress(p, in + (size_t)Wire<F>::COMPRESSED * i)) atomicOr(flags, FLAG_BAD_POINT);
+    Wire<F>::serialize(out + (size_t)Wire<F>::AFFINE * i, p);
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_compress(const uint8_t* __restrict__ in, uint32_t n, uint8_t* __restrict__ out, int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p;
+    if (!Wire<F>::parse(p, in + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
+    Wire<F>::compress(out + (size_t)Wire<F>::COMPRESSED * i, p);
 }
 
 // ---- host pipeline ------------------------------------------------------------------------------------------
@@ -504,11 +540,42 @@ template <class F> int fixed_base_run(const uint8_t* d_scalars, size_t n, uint8_
     Affine<F>*& table = fixed_base_table_slot<F>();
     if (!table) {   // first use on this context: build the window table (4,096 scalar multiplications, once)
         C12_CUDA(cudaMalloc(&table, sizeof(Affine<F>) * FB_WINDOWS * FB_HALF));
-        k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(table);
+        k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(nullptr, 1, table, c.d_flags);
         C12_LAUNCHED();
         C12_CUDA(cudaStreamSynchronize(s));   // later calls may come on other streams
     }
-    k_fixed_base<F><<<cdiv(n, 128), 128, 0, s>>>(d_scalars, (uint32_t)n, table, d_out, c.d_flags);
+    k_fixed_base<F><<<cdiv(n, 128), 128, 0, s>>>(d_scalars, (uint32_t)n, 1, table, d_out, c.d_flags);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+// out[b] = sum_j scalars[b * m + j] * bases[j] for m caller-supplied bases shared by all B instances (window tables are
+// built per call in the caller's arena reservation: multi_fixed_scratch<F>(m) bytes)
+template <class F> size_t multi_fixed_scratch(size_t m) { return align_up(sizeof(Affine<F>) * m * FB_WINDOWS * FB_HALF) + 4096; }
+template <class F> int multi_fixed_base_run(const uint8_t* d_bases, size_t m, const uint8_t* d_scalars, size_t B, uint8_t* d_out, cudaStream_t s)
+{
+    Ctx& c = ctx();
+    if (B == 0) return C12381_OK;
+    if (m == 0 || m > 4096) return set_error(C12381_EARG, "multi_fixed_base: between 1 and 4096 bases");
+    if (B > 0x7fffffffull) return set_error(C12381_EARG, "multi_fixed_base: too many instances");
+    Affine<F>* table = (Affine<F>*)arena_take(sizeof(Affine<F>) * m * FB_WINDOWS * FB_HALF);
+    if (!table) return set_error(C12381_ECUDA, "multi_fixed_base: scratch arena bound too small");
+    k_fixed_base_table<F><<<cdiv(m * FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(d_bases, (uint32_t)m, table, c.d_flags);
+    C12_LAUNCHED();
+    k_fixed_base<F><<<cdiv(B, 128), 128, 0, s>>>(d_scalars, (uint32_t)B, (uint32_t)m, table, d_out, c.d_flags);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+template <class F> int convert_run(const uint8_t* d_in, size_t n, uint8_t* d_out, bool decompress, cudaStream_t s)
+{
+    Ctx& c = ctx();
+    if (n == 0) return C12381_OK;
+    if (n > 0x7fffffffull) return set_error(C12381_EARG, "convert: too many points");
+    if (decompress)
+        k_decompress<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, c.d_flags);
+    else
+        k_compress<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, c.d_flags);
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -641,6 +708,45 @@ template <class F> int entry_fixed_host(const uint8_t* scalars, size_t n, uint8_
     size_t sz[1] = {n * 32};
     return with_staged(in, sz, 1, out, n * Wire<F>::AFFINE, 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
         return fixed_base_run<F>(d_in[0], n, d_out, s);
+    });
+}
+
+template <class F> int entry_multi_fixed_dev(const uint8_t* d_bases, size_t m, const uint8_t* d_scalars, size_t B, uint8_t* d_out, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (B && (!d_out || !d_scalars || !d_bases)) return set_error(C12381_EARG, "multi_fixed_base: null pointer");
+    cudaStream_t s = pick_stream(stream);
+    int rc = arena_begin(multi_fixed_scratch<F>(m), s);
+    if (rc) return rc;
+    return multi_fixed_base_run<F>(d_bases, m, d_scalars, B, d_out, s);
+}
+
+template <class F> int entry_multi_fixed_host(const uint8_t* bases, size_t m, const uint8_t* scalars, size_t B, uint8_t* out)
+{
+    C12_REQUIRE_CTX();
+    if (B && (!out || !scalars || !bases)) return set_error(C12381_EARG, "multi_fixed_base: null pointer");
+    const void* in[2] = {bases, scalars};
+    size_t sz[2] = {m * Wire<F>::AFFINE, B * m * 32};
+    return with_staged(in, sz, 2, out, B * Wire<F>::AFFINE, multi_fixed_scratch<F>(m), [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+        return multi_fixed_base_run<F>(d_in[0], m, d_in[1], B, d_out, s);
+    });
+}
+
+template <class F> int entry_convert_dev(const uint8_t* d_in, size_t n, uint8_t* d_out, bool decompress, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!d_in || !d_out)) return set_error(C12381_EARG, "convert: null pointer");
+    return convert_run<F>(d_in, n, d_out, decompress, pick_stream(stream));
+}
+
+template <class F> int entry_convert_host(const uint8_t* in_bytes, size_t n, uint8_t* out, bool decompress)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!in_bytes || !out)) return set_error(C12381_EARG, "convert: null pointer");
+    const void* in[1] = {in_bytes};
+    size_t sz[1] = {n * (decompress ? Wire<F>::COMPRESSED : Wire<F>::AFFINE)};
+    return with_staged(in, sz, 1, out, n * (decompress ? Wire<F>::AFFINE : Wire<F>::COMPRESSED), 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+        return convert_run<F>(d_in[0], n, d_out, decompress, s);
     });
 }
 

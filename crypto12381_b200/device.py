@@ -177,6 +177,55 @@ def gt_pow_batch(a, scalars, out=None):
     return out
 
 
+def _multi_fixed(fn_name, point_bytes, bases, scalars, out=None):
+    ensure_init()
+    _chk(bases, "bases"), _chk(scalars, "scalars")
+    m = bases.numel() // point_bytes
+    B = scalars.numel() // (SCALAR * m) if m else 0
+    if bases.numel() != m * point_bytes or scalars.numel() != B * m * SCALAR:
+        raise ValueError("bases / scalars size mismatch")
+    if out is None:
+        out = _new(B * point_bytes, scalars)
+    check(getattr(lib(), fn_name)(bases.data_ptr(), m, scalars.data_ptr(), B, out.data_ptr(), _stream()))
+    return out
+
+
+def g1_multi_fixed_base_batch(bases, scalars, out=None):
+    """out[b] = Σ_j scalars[b][j]·bases[j] (m shared G1 bases) -> affine 96 B per instance."""
+    return _multi_fixed("c12381_g1_multi_fixed_base_batch_dev", G1_AFFINE, bases, scalars, out)
+
+
+def g2_multi_fixed_base_batch(bases, scalars, out=None):
+    return _multi_fixed("c12381_g2_multi_fixed_base_batch_dev", G2_AFFINE, bases, scalars, out)
+
+
+def _convert(fn_name, in_bytes, out_bytes, data, out=None):
+    ensure_init()
+    n = _chk(data, "data").numel() // in_bytes
+    if data.numel() != n * in_bytes:
+        raise ValueError("size mismatch")
+    if out is None:
+        out = _new(n * out_bytes, data)
+    check(getattr(lib(), fn_name)(data.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
+def g1_decompress_batch(data, out=None):
+    return _convert("c12381_g1_decompress_batch_dev", G1_COMPRESSED, G1_AFFINE, data, out)
+
+
+def g2_decompress_batch(data, out=None):
+    return _convert("c12381_g2_decompress_batch_dev", G2_COMPRESSED, G2_AFFINE, data, out)
+
+
+def g1_compress_batch(data, out=None):
+    return _convert("c12381_g1_compress_batch_dev", G1_AFFINE, G1_COMPRESSED, data, out)
+
+
+def g2_compress_batch(data, out=None):
+    return _convert("c12381_g2_compress_batch_dev", G2_AFFINE, G2_COMPRESSED, data, out)
+
+
 def launch_count() -> int:
     return int(lib().c12381_launch_count())
 

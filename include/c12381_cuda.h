@@ -95,6 +95,30 @@ C12381_API int c12381_g2_fixed_base_mul_batch(const uint8_t* scalars32, size_t n
 C12381_API int c12381_g1_fixed_base_mul_batch_dev(const uint8_t* d_scalars32, size_t n, uint8_t* d_out96, void* stream);
 C12381_API int c12381_g2_fixed_base_mul_batch_dev(const uint8_t* d_scalars32, size_t n, uint8_t* d_out192, void* stream);
 
+/* out[b] = sum_j scalars[b * m + j] * bases[j], AFFINE: B independent small sums over m bases shared by all instances
+ * (window tables for the bases are built inside the call).  This is the shape of the per-signature products in the
+ * examples - g1 * h0^r * Π[n](h[i]^m[i]) over the public parameters (examples/bbs-plus/src/bbs+.cpp:53,72; ps.cpp:81,98) -
+ * when many signatures are processed at once; it replaces one chain of double_multiply / multiply / add calls
+ * (src/miracl_core_interface.cpp:129-132,174-182,202-215) per instance. */
+C12381_API int c12381_g1_multi_fixed_base_batch(const uint8_t* bases96, size_t m, const uint8_t* scalars32, size_t B, uint8_t* out96);
+C12381_API int c12381_g2_multi_fixed_base_batch(const uint8_t* bases192, size_t m, const uint8_t* scalars32, size_t B, uint8_t* out192);
+C12381_API int c12381_g1_multi_fixed_base_batch_dev(const uint8_t* d_bases96, size_t m, const uint8_t* d_scalars32, size_t B, uint8_t* d_out96, void* stream);
+C12381_API int c12381_g2_multi_fixed_base_batch_dev(const uint8_t* d_bases192, size_t m, const uint8_t* d_scalars32, size_t B, uint8_t* d_out192, void* stream);
+
+/* ---- wire-format conversions in batch ------------------------------------------------------------- */
+/* decompress: 49 / 97-byte encodings -> affine 96 / 192 B.  Replaces from_bytes(point1&, bytes_view&) -> ECP_fromOctet and
+ * from_bytes(point2&, ...) -> ECP2_fromOctet (src/miracl_core_interface.cpp:109-112,187-190): y = sqrt(x^3 + b) with the
+ * sign from the tag byte; all-zero input = identity (g1_point.hpp:87-106); a bad tag, x >= p or x not on the curve is
+ * reported as C12381_EINPUT (the reference returns status 0).  compress: the inverse (to_bytes, :114-117,192-195). */
+C12381_API int c12381_g1_decompress_batch(const uint8_t* in49, size_t n, uint8_t* out96);
+C12381_API int c12381_g2_decompress_batch(const uint8_t* in97, size_t n, uint8_t* out192);
+C12381_API int c12381_g1_compress_batch(const uint8_t* in96, size_t n, uint8_t* out49);
+C12381_API int c12381_g2_compress_batch(const uint8_t* in192, size_t n, uint8_t* out97);
+C12381_API int c12381_g1_decompress_batch_dev(const uint8_t* d_in49, size_t n, uint8_t* d_out96, void* stream);
+C12381_API int c12381_g2_decompress_batch_dev(const uint8_t* d_in97, size_t n, uint8_t* d_out192, void* stream);
+C12381_API int c12381_g1_compress_batch_dev(const uint8_t* d_in96, size_t n, uint8_t* d_out49, void* stream);
+C12381_API int c12381_g2_compress_batch_dev(const uint8_t* d_in192, size_t n, uint8_t* d_out97, void* stream);
+
 /* ---- pairings --------------------------------------------------------------------------------------------- */
 /* B instances, k pairs each (1 <= k <= C12381_MAX_PAIRS): g1s = B*k*96 B, g2s = B*k*192 B, instance-major.
  * miller: out[b] = conj-adjusted product of Miller loops, NOT exponentiated (576 B raw Fp12).

@@ -220,4 +220,25 @@ void hm_gls_split(const uint8_t* k32, uint8_t* mags32, uint32_t* signs)
         signs[q] = sp.neg[q];
     }
 }
+// compressed -> affine (Wire<F>::decompress, the body of k_decompress); returns 0 ok, -1 on a malformed encoding
+int hm_g1_decompress(const uint8_t* in49, uint32_t n, uint8_t* out96)
+{
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        Affine<Fp> p;
+        if (!Wire<Fp>::decompress(p, in49 + 49 * (size_t)i)) rc = -1;
+        Wire<Fp>::serialize(out96 + 96 * (size_t)i, p);
+    }
+    return rc;
+}
+int hm_g2_decompress(const uint8_t* in97, uint32_t n, uint8_t* out192)
+{
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        Affine<Fp2> p;
+        if (!Wire<Fp2>::decompress(p, in97 + 97 * (size_t)i)) rc = -1;
+        Wire<Fp2>::serialize(out192 + 192 * (size_t)i, p);
+    }
+    return rc;
+}
 }

@@ -5,6 +5,7 @@ from conftest import chunks, load_golden
 
 H = bytes.fromhex
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
 ONE_GT = bytes(575) + b"\x01"
 
 

@@ -1,0 +1,119 @@
+"""GPU: batched wire-format conversion, products over shared bases, and the BBS+ batch verification built from them
+(BASELINE configs[4]; reference: examples/bbs-plus/src/bbs+.cpp:38-73), checked against the oracle restatement and the
+compiled reference."""
+import random
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import bls12381_oracle as o   # checker only
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+R = o.R
+
+
+def be32(v):
+    return int(v).to_bytes(32, "big")
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from crypto12381_b200 import _lib, bbs_plus, bridge
+    _lib.init(0)
+    return bridge, bbs_plus
+
+
+def test_conversions_round_trip_and_golden(gpu):
+    bridge, _ = gpu
+    g = load_golden("points.json")
+    assert bridge.to_bytes(H(g["g1_affine"])) == H(g["g1_compressed"])
+    assert bridge.to_bytes2(H(g["g2_affine"])) == H(g["g2_compressed"])
+    assert bridge.from_bytes(H(g["g1_compressed"]) + bytes(49)) == H(g["g1_affine"]) + bytes(96)
+    assert bridge.from_bytes2(H(g["g2_compressed"]) + bytes(97)) == H(g["g2_affine"]) + bytes(192)
+    rnd = random.Random(5)
+    ks = b"".join(be32(rnd.randrange(R)) for _ in range(3000))
+    p1, p2 = bridge.generator_power(ks), bridge.generator_power2(ks[:32 * 500])
+    assert bridge.from_bytes(bridge.to_bytes(p1)) == p1
+    assert bridge.from_bytes2(bridge.to_bytes2(p2)) == p2
+    # the reference rejects these (unit-tests/g1_point.cpp:132-138, g2_point.cpp:112-118): status, not a result
+    from crypto12381_b200._lib import C12381Error, EINPUT
+    for bad, fn in ((b"\xff" * 49, bridge.from_bytes), (b"\x80" + bytes(96), bridge.from_bytes2)):
+        with pytest.raises(C12381Error) as e:
+            fn(bad)
+        assert e.value.code == EINPUT
+
+
+def test_conversions_vs_oracle(gpu):
+    bridge, _ = gpu
+    rnd = random.Random(6)
+    pts = [o.g1_mul(o.G1_GEN, rnd.randrange(1, R)) for _ in range(4)]
+    enc = b"".join(o.g1_compress(p) for p in pts)
+    assert bridge.from_bytes(enc) == b"".join(o.g1_to_affine_bytes(p) for p in pts)
+    q = [o.g2_mul(o.G2_GEN, rnd.randrange(1, R)) for _ in range(3)]
+    enc2 = b"".join(o.g2_compress(p) for p in q)
+    assert bridge.from_bytes2(enc2) == b"".join(o.g2_to_affine_bytes(p) for p in q)
+
+
+def test_products_over_shared_bases(gpu):
+    bridge, _ = gpu
+    rnd = random.Random(7)
+    m, B = 12, 257
+    bases = bridge.generator_power(b"".join(be32(rnd.randrange(R)) for _ in range(m - 1))) + bytes(96)   # one identity base
+    vals = [[rnd.randrange(R) for _ in range(m)] for _ in range(B)]
+    vals[0] = [0] * m
+    vals[1] = [R - 1] * m
+    vals[2] = [1] + [0] * (m - 1)
+    flat = b"".join(be32(v) for row in vals for v in row)
+    got = bridge.products_over_bases(bases, flat)
+    # each instance is an m-term sum of products: the MSM entry computes the same value
+    for b in (0, 1, 2, 3, 100, B - 1):
+        want = bridge.sum_of_products(bases, b"".join(be32(v) for v in vals[b]))
+        assert bridge.to_bytes(got[96 * b:96 * b + 96]) == want
+    if ref.available():
+        want = b"".join(ref.g1_msm(bases, b"".join(be32(v) for v in vals[b])) for b in range(0, B, 16))
+        assert b"".join(bridge.to_bytes(got[96 * b:96 * b + 96]) for b in range(0, B, 16)) == want
+    bases2 = bridge.generator_power2(b"".join(be32(rnd.randrange(R)) for _ in range(2)))
+    flat2 = b"".join(be32(1) + be32(rnd.randrange(R)) for _ in range(33))
+    got2 = bridge.products_over_bases2(bases2, flat2)
+    for b in (0, 32):
+        assert bridge.to_bytes2(got2[192 * b:192 * b + 192]) == bridge.sum_of_products2(bases2, flat2[64 * b:64 * b + 64])
+
+
+def test_bbs_plus_sign_verify_batch(gpu):
+    bridge, bbs = gpu
+    rnd = random.Random(8)
+    n = 16
+    gens = bridge.to_bytes(bridge.generator_power(b"".join(be32(rnd.randrange(1, R)) for _ in range(n + 2))))
+    g2 = bridge.to_bytes2(bridge.generator_power2(be32(rnd.randrange(1, R))))
+    pp = bbs.PublicParameters(gens[:49] + g2 + gens[49:98], [gens[49 * i:49 * i + 49] for i in range(2, n + 2)])
+    gamma = rnd.randrange(1, R)
+    pk = bridge.multiply2(pp.g2, be32(gamma))            # w = g2^γ, 97 B
+    sk = gamma.to_bytes(48, "big")
+    B = 64
+    msgs = [b"Hello, BBS+!"] + [bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 31 * n))) for _ in range(B - 1)]
+    xs, rs = [rnd.randrange(R) for _ in range(B)], [rnd.randrange(R) for _ in range(B)]
+    sigs = bbs.sign_batch(pp, sk, msgs, xs, rs)
+    assert all(len(s) == 145 for s in sigs)
+    assert bbs.verify_batch(pp, pk, msgs, sigs) == [True] * B
+    # tampering: wrong message, wrong x, A replaced, A not on the curve, x out of range
+    bad_msgs, bad_sigs = list(msgs), list(sigs)
+    bad_msgs[3] = msgs[3] + b"!"
+    bad_sigs[5] = sigs[5][:49] + ((xs[5] + 1) % R).to_bytes(48, "big") + sigs[5][97:]
+    bad_sigs[7] = sigs[8][:49] + sigs[7][49:]
+    bad_sigs[9] = b"\xff" * 49 + sigs[9][49:]
+    bad_sigs[11] = sigs[11][:49] + R.to_bytes(48, "big") + sigs[11][97:]
+    want = [i not in (3, 5, 7, 9, 11) for i in range(B)]
+    assert bbs.verify_batch(pp, pk, bad_msgs, bad_sigs) == want
+    # one signature against the oracle's restatement of verify (bbs+.cpp:72) with its own pairing
+    A = o.g1_decompress(sigs[0][:49])
+    W = o.g2_add(o.g2_from_affine_bytes(bridge.from_bytes2(pk)), o.g2_mul(o.g2_from_affine_bytes(pp.g2), xs[0]))
+    ms = bbs.encode_to_zp(msgs[0])
+    Bp = o.g1_add(o.g1_add(o.g1_from_affine_bytes(pp.g1), o.g1_mul(o.g1_from_affine_bytes(pp.h0), rs[0])),
+                  o.g1_mul(o.g1_from_affine_bytes(pp.h[:96]), ms[0]))
+    assert len(ms) == 1 and ms[0] == (1 << 248) | int.from_bytes(b"Hello, BBS+!" + bytes(31 - 12), "big")
+    assert o.pairing(A, W) == o.pairing(Bp, o.g2_from_affine_bytes(pp.g2))

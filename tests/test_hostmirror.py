@@ -162,3 +162,24 @@ def test_pod_conversions_against_reference_structs():
     assert ref.fp12_to_bytes(pods, 2) == gt
     back = ctypes.create_string_buffer(576 * 2)
     assert l.hm_pod_fp12_to_wire(pods, 2, back) == 0 and back.raw == gt
+
+
+def test_decompress_golden(golden_points):
+    """Wire<F>::decompress (the body of k_decompress) inverts the reference's compressed encodings; bad encodings are refused."""
+    l = hm.lib()
+    H = bytes.fromhex
+    g1c, g2c = H(golden_points["g1_compressed"]), H(golden_points["g2_compressed"])
+    o1 = ctypes.create_string_buffer(96 * (len(g1c) // 49 + 1))
+    assert l.hm_g1_decompress(g1c + bytes(49), len(g1c) // 49 + 1, o1) == 0
+    assert o1.raw == H(golden_points["g1_affine"]) + bytes(96)
+    o2 = ctypes.create_string_buffer(192 * (len(g2c) // 97 + 1))
+    assert l.hm_g2_decompress(g2c + bytes(97), len(g2c) // 97 + 1, o2) == 0
+    assert o2.raw == H(golden_points["g2_affine"]) + bytes(192)
+    # unit-tests/g1_point.cpp:132-138 (0xff...), g2_point.cpp:112-118 (0x80 00...)
+    bad = ctypes.create_string_buffer(192)
+    assert l.hm_g1_decompress(b"\xff" * 49, 1, bad) == -1
+    assert l.hm_g2_decompress(b"\x80" + bytes(96), 1, bad) == -1
+    # flipping the sign bit gives the negated point
+    flipped = bytes([g1c[0] ^ 1]) + g1c[1:49]
+    assert l.hm_g1_decompress(flipped, 1, bad) == 0
+    assert bad.raw[:48] == o1.raw[:48] and (int.from_bytes(bad.raw[48:96], "big") + int.from_bytes(o1.raw[48:96], "big")) % ps.P == 0

@@ -12,3 +12,8 @@ for f in sorted(glob.glob("gpurun_out/$TAG/bench*.json")):
     print(" pairings/s", s.get("value"), "ms", s.get("ms"), "frac", s.get("frac_of_int32_mad_peak"))
     print(" g2", d.get("secondary_g2_msm"))
 PY
+python - <<PY
+import json
+d=json.load(open("gpurun_out/$TAG/bench.json"))
+print(" bbs", d.get("secondary_bbs_plus_verify"))
+PY
