@@ -26,6 +26,7 @@ SIGNATURES = {
     "c12381_device": (_i, []),
     "c12381_sync_status": (_i, [_p]),
     "c12381_set_msm_window": (None, [_i]),
+    "c12381_set_msm_batch_affine": (None, [_i]),
     "c12381_g1_msm": (_i, [_p, _p, _sz, _p]),
     "c12381_g1_msm_dev": (_i, [_p, _p, _sz, _p, _p]),
     "c12381_g1_msm_partial_dev": (_i, [_p, _p, _sz, _p, _p]),

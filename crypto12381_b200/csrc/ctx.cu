@@ -208,6 +208,7 @@ void c12381_shutdown(void)
 const char* c12381_last_error(void) { return ctx().err.c_str(); }
 int c12381_device(void) { return ctx().device; }
 void c12381_set_msm_window(int c) { ctx().forced_window = c; }
+void c12381_set_msm_batch_affine(int rounds) { ctx().ba_rounds = rounds < 0 ? 0 : (rounds > 2 ? 2 : rounds); }
 unsigned long long c12381_launch_count(void) { return ctx().launches; }
 
 int c12381_last_msm_stats(double* accumulate_ms, double* total_ms, unsigned long long* bucket_adds, int* window_bits)

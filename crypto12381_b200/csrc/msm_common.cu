@@ -41,6 +41,29 @@ __global__ void k_bucket_size_keys(uint32_t total, const uint32_t* __restrict__ 
     ids[b] = b;
 }
 
+__global__ void k_ba_counts(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end, uint32_t* __restrict__ out)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < total) out[b] = ba_pairs0(end[b] - start[b]);
+}
+
+size_t ba_offsets_tile_words(const MsmPlan& pl) { return cdiv(pl.total, SCAN_TILE) + 2; }
+
+// o0[b] = sum of the round-0 pair counts of the buckets before b
+int launch_ba_offsets(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* o0, uint32_t* tile_sums, cudaStream_t s)
+{
+    k_ba_counts<<<cdiv(pl.total, 256), 256, 0, s>>>(pl.total, start, end, o0);
+    C12_LAUNCHED();
+    const uint32_t ntiles = cdiv(pl.total, SCAN_TILE);
+    k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, s>>>(o0, pl.total, tile_sums);
+    C12_LAUNCHED();
+    k_scan_top<<<1, SCAN_THREADS, 0, s>>>(tile_sums, ntiles);
+    C12_LAUNCHED();
+    k_scan_apply<<<ntiles, SCAN_THREADS, 0, s>>>(o0, pl.total, tile_sums);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
 size_t bucket_order_scratch_words(const MsmPlan& pl)
 {
     size_t tile_words = 0;

@@ -428,6 +428,87 @@ C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint
     return xyzz_to_proj(acc);
 }
 
+// ---- batch-affine pre-reduction of the bucket lists -----------------------------------------------------------------
+// Before the XYZZ accumulation, up to two rounds halve each bucket's list with AFFINE additions whose inversions are
+// shared by Montgomery's trick: round 0 adds the entries of a bucket pairwise (2i, 2i+1), round 1 adds round 0's results
+// pairwise.  An affine addition is 1 product for the running denominator product, 2 to unwind it, and lambda, lambda^2,
+// y3: 6 Fp products against 10 for the XYZZ mixed addition; one field inversion serves a whole thread block
+// (BA_CAP pairs x 128 buckets), staged through a product tree in shared memory.
+//   round 0: p0 = min(m / 2, BA_CAP) pairs of bucket b (m entries) -> A0[o0 .. o0 + p0), o0 = exclusive scan of p0
+//   round 1: p1 = p0 / 2 pairs of those                            -> A1[ceil(o0 / 2) .. + p1)
+//   the accumulation then sums  A1 (or A0 after one round) + the odd A0 element + the untouched entries 2 p0 .. m
+constexpr uint32_t BA_CAP = 64;
+
+C12_HD uint32_t ba_pairs0(uint32_t m) { return m / 2 < BA_CAP ? m / 2 : BA_CAP; }
+
+// entry j of a bucket's sorted list as a signed affine point
+template <class F> C12_HD Affine<F> ba_fetch(const uint32_t* vals, const Affine<F>* points, uint32_t j)
+{
+    uint32_t v = vals[j];
+    Affine<F> pt = points[v & 0x7fffffffu];
+    if ((v >> 31) && !affine_is_inf(pt)) pt.y = neg(pt.y);
+    return pt;
+}
+
+// The addition P + Q in affine form is  lambda = num / den.  kind 0: chord (den = Qx - Px); 1: tangent (den = 2 Py);
+// 2: result P (Q is the identity); 3: result Q; 4: result is the identity (Q = -P).  den = 1 where no inverse is needed.
+template <class F> C12_HD int ba_denominator(const Affine<F>& P, const Affine<F>& Q, F& den)
+{
+    den = FieldOps<F>::one();
+    if (affine_is_inf(P)) return 3;
+    if (affine_is_inf(Q)) return 2;
+    F dx = sub(Q.x, P.x);
+    if (!is_zero(dx)) {
+        den = dx;
+        return 0;
+    }
+    if (!eq(Q.y, P.y)) return 4;
+    den = dbl(P.y);     // never zero: the groups have odd order
+    return 1;
+}
+template <class F> C12_HD Affine<F> ba_finish(const Affine<F>& P, const Affine<F>& Q, int kind, const F& inv_den)
+{
+    if (kind == 2) return P;
+    if (kind == 3) return Q;
+    if (kind == 4) return affine_inf<F>();
+    F num = kind == 0 ? sub(Q.y, P.y) : mul3(sqr(P.x));
+    F lam = mul_hot(num, inv_den);
+    F x3 = sub(sub(sqr_hot(lam), P.x), Q.x);
+    F y3 = sub(mul_hot(lam, sub(P.x, x3)), P.y);
+    return Affine<F>{x3, y3};
+}
+
+// Bucket accumulation after `rounds` (0, 1, 2) pre-reduction rounds: see the layout above.
+template <class F>
+C12_HD Proj<F> msm_accumulate_reduced_body(uint32_t b, const uint32_t* start, const uint32_t* end, const uint32_t* vals, const Affine<F>* points,
+                                           uint32_t rounds, const uint32_t* o0, const Affine<F>* A0, const Affine<F>* A1)
+{
+    XYZZ<F> acc = xyzz_inf<F>();
+    const uint32_t lo = start[b], hi = end[b];
+    uint32_t p0 = 0;
+    if (rounds) {
+        p0 = ba_pairs0(hi - lo);
+        const uint32_t base0 = o0[b];
+        const Affine<F>* src = rounds == 2 ? A1 + (base0 + 1) / 2 : A0 + base0;
+        const uint32_t cnt = rounds == 2 ? p0 / 2 : p0;
+#pragma unroll 1
+        for (uint32_t i = 0; i < cnt; ++i) {
+            Affine<F> pt = src[i];
+            if (!affine_is_inf(pt)) xyzz_madd(acc, pt);
+        }
+        if (rounds == 2 && (p0 & 1u)) {
+            Affine<F> pt = A0[base0 + p0 - 1];
+            if (!affine_is_inf(pt)) xyzz_madd(acc, pt);
+        }
+    }
+#pragma unroll 1
+    for (uint32_t j = lo + 2 * p0; j < hi; ++j) {
+        Affine<F> pt = ba_fetch<F>(vals, points, j);
+        if (!affine_is_inf(pt)) xyzz_madd(acc, pt);
+    }
+    return xyzz_to_proj(acc);
+}
+
 // ---- bucket reduction:  S_w = sum_j (j + 1) B[j]  over the half buckets of window w ----------------------------------
 // Level 0 cuts the buckets into segments of L_0 = seg_len: segment t yields sum0_t = sum_i (i + 1) B[t L_0 + i] and the
 // plain total R1[t], so  S_w = sum_t sum0_t + L_0 sum_t t R1[t].  The second term is the same problem on the (8 x shorter)

@@ -84,6 +84,90 @@ int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* star
 int launch_bucket_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** order, cudaStream_t s);
 size_t bucket_order_scratch_words(const MsmPlan& pl);
 
+// p0 of every bucket: input of the exclusive scan that yields the A0 offsets (msm_common.cu)
+size_t ba_offsets_tile_words(const MsmPlan& pl);
+int launch_ba_offsets(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* o0, uint32_t* tile_sums, cudaStream_t s);
+
+// One pre-reduction round (msm_core.cuh "batch-affine pre-reduction"): thread t owns bucket order[t] and its k pairs.
+//   forward : running product of the k denominators, every prefix parked in `scratch` (slot i of thread t at [i * stride + t])
+//   block   : product tree over the 128 thread totals in shared memory, ONE inversion at the root, inverses pushed back down
+//   backward: unwind the prefixes -> 1 / den_i, finish each affine addition, write the result
+template <class F, int ROUND>
+__global__ void __launch_bounds__(128) k_ba_round(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                                  const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
+                                                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ o0, Affine<F>* __restrict__ A0,
+                                                  Affine<F>* __restrict__ A1, F* __restrict__ scratch)
+{
+    __shared__ F node[255];
+    const uint32_t tid = threadIdx.x, t = blockIdx.x * 128 + tid;
+    const size_t stride = (size_t)gridDim.x * 128;
+    uint32_t lo = 0, k = 0, base0 = 0;
+    if (t < total) {
+        const uint32_t b = order[t];
+        lo = start[b];
+        const uint32_t p0 = ba_pairs0(end[b] - lo);
+        k = ROUND == 0 ? p0 : p0 / 2;
+        base0 = o0[b];
+    }
+    const Affine<F>* in1 = A0 + base0;                                    // ROUND 1 reads round 0's results
+    Affine<F>* out = ROUND == 0 ? A0 + base0 : A1 + (base0 + 1) / 2;
+    F c = FieldOps<F>::one();
+#pragma unroll 1
+    for (uint32_t i = 0; i < k; ++i) {
+        Affine<F> P = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i) : in1[2 * i];
+        Affine<F> Q = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i + 1) : in1[2 * i + 1];
+        F den;
+        ba_denominator(P, Q, den);
+        c = mul_hot(c, den);
+        scratch[(size_t)i * stride + t] = c;
+    }
+    node[tid] = c;
+    uint32_t base = 0;
+#pragma unroll 1
+    for (uint32_t n = 64; n >= 1; n >>= 1) {         // level with n nodes from the 2n below it
+        __syncthreads();
+        if (tid < n) node[base + 2 * n + tid] = mul(node[base + 2 * tid], node[base + 2 * tid + 1]);
+        base += 2 * n;
+    }
+    __syncthreads();
+    if (tid == 0) node[254] = inv(node[254]);
+#pragma unroll 1
+    for (uint32_t n = 1; n <= 64; n <<= 1) {         // n parents hold inverses; give each child the inverse of its own product
+        base -= 2 * n;
+        __syncthreads();
+        if (tid < n) {
+            F iv = node[base + 2 * n + tid], a = node[base + 2 * tid], bb = node[base + 2 * tid + 1];
+            node[base + 2 * tid] = mul(iv, bb);
+            node[base + 2 * tid + 1] = mul(iv, a);
+        }
+    }
+    __syncthreads();
+    F iv = node[tid];                                // 1 / (den_0 ... den_(k-1)) of this thread
+#pragma unroll 1
+    for (uint32_t i = k; i-- > 0;) {
+        Affine<F> P = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i) : in1[2 * i];
+        Affine<F> Q = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i + 1) : in1[2 * i + 1];
+        F den;
+        const int kind = ba_denominator(P, Q, den);
+        F inv_den = i ? mul_hot(iv, scratch[(size_t)(i - 1) * stride + t]) : iv;
+        iv = mul_hot(iv, den);
+        out[i] = ba_finish(P, Q, kind, inv_den);
+    }
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_accumulate_reduced(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                                            const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
+                                                            const uint32_t* __restrict__ order, uint32_t rounds, const uint32_t* __restrict__ o0,
+                                                            const Affine<F>* __restrict__ A0, const Affine<F>* __restrict__ A1,
+                                                            Proj<F>* __restrict__ buckets)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    uint32_t b = order[t];
+    buckets[b] = msm_accumulate_reduced_body<F>(b, start, end, vals, pts, rounds, o0, A0, A1);
+}
+
 template <class F>
 __global__ void __launch_bounds__(128) k_accumulate(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
                                                     const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
@@ -395,6 +479,15 @@ int sort_pairs_segmented(uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, 
                          uint32_t key_bits, uint32_t* hist, uint32_t* tile_sums, cudaStream_t s);
 size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words);
 
+// pre-reduction rounds for this plan: the context's setting (c12381_set_msm_batch_affine), none when the buckets are too
+// short for the rounds to pay for their launches
+inline uint32_t msm_ba_rounds(const MsmPlan& pl)
+{
+    uint32_t r = (uint32_t)ctx().ba_rounds;
+    if ((uint64_t)pl.n * pl.windows < 8ull * pl.total) return 0;
+    return r > 2 ? 2 : r;
+}
+
 template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
 {
     size_t N = (size_t)pl.n * pl.windows;
@@ -407,6 +500,11 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
     b += 2 * align_up(4 * (size_t)pl.total);
     b += align_up(4 * bucket_order_scratch_words(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
+    if (msm_ba_rounds(pl)) {
+        b += align_up(4 * ((size_t)pl.total + 1)) + align_up(4 * ba_offsets_tile_words(pl));
+        b += align_up(sizeof(Affine<F>) * (N / 2 + 1)) + align_up(sizeof(Affine<F>) * (N / 4 + 2));
+        b += align_up(sizeof(F) * BA_CAP * (size_t)cdiv(pl.total, 128) * 128);
+    }
     b += align_up(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
     return b + 65536;
@@ -460,6 +558,17 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)pl.total);
     uint32_t* order_scratch = (uint32_t*)arena_take(4 * bucket_order_scratch_words(pl));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
+    const uint32_t ba_rounds = msm_ba_rounds(pl);
+    uint32_t *o0 = nullptr, *o0_tiles = nullptr;
+    Affine<F>*A0 = nullptr, *A1 = nullptr;
+    F* ba_scratch = nullptr;
+    if (ba_rounds) {
+        o0 = (uint32_t*)arena_take(4 * ((size_t)pl.total + 1));
+        o0_tiles = (uint32_t*)arena_take(4 * ba_offsets_tile_words(pl));
+        A0 = (Affine<F>*)arena_take(sizeof(Affine<F>) * (N / 2 + 1));
+        A1 = (Affine<F>*)arena_take(sizeof(Affine<F>) * (N / 4 + 2));
+        ba_scratch = (F*)arena_take(sizeof(F) * BA_CAP * (size_t)cdiv(pl.total, 128) * 128);
+    }
     Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
     if (!wsum) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
@@ -483,8 +592,21 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
-    k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, buckets);
-    C12_LAUNCHED();
+    if (ba_rounds) {
+        rc = launch_ba_offsets(pl, start, end, o0, o0_tiles, s);
+        if (rc) return rc;
+        k_ba_round<F, 0><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, o0, A0, A1, ba_scratch);
+        C12_LAUNCHED();
+        if (ba_rounds == 2) {
+            k_ba_round<F, 1><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, o0, A0, A1, ba_scratch);
+            C12_LAUNCHED();
+        }
+        k_accumulate_reduced<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, ba_rounds, o0, A0, A1, buckets);
+        C12_LAUNCHED();
+    } else {
+        k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, buckets);
+        C12_LAUNCHED();
+    }
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));
     k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);

@@ -59,6 +59,8 @@ C12381_API int c12381_device(void);              /* bound device or -1 */
 C12381_API int c12381_sync_status(void* stream);
 /* testing/tuning knob: force the MSM window width (0 = automatic) */
 C12381_API void c12381_set_msm_window(int c);
+/* testing/tuning knob: batch-affine pre-reduction rounds before the bucket accumulation (0, 1 or 2; same results) */
+C12381_API void c12381_set_msm_batch_affine(int rounds);
 
 /* ---- multi-scalar multiplication ------------------------------------------------------------------------- */
 /* out = sum_i scalars[i] * points[i] over G1.

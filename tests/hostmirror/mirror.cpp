@@ -23,7 +23,7 @@ MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, uint32_t parts)
 }
 
 // parts = 1: no split; MsmTraits<F>::PARTS: the split the device entries use
-template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1)
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0)
 {
     using W = Wire<F>;
     if (n_in == 0) {
@@ -59,7 +59,32 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
             if (i + 1 == n || sk[g + 1] != k) end[b] = (uint32_t)g + 1;
         }
     std::vector<Proj<F>> buckets(pl.total);
-    for (uint32_t b = 0; b < pl.total; ++b) buckets[b] = msm_accumulate_body<F>(b, start.data(), end.data(), sv.data(), P.data());
+    if (rounds == 0) {
+        for (uint32_t b = 0; b < pl.total; ++b) buckets[b] = msm_accumulate_body<F>(b, start.data(), end.data(), sv.data(), P.data());
+    } else {
+        // the batch-affine pre-reduction rounds (k_ba_round), one inversion per pair here instead of one per block
+        std::vector<uint32_t> o0(pl.total + 1, 0);
+        for (uint32_t b = 0; b < pl.total; ++b) o0[b + 1] = o0[b] + ba_pairs0(end[b] - start[b]);
+        std::vector<Affine<F>> A0(o0[pl.total] + 1), A1(o0[pl.total] / 2 + 2);
+        for (uint32_t b = 0; b < pl.total; ++b) {
+            uint32_t p0 = ba_pairs0(end[b] - start[b]);
+            for (uint32_t i = 0; i < p0; ++i) {
+                Affine<F> X = ba_fetch<F>(sv.data(), P.data(), start[b] + 2 * i), Y = ba_fetch<F>(sv.data(), P.data(), start[b] + 2 * i + 1);
+                F den;
+                int kind = ba_denominator(X, Y, den);
+                A0[o0[b] + i] = ba_finish(X, Y, kind, inv(den));
+            }
+            if (rounds == 2)
+                for (uint32_t i = 0; i < p0 / 2; ++i) {
+                    Affine<F> X = A0[o0[b] + 2 * i], Y = A0[o0[b] + 2 * i + 1];
+                    F den;
+                    int kind = ba_denominator(X, Y, den);
+                    A1[(o0[b] + 1) / 2 + i] = ba_finish(X, Y, kind, inv(den));
+                }
+        }
+        for (uint32_t b = 0; b < pl.total; ++b)
+            buckets[b] = msm_accumulate_reduced_body<F>(b, start.data(), end.data(), sv.data(), P.data(), rounds, o0.data(), A0.data(), A1.data());
+    }
     std::vector<Proj<F>> wsum(pl.windows);
     for (uint32_t w = 0; w < pl.windows; ++w) {
         // the multi-level reduction of msm_core.cuh, level by level (k_reduce_level0 / k_reduce_level / k_reduce2 / k_finish)
@@ -107,6 +132,15 @@ void hm_fp_op(int op, const uint8_t* a48, const uint8_t* b48, uint8_t* out48)
 
 int hm_g1_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out49) { return msm<Fp>(p, s, n, c, seg, out49); }
 int hm_g2_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out97) { return msm<Fp2>(p, s, n, c, seg, out97); }
+// with `rounds` batch-affine pre-reduction rounds and the device entries' scalar split
+int hm_g1_msm_ba(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint8_t* out49)
+{
+    return msm<Fp>(p, s, n, c, 0, out49, MsmTraits<Fp>::PARTS, rounds);
+}
+int hm_g2_msm_ba(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint8_t* out97)
+{
+    return msm<Fp2>(p, s, n, c, 0, out97, MsmTraits<Fp2>::PARTS, rounds);
+}
 
 int hm_g1_mul(const uint8_t* p96, const uint8_t* s32, uint32_t n, uint8_t* out49)
 {

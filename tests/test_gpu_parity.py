@@ -83,7 +83,15 @@ def test_points_golden(cuda):
     ps.check_points(cuda)
 
 
-def test_msm_golden_all_windows(cuda):
+@pytest.fixture(params=[0, 1, 2], ids=["xyzz-only", "batch-affine-1", "batch-affine-2"])
+def ba_rounds(request):
+    from crypto12381_b200 import _lib
+    _lib.lib().c12381_set_msm_batch_affine(request.param)
+    yield request.param
+    _lib.lib().c12381_set_msm_batch_affine(2)
+
+
+def test_msm_golden_all_windows(cuda, ba_rounds):
     ps.check_msm(cuda, windows=(0, 2, 3, 5, 8, 9, 13, 16))
 
 
@@ -105,7 +113,7 @@ needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref12
 
 @needs_ref
 @pytest.mark.parametrize("n", [1, 2, 3, 31, 100, 1000, 4097, 20000])
-def test_g1_msm_vs_reference(cuda, n):
+def test_g1_msm_vs_reference(cuda, n, ba_rounds):
     t = ref.hardware_threads()
     ks = ref.random_scalars(f"msm-g1-points-{n}", n)
     ss = ref.random_scalars(f"msm-g1-{n}", n)
@@ -119,7 +127,7 @@ def test_g1_msm_vs_reference(cuda, n):
 
 @needs_ref
 @pytest.mark.parametrize("n", [1, 2, 17, 300, 3000])
-def test_g2_msm_vs_reference(cuda, n):
+def test_g2_msm_vs_reference(cuda, n, ba_rounds):
     t = ref.hardware_threads()
     ks = ref.random_scalars(f"msm-g2-points-{n}", n)
     ss = ref.random_scalars(f"msm-g2-{n}", n)
@@ -242,7 +250,7 @@ def test_g2_msm_full_size_linearity(cuda):
     assert bytes(dv.g2_sum(parts).cpu().numpy()) == got
 
 
-def test_skewed_scalars_and_repeated_points(cuda):
+def test_skewed_scalars_and_repeated_points(cuda, ba_rounds):
     """Ragged buckets: every scalar equal (one bucket per window takes all terms), tiny scalars, repeated points."""
     n = 3000
     gen = bytes.fromhex(load_golden("points.json")["g1_generator"])

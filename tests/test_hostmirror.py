@@ -183,3 +183,29 @@ def test_decompress_golden(golden_points):
     flipped = bytes([g1c[0] ^ 1]) + g1c[1:49]
     assert l.hm_g1_decompress(flipped, 1, bad) == 0
     assert bad.raw[:48] == o1.raw[:48] and (int.from_bytes(bad.raw[48:96], "big") + int.from_bytes(o1.raw[48:96], "big")) % ps.P == 0
+
+
+def test_msm_batch_affine_rounds(golden_msm):
+    """The batch-affine pre-reduction rounds (bodies of k_ba_round / k_accumulate_reduced) give the same sums, including on
+    repeated points, P and -P, identities and zero scalars; small windows make the bucket lists long enough to pair up."""
+    l = hm.lib()
+    H = bytes.fromhex
+    for case in golden_msm["cases"]:
+        if case["n"] > 300:
+            continue
+        g1 = case["group"] == "g1"
+        pts = (hm.g1_fixed_base if g1 else hm.g2_fixed_base)(H(case["point_scalars"]))
+        for rounds in (1, 2):
+            for c in (2, 3, 5):
+                out = ctypes.create_string_buffer(49 if g1 else 97)
+                fn = l.hm_g1_msm_ba if g1 else l.hm_g2_msm_ba
+                assert fn(pts, H(case["scalars"]), case["n"], c, rounds, out) == 0
+                assert out.raw == H(case["result"]), (case["group"], case["n"], rounds, c)
+    for key, want in (("edge_g1", None), ("cancel_g1", bytes(49))):
+        e = golden_msm[key]
+        n = len(H(e["scalars"])) // 32
+        for rounds in (1, 2):
+            for c in (2, 4):
+                out = ctypes.create_string_buffer(49)
+                assert l.hm_g1_msm_ba(H(e["points"]), H(e["scalars"]), n, c, rounds, out) == 0
+                assert out.raw == (want if want is not None else H(e["result"])), (key, rounds, c)
