@@ -35,7 +35,7 @@ struct Ctx {
     int* h_flags = nullptr;
     int* d_flags = nullptr;
     int forced_window = 0;
-    int ba_rounds = 2;      // batch-affine pre-reduction rounds before the XYZZ accumulation (0, 1, 2)
+    int ba_rounds = 0;      // batch-affine pre-reduction rounds before the XYZZ accumulation (0, 1, 2): measured slower, opt-in
     void* fb_table[2] = {nullptr, nullptr};   // fixed-base window tables (G1, G2), built on first use
     MsmStats stats;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -88,7 +88,7 @@ def ba_rounds(request):
     from crypto12381_b200 import _lib
     _lib.lib().c12381_set_msm_batch_affine(request.param)
     yield request.param
-    _lib.lib().c12381_set_msm_batch_affine(2)
+    _lib.lib().c12381_set_msm_batch_affine(0)
 
 
 def test_msm_golden_all_windows(cuda, ba_rounds):
