@@ -121,13 +121,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restric
 }
 
 // ---- stable scatter ------------------------------------------------------------------------------------------
+// Ranks every item of the tile stably (warp match/ballot + per-warp counters), then STAGES the tile in shared memory in
+// digit order before writing: a tile of 4,096 items over 256 digits holds ~16 items per digit, so consecutive threads
+// write runs of ~64 contiguous bytes instead of 4,096 isolated 4-byte words (the direct scatter moved 8x the sectors).
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t* __restrict__ keys_in,
                                                                   const uint32_t* __restrict__ vals_in,
                                                                   uint32_t* __restrict__ keys_out,
                                                                   uint32_t* __restrict__ vals_out, uint32_t n, int shift,
                                                                   const uint32_t* __restrict__ hist_scanned, uint32_t nblk)
 {
-    __shared__ uint32_t cnt[SORT_WARPS][256];
+    __shared__ uint32_t cnt[SORT_WARPS][256];     // per-warp digit counts, then per-warp tile-local offsets
+    __shared__ uint32_t tile_off[257];            // tile-local start of each digit's run
+    __shared__ uint32_t gbase[256];               // global position of each digit's run of this tile
+    __shared__ uint32_t skey[SORT_TILE], sval[SORT_TILE];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&cnt[0][0])[i] = 0;
     __syncthreads();
@@ -153,15 +159,21 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t* 
     }
     __syncthreads();
     {
-        // thread d: turn per-warp counts into exclusive offsets, seeded with this tile's global base for digit d
-        uint32_t d = threadIdx.x;
-        uint32_t run = hist_scanned[((uint64_t)blockIdx.y * 256 + d) * nblk + blockIdx.x];
+        // thread d: digit d's count in this tile, per-warp exclusive offsets inside the digit's run
+        const uint32_t d = threadIdx.x;
+        uint32_t run = 0;
 #pragma unroll
         for (int ww = 0; ww < SORT_WARPS; ++ww) {
             uint32_t c = cnt[ww][d];
             cnt[ww][d] = run;
             run += c;
         }
+        gbase[d] = hist_scanned[((uint64_t)blockIdx.y * 256 + d) * nblk + blockIdx.x];
+        // exclusive scan of the 256 digit counts -> tile-local run starts
+        uint32_t total;
+        uint32_t e = block_exclusive_scan_256(run, &total);
+        tile_off[d] = e;
+        if (d == 255) tile_off[256] = total;
     }
     __syncthreads();
 #pragma unroll
@@ -169,10 +181,19 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t* 
         uint64_t idx = base + (uint64_t)i * 32 + lane;
         if (idx < n) {
             uint32_t d = (k[i] >> shift) & 255u;
-            uint32_t pos = cnt[w][d] + rank[i];
-            keys_out[pos] = k[i];
-            vals_out[pos] = v[i];
+            uint32_t slot = tile_off[d] + cnt[w][d] + rank[i];
+            skey[slot] = k[i];
+            sval[slot] = v[i];
         }
+    }
+    __syncthreads();
+    const uint32_t count = tile_off[256];
+    for (uint32_t slot = threadIdx.x; slot < count; slot += SORT_THREADS) {
+        uint32_t kk = skey[slot];
+        uint32_t d = (kk >> shift) & 255u;
+        uint32_t pos = gbase[d] + (slot - tile_off[d]);
+        keys_out[pos] = kk;
+        vals_out[pos] = sval[slot];
     }
 }
 
