@@ -225,7 +225,7 @@ template <class F, int N> __device__ __forceinline__ void coop_mul(F (&out)[N], 
         x = select(lane == i, a[i], x);
         y = select(lane == i, b[i], y);
     }
-    F m = mul(x, y);
+    F m = mul_hot(x, y);     // straight-line product: these are single-warp latency chains
 #pragma unroll
     for (int i = 0; i < N; ++i) out[i] = group_bcast_obj(m, i, mask);
 }
