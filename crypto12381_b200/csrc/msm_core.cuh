@@ -357,9 +357,7 @@ template <> struct MsmTraits<Fp2> {
 
 // Body of the recode kernel for term i: writes W (key, value) pairs at out index w * n + i.
 // The w-major layout keeps each window's entries in term order before the (stable) sort.
-// With a split on, term i yields `parts` pipeline terms: piece q at index parts * i + q (point [mu^q]P_i resp. [z^q]P_i) -
-// interleaved, so that a prefix of the caller's terms is a prefix of every bucket's (index-ordered) list, which is what
-// lets the host entry start accumulating while the second half of the points is still being uploaded.
+// With a split on, term i yields `parts` pipeline terms: piece q at index q n_in + i (point [mu^q]P_i resp. [z^q]P_i).
 C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalars_be32, uint32_t* keys, uint32_t* vals)
 {
     Scalar256 s = scalar_from_be32(scalars_be32 + 32ull * i);
@@ -368,7 +366,7 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
         msm_split(s, pl.parts, sp);
         for (uint32_t part = 0; part < pl.parts; ++part) {
             const uint32_t sgn = sp.neg[part];
-            const uint32_t idx = pl.parts * i + part;
+            const uint32_t idx = i + part * pl.n_in;
             uint32_t carry = 0;
             for (uint32_t w = 0; w < pl.windows; ++w) {
                 uint32_t d = limbs_bits<4>(sp.mag[part], w * pl.c, pl.c) + carry;
@@ -428,37 +426,6 @@ C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint
         xyzz_madd(acc, pt);
     }
     return xyzz_to_proj(acc);
-}
-
-// The same in two launches (host entry): phase 0 adds the entries whose pipeline index is below `split` and parks the
-// accumulator; phase 1 resumes from there.  Lists are in index order, so phase 0's entries are a prefix.
-template <class F>
-C12_HD void msm_accumulate_phase_body(uint32_t b, const uint32_t* start, const uint32_t* end, const uint32_t* vals, const Affine<F>* points,
-                                      uint32_t phase, uint32_t split, XYZZ<F>* state, uint32_t* resume, Proj<F>* buckets)
-{
-    XYZZ<F> acc = xyzz_inf<F>();
-    uint32_t j = start[b];
-    const uint32_t hi = end[b];
-    if (phase) {
-        acc = state[b];
-        j = resume[b];
-    }
-#pragma unroll 1
-    for (; j < hi; ++j) {
-        uint32_t v = vals[j];
-        uint32_t idx = v & 0x7fffffffu;
-        if (!phase && idx >= split) break;
-        Affine<F> pt = points[idx];
-        if (affine_is_inf(pt)) continue;
-        if (v >> 31) pt.y = neg(pt.y);
-        xyzz_madd(acc, pt);
-    }
-    if (phase) {
-        buckets[b] = xyzz_to_proj(acc);
-    } else {
-        state[b] = acc;
-        resume[b] = j;
-    }
 }
 
 // ---- batch-affine pre-reduction of the bucket lists -----------------------------------------------------------------

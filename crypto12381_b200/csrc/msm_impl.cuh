@@ -66,15 +66,15 @@ template <class F> __device__ Proj<F> block_sum_256(Proj<F> acc)
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t first, uint32_t last, uint32_t parts,
-                                                      Affine<F>* __restrict__ pts, int* flags)
+__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t n, uint32_t parts, Affine<F>* __restrict__ pts,
+                                                      int* flags)
 {
-    uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= last) return;
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
     Affine<F> p;
     if (!Wire<F>::parse(p, bytes + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
-    pts[(size_t)parts * i] = p;
-    for (uint32_t q = 1; q < parts; ++q) pts[(size_t)parts * i + q] = MsmTraits<F>::endo(q, p);   // the identity (0, 0) maps to itself
+    pts[i] = p;
+    for (uint32_t q = 1; q < parts; ++q) pts[(size_t)q * n + i] = MsmTraits<F>::endo(q, p);   // the identity (0, 0) maps to itself
 }
 
 // defined once in msm_common.cu (kernels there are launched through these host functions)
@@ -153,17 +153,6 @@ __global__ void __launch_bounds__(128) k_ba_round(uint32_t total, const uint32_t
         iv = mul_hot(iv, den);
         out[i] = ba_finish(P, Q, kind, inv_den);
     }
-}
-
-template <class F>
-__global__ void __launch_bounds__(128) k_accumulate_phase(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                                          const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
-                                                          const uint32_t* __restrict__ order, uint32_t phase, uint32_t split,
-                                                          XYZZ<F>* __restrict__ state, uint32_t* __restrict__ resume, Proj<F>* __restrict__ buckets)
-{
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    msm_accumulate_phase_body<F>(order[t], start, end, vals, pts, phase, split, state, resume, buckets);
 }
 
 template <class F>
@@ -516,7 +505,6 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
         b += align_up(sizeof(Affine<F>) * (N / 2 + 1)) + align_up(sizeof(Affine<F>) * (N / 4 + 2));
         b += align_up(sizeof(F) * BA_CAP * (size_t)cdiv(pl.total, 128) * 128);
     }
-    b += align_up(sizeof(XYZZ<F>) * (size_t)pl.total) + align_up(4 * (size_t)pl.total);    // two-phase accumulation (host entry)
     b += align_up(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
     return b + 65536;
@@ -536,17 +524,11 @@ template <class F> size_t msm_scratch_for(size_t n)
 // d_points: n wire-format affine points; d_scalars: n x 32 B big-endian; d_out: Wire<F>::COMPRESSED or ::AFFINE bytes.
 // Everything is enqueued on `s`; malformed input is reported through the context flag word (c12381_sync_status /
 // the host entry's return code), never by a different code path.
-// Host entries upload the points on a second stream, in two halves, while the pipeline already runs: `half_ready[0]`
-// (terms [0, n_half)) is awaited before the first parse + accumulation phase, `half_ready[1]` before the second; the
-// scalar-only stages - recode, sort, bucket bounds - need neither.
-struct PointUpload {
-    cudaEvent_t half_ready[2];
-    uint32_t n_half;
-};
-
+// points_ready: optional event after which d_points is valid (host entries upload the points on a second stream while
+// the scalar-only stages - recode, sort, bucket bounds - already run).
 template <class F>
 int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint8_t* d_out, int out_mode, cudaStream_t s,
-            const PointUpload* upload = nullptr)
+            cudaEvent_t points_ready = nullptr)
 {
     Ctx& c = ctx();
     const int out_bytes = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
@@ -604,12 +586,9 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* order = nullptr;
     rc = launch_bucket_order(pl, start, end, order_scratch, &order, s);
     if (rc) return rc;
-    const bool phased = upload && !msm_ba_rounds(pl) && upload->n_half > 0 && upload->n_half < n;
-    if (upload) C12_CUDA(cudaStreamWaitEvent(s, upload->half_ready[0], 0));
-    if (upload && !phased) C12_CUDA(cudaStreamWaitEvent(s, upload->half_ready[1], 0));
+    if (points_ready) C12_CUDA(cudaStreamWaitEvent(s, points_ready, 0));
     C12_CUDA(cudaEventRecord(c.pev[3], s));
-    const uint32_t first_n = phased ? upload->n_half : n;
-    k_parse_points<F><<<cdiv(first_n, 128), 128, 0, s>>>(d_points, 0, first_n, pl.parts, pts, c.d_flags);
+    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.parts, pts, c.d_flags);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
@@ -623,17 +602,6 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
             C12_LAUNCHED();
         }
         k_accumulate_reduced<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, ba_rounds, o0, A0, A1, buckets);
-        C12_LAUNCHED();
-    } else if (phased) {
-        XYZZ<F>* state = (XYZZ<F>*)arena_take(sizeof(XYZZ<F>) * (size_t)pl.total);
-        uint32_t* resume = (uint32_t*)arena_take(4 * (size_t)pl.total);
-        if (!resume) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
-        k_accumulate_phase<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, 0, pl.parts * first_n, state, resume, buckets);
-        C12_LAUNCHED();
-        C12_CUDA(cudaStreamWaitEvent(s, upload->half_ready[1], 0));
-        k_parse_points<F><<<cdiv(n - first_n, 128), 128, 0, s>>>(d_points, first_n, n, pl.parts, pts, c.d_flags);
-        C12_LAUNCHED();
-        k_accumulate_phase<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, 1, pl.parts * first_n, state, resume, buckets);
         C12_LAUNCHED();
     } else {
         k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, buckets);
@@ -803,21 +771,16 @@ template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scal
     uint8_t* d_out = (uint8_t*)arena_take(Wire<F>::COMPRESSED);
     rc = flags_reset(s);
     if (rc) return rc;
-    PointUpload up;
+    cudaEvent_t ready = nullptr;
     if (n) {
         C12_CUDA(cudaMemcpyAsync(d_sc, scalars, sb, cudaMemcpyHostToDevice, s));
         C12_CUDA(cudaEventRecord(c.copy_ev[0], s));                        // the arena is ours from here on
         C12_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_ev[0], 0));
-        up.n_half = (uint32_t)(n / 2);
-        const size_t hb = (size_t)up.n_half * Wire<F>::AFFINE;
-        if (hb) C12_CUDA(cudaMemcpyAsync(d_pts, points, hb, cudaMemcpyHostToDevice, c.copy_stream));
+        C12_CUDA(cudaMemcpyAsync(d_pts, points, pb, cudaMemcpyHostToDevice, c.copy_stream));
         C12_CUDA(cudaEventRecord(c.copy_ev[1], c.copy_stream));
-        C12_CUDA(cudaMemcpyAsync(d_pts + hb, points + hb, pb - hb, cudaMemcpyHostToDevice, c.copy_stream));
-        C12_CUDA(cudaEventRecord(c.copy_ev[2], c.copy_stream));
-        up.half_ready[0] = c.copy_ev[1];
-        up.half_ready[1] = c.copy_ev[2];
+        ready = c.copy_ev[1];
     }
-    rc = msm_run<F>(d_pts, d_sc, n, d_out, OUT_COMPRESSED, s, n ? &up : nullptr);
+    rc = msm_run<F>(d_pts, d_sc, n, d_out, OUT_COMPRESSED, s, ready);
     if (rc) {
         cudaStreamSynchronize(c.copy_stream);
         cudaStreamSynchronize(s);

@@ -23,7 +23,7 @@ MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, uint32_t parts)
 }
 
 // parts = 1: no split; MsmTraits<F>::PARTS: the split the device entries use
-template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0, bool phased = false)
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0)
 {
     using W = Wire<F>;
     if (n_in == 0) {
@@ -34,8 +34,8 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
     const uint32_t n = pl.n;
     std::vector<Affine<F>> P(n);
     for (uint32_t i = 0; i < n_in; ++i) {
-        if (!W::parse(P[(size_t)parts * i], pts + (size_t)W::AFFINE * i)) return -1;
-        for (uint32_t q = 1; q < parts; ++q) P[(size_t)parts * i + q] = MsmTraits<F>::endo(q, P[(size_t)parts * i]);
+        if (!W::parse(P[i], pts + (size_t)W::AFFINE * i)) return -1;
+        for (uint32_t q = 1; q < parts; ++q) P[(size_t)q * n_in + i] = MsmTraits<F>::endo(q, P[i]);
     }
     size_t N = (size_t)n * pl.windows;
     std::vector<uint32_t> keys(N), vals(N);
@@ -59,14 +59,7 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
             if (i + 1 == n || sk[g + 1] != k) end[b] = (uint32_t)g + 1;
         }
     std::vector<Proj<F>> buckets(pl.total);
-    if (rounds == 0 && phased) {
-        // the host entry's two-phase accumulation (k_accumulate_phase): first the entries of terms [0, n_in / 2), then the rest
-        std::vector<XYZZ<F>> state(pl.total);
-        std::vector<uint32_t> resume(pl.total);
-        for (uint32_t ph = 0; ph < 2; ++ph)
-            for (uint32_t b = 0; b < pl.total; ++b)
-                msm_accumulate_phase_body<F>(b, start.data(), end.data(), sv.data(), P.data(), ph, parts * (n_in / 2), state.data(), resume.data(), buckets.data());
-    } else if (rounds == 0) {
+    if (rounds == 0) {
         for (uint32_t b = 0; b < pl.total; ++b) buckets[b] = msm_accumulate_body<F>(b, start.data(), end.data(), sv.data(), P.data());
     } else {
         // the batch-affine pre-reduction rounds (k_ba_round), one inversion per pair here instead of one per block
@@ -139,15 +132,6 @@ void hm_fp_op(int op, const uint8_t* a48, const uint8_t* b48, uint8_t* out48)
 
 int hm_g1_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out49) { return msm<Fp>(p, s, n, c, seg, out49); }
 int hm_g2_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out97) { return msm<Fp2>(p, s, n, c, seg, out97); }
-// the host entries' two-phase accumulation with the device entries' scalar split
-int hm_g1_msm_phased(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint8_t* out49)
-{
-    return msm<Fp>(p, s, n, c ? c : msm_choose_window(2 * (uint64_t)n, 128), 0, out49, MsmTraits<Fp>::PARTS, 0, true);
-}
-int hm_g2_msm_phased(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint8_t* out97)
-{
-    return msm<Fp2>(p, s, n, c ? c : msm_choose_window(4 * (uint64_t)n, 64), 0, out97, MsmTraits<Fp2>::PARTS, 0, true);
-}
 // with `rounds` batch-affine pre-reduction rounds and the device entries' scalar split
 int hm_g1_msm_ba(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint8_t* out49)
 {

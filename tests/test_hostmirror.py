@@ -209,21 +209,3 @@ def test_msm_batch_affine_rounds(golden_msm):
                 out = ctypes.create_string_buffer(49)
                 assert l.hm_g1_msm_ba(H(e["points"]), H(e["scalars"]), n, c, rounds, out) == 0
                 assert out.raw == (want if want is not None else H(e["result"])), (key, rounds, c)
-
-
-def test_msm_two_phase_accumulation(golden_msm):
-    """The host entries accumulate in two launches (first half of the terms, then the rest: k_accumulate_phase) - same sums."""
-    l = hm.lib()
-    H = bytes.fromhex
-    for case in golden_msm["cases"]:
-        if case["n"] > 300:
-            continue
-        g1 = case["group"] == "g1"
-        pts = (hm.g1_fixed_base if g1 else hm.g2_fixed_base)(H(case["point_scalars"]))
-        for c in (0, 3, 7):
-            out = ctypes.create_string_buffer(49 if g1 else 97)
-            assert (l.hm_g1_msm_phased if g1 else l.hm_g2_msm_phased)(pts, H(case["scalars"]), case["n"], c, out) == 0
-            assert out.raw == H(case["result"]), (case["group"], case["n"], c)
-    e = golden_msm["edge_g1"]
-    out = ctypes.create_string_buffer(49)
-    assert l.hm_g1_msm_phased(H(e["points"]), H(e["scalars"]), len(H(e["scalars"])) // 32, 4, out) == 0 and out.raw == H(e["result"])
