@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample-log-n", type=int, default=15)
     ap.add_argument("--g2-log-n", type=int, default=18)
     ap.add_argument("--bbs-log-b", type=int, default=16)
+    ap.add_argument("--sweep-max-log-n", type=int, default=24)
     ap.add_argument("--no-secondary", action="store_true")
     return ap.parse_args()
 
@@ -360,6 +361,34 @@ def run_ours(args):
             except Exception as e:
                 g2["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
             line["secondary_g2_msm"] = g2
+    # secondary: the G1 sweep of BASELINE configs[1], n = 2^10 .. 2^24 (rank 0 only, device-resident, same pipeline)
+    if not args.no_secondary and args.sweep_max_log_n >= 10 and rank == 0:
+        gsw = torch.Generator(device=dev).manual_seed(9000)
+        nmax = 1 << args.sweep_max_log_n
+        kk = torch.randint(0, 256, (nmax, 32), dtype=torch.uint8, device=dev, generator=gsw)
+        sw_s = torch.randint(0, 256, (nmax, 32), dtype=torch.uint8, device=dev, generator=gsw)
+        kk[:, 0] %= R_TOP
+        sw_s[:, 0] %= R_TOP
+        sw_p = dv.g1_fixed_base_mul_batch(kk.reshape(-1))
+        sw_s = sw_s.reshape(-1)
+        del kk
+        sweep = []
+        for ln in range(10, args.sweep_max_log_n + 1, 2):
+            m = 1 << ln
+            reps = 10 if ln <= 18 else 3
+            dv.g1_msm(sw_p[:96 * m], sw_s[:32 * m])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                dv.g1_msm(sw_p[:96 * m], sw_s[:32 * m])
+            e1.record()
+            torch.cuda.synchronize()
+            ms_s = e0.elapsed_time(e1) / reps
+            sweep.append({"log_n": ln, "ms": ms_s, "points_per_s": m / (ms_s * 1e-3), "window_bits": dv.last_msm_stats()["window_bits"]})
+        dv.sync_status()
+        line["secondary_g1_sweep"] = sweep
+        del sw_p, sw_s
     # secondary 3: BBS+ batch verification (BASELINE configs[4]): 2^16 signatures x 10 message blocks over all ranks,
     # instances split across ranks with no collective; the timed region is the whole device pipeline of bbs_plus.verify_batch_device
     if not args.no_secondary and args.bbs_log_b > 0:

@@ -208,7 +208,7 @@ def test_reference_pods_pass_through(cuda):
 
 
 # ---- full-size properties (no oracle needed) --------------------------------------------------------------------------
-@pytest.mark.parametrize("log_n", [16, 20])
+@pytest.mark.parametrize("log_n", [10, 16, 20, 22])
 def test_g1_msm_full_size_linearity(cuda, log_n):
     """Σ s_i (k_i G) == (Σ s_i k_i mod r) G at BASELINE's n = 2^20, on device-resident data (the _dev entries)."""
     n = 1 << log_n
@@ -231,6 +231,27 @@ def test_g1_msm_full_size_linearity(cuda, log_n):
     h = n // 2
     parts = torch.cat([dv.g1_msm_partial(pts[:96 * h], d_s[:32 * h]), dv.g1_msm_partial(pts[96 * h:], d_s[32 * h:])])
     assert bytes(dv.g1_sum(parts).cpu().numpy()) == got
+
+
+def test_g1_msm_sweep_maximum(cuda):
+    """The top of BASELINE's sweep, n = 2^24: the one-call sum equals sixteen 2^20-term partials merged by the point-sum
+    entry (a different plan per call: the property holds only if both are the true sum), and is bit-identical run to run."""
+    n, chunk = 1 << 24, 1 << 20
+    dv = cuda.device
+    g = torch.Generator(device="cuda").manual_seed(2024)
+    d_k = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    d_s = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device="cuda", generator=g)
+    d_k[:, 0] %= 0x73
+    d_s[:, 0] %= 0x73
+    d_k, d_s = d_k.reshape(-1), d_s.reshape(-1)
+    pts = dv.g1_fixed_base_mul_batch(d_k)
+    del d_k
+    whole = bytes(dv.g1_msm(pts, d_s).cpu().numpy())
+    dv.sync_status()
+    parts = torch.cat([dv.g1_msm_partial(pts[96 * i:96 * (i + chunk)], d_s[32 * i:32 * (i + chunk)]) for i in range(0, n, chunk)])
+    assert bytes(dv.g1_sum(parts).cpu().numpy()) == whole
+    assert bytes(dv.g1_msm(pts, d_s).cpu().numpy()) == whole
+    assert whole != bytes(49)
 
 
 def test_g2_msm_full_size_linearity(cuda):

@@ -23,7 +23,7 @@ for f in sorted(glob.glob("$OUT/bench*.json")):
     except Exception as e: print(f, "unreadable", e)
 PY
 if [ "${SKIP_NCU:-0}" = "0" ] && [ $BE -eq 0 ]; then
-  CMD="python bench.py --steps 2 --warmup 1 --cpu-sample-log-n 10 --pairing-instances 16384 --g2-log-n 14 --bbs-log-b 10"
+  CMD="python bench.py --steps 2 --warmup 1 --cpu-sample-log-n 10 --pairing-instances 16384 --g2-log-n 14 --bbs-log-b 10 --sweep-max-log-n 12"
   timeout 600 $CMD > $OUT/plain_for_ncu.log 2>&1 &&
   timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
   echo "ncu launches exit $?" | tee -a $OUT/status.txt
