@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--pairing-instances", type=int, default=1 << 16)
-    ap.add_argument("--cpu-sample-log-n", type=int, default=15)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=18)
     ap.add_argument("--g2-log-n", type=int, default=18)
     ap.add_argument("--bbs-log-b", type=int, default=16)
     ap.add_argument("--sweep-max-log-n", type=int, default=24)

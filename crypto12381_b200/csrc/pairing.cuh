@@ -187,15 +187,27 @@ struct LineCoeffs {
     Fp2 aa, bb, cc;
 };
 
-// PAIR_double (pair_BLS12381.cpp:40-78): line through A,A then A <- 2A (ECP2_dbl)
+// PAIR_double (pair_BLS12381.cpp:40-78): line through A,A then A <- 2A (ECP2_dbl, ecp2_BLS12381.cpp:358-409).
+// The reference computes Y^2, YZ and Z^2 once for the line and once more inside the doubling; the values are the same
+// field elements, so they are computed once here.
 C12_HD LineCoeffs pair_double(Proj<Fp2>& A)
 {
     LineCoeffs l;
     Fp2 yy = sqr(A.y);
-    l.aa = mul_ip(neg(dbl(mul(A.y, A.z))));   // -2YZ (1+i)
-    l.bb = sub(mul_ip(mul12(sqr(A.z))), yy);  // 3b Z^2 (1+i) - Y^2
-    l.cc = mul3(sqr(A.x));                    // 3X^2
-    A = proj_dbl(A);
+    Fp2 yz = mul(A.y, A.z);
+    Fp2 t2 = FieldOps<Fp2>::mul_b3(sqr(A.z));   // 3b' Z^2 = 12 (1+i) Z^2
+    l.aa = mul_ip(neg(dbl(yz)));                // -2YZ (1+i)
+    l.bb = sub(t2, yy);                         // 3b' Z^2 - Y^2
+    l.cc = mul3(sqr(A.x));                      // 3X^2
+    // RCB15 Algorithm 9 on the shared products (proj_dbl in ec.cuh)
+    Fp2 xy = mul(A.x, A.y);
+    Fp2 z3 = mul8(yy);
+    Fp2 x3 = mul(t2, z3);
+    Fp2 y3 = add(yy, t2);
+    Fp2 t0 = sub(yy, mul3(t2));
+    A.z = mul(z3, yz);
+    A.y = add(mul(y3, t0), x3);
+    A.x = dbl(mul(t0, xy));
     return l;
 }
 
