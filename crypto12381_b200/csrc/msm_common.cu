@@ -89,6 +89,82 @@ int launch_bucket_order(const MsmPlan& pl, const uint32_t* start, const uint32_t
     return C12381_OK;
 }
 
+// ---- chunking of the bucket lists (virtual buckets) ------------------------------------------------------------------
+__global__ void k_chunk_counts(uint32_t total, uint32_t chunk, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                               uint32_t* __restrict__ out)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < total) out[b] = msm_chunks(end[b] - start[b], chunk);
+    if (b == total) out[b] = 0;
+}
+__global__ void k_chunk_pad(uint32_t vmax, uint32_t* __restrict__ keys, uint32_t* __restrict__ ids)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= vmax) return;
+    keys[v] = 255u;             // sorts behind every real chunk
+    ids[v] = 0xffffffffu;
+}
+__global__ void k_chunk_map(uint32_t total, uint32_t chunk, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                            const uint32_t* __restrict__ vstart, uint32_t* __restrict__ vbucket, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ ids)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    const uint32_t m = end[b] - start[b], n = msm_chunks(m, chunk), v0 = vstart[b];
+    for (uint32_t j = 0; j < n; ++j) {
+        uint32_t sz = m - j * chunk;
+        if (sz > chunk) sz = chunk;
+        vbucket[v0 + j] = b;
+        keys[v0 + j] = 255u - (sz > 255u ? 255u : sz);   // ascending key = descending length
+        ids[v0 + j] = v0 + j;
+    }
+}
+
+// layout of the scratch: vstart[total + 1] | vbucket[vmax] | keys, ids, keys2, ids2 [vmax each] | hist | scan tiles
+size_t chunk_order_scratch_words(const MsmPlan& pl)
+{
+    size_t tile_words = 0;
+    size_t hist = sort_scratch_words(pl.vmax, 1, &tile_words);
+    size_t scan_tiles = cdiv((size_t)pl.total + 1, SCAN_TILE) + 2;
+    return (size_t)pl.total + 1 + 5 * (size_t)pl.vmax + hist + tile_words + scan_tiles + 64;
+}
+
+int launch_chunk_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** vstart_out,
+                       uint32_t** vbucket_out, uint32_t** order, cudaStream_t s)
+{
+    size_t tile_words = 0;
+    size_t hist_words = sort_scratch_words(pl.vmax, 1, &tile_words);
+    uint32_t* vstart = scratch;
+    uint32_t* vbucket = vstart + pl.total + 1;
+    uint32_t* keys = vbucket + pl.vmax;
+    uint32_t* ids = keys + pl.vmax;
+    uint32_t* keys2 = ids + pl.vmax;
+    uint32_t* ids2 = keys2 + pl.vmax;
+    uint32_t* hist = ids2 + pl.vmax;
+    uint32_t* tiles = hist + hist_words;
+    uint32_t* scan_tiles = tiles + tile_words;
+    const uint32_t m = pl.total + 1;
+    k_chunk_counts<<<cdiv(m, 256), 256, 0, s>>>(pl.total, pl.chunk, start, end, vstart);
+    C12_LAUNCHED();
+    const uint32_t ntiles = cdiv(m, SCAN_TILE);
+    k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, s>>>(vstart, m, scan_tiles);
+    C12_LAUNCHED();
+    k_scan_top<<<1, SCAN_THREADS, 0, s>>>(scan_tiles, ntiles);
+    C12_LAUNCHED();
+    k_scan_apply<<<ntiles, SCAN_THREADS, 0, s>>>(vstart, m, scan_tiles);
+    C12_LAUNCHED();
+    k_chunk_pad<<<cdiv(pl.vmax, 256), 256, 0, s>>>(pl.vmax, keys, ids);
+    C12_LAUNCHED();
+    k_chunk_map<<<cdiv(pl.total, 256), 256, 0, s>>>(pl.total, pl.chunk, start, end, vstart, vbucket, keys, ids);
+    C12_LAUNCHED();
+    int rc = sort_pairs_segmented(keys, ids, keys2, ids2, pl.vmax, 1, 8, hist, tiles, s);
+    if (rc) return rc;
+    *vstart_out = vstart;
+    *vbucket_out = vbucket;
+    *order = ids;
+    return C12381_OK;
+}
+
 size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words)
 {
     size_t nblk = cdiv(n, SORT_TILE);

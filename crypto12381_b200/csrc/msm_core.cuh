@@ -41,6 +41,10 @@ struct MsmPlan {
     // multi-level bucket reduction: level k turns count[k] entries per window into count[k+1] (sum, total) pairs
     uint32_t levels;
     uint32_t count[MSM_MAX_LEVELS + 1];
+    // bucket lists longer than `chunk` entries are accumulated by several threads (one per chunk) and folded afterwards:
+    // bounds the serial chain of a thread under skewed scalars and evens out the load at large n
+    uint32_t chunk;       // entries per accumulation thread, a power of two in [32, 256]
+    uint32_t vmax;        // upper bound on the number of chunks (virtual buckets): total + n W / chunk
 };
 
 // Window width for n terms of `bits`-bit scalars: minimises  W * (10 n + 45 * 2^(c-1))  Fp products (10 per mixed
@@ -52,7 +56,12 @@ inline uint32_t msm_choose_window(uint64_t n, uint32_t bits = 256)
     uint32_t best = 4;
     double best_cost = 1e300;
     for (uint32_t c = 4; c <= 16; ++c) {
-        double W = (double)((bits + c - 1) / c);
+        const uint32_t Wi = (bits + c - 1) / c;
+        // the top window sees only  t = (bits - 1) - c (W - 1)  bits of the magnitudes: with t small, a handful of
+        // buckets would receive every term of that window (one long serial chain each) - skip such widths
+        const uint32_t t = (bits - 1) - c * (Wi - 1);
+        if (2 * t < c && c != 4) continue;
+        double W = (double)Wi;
         double cost = W * (10.0 * (double)n + 45.0 * (double)(1u << (c - 1)));
         if (cost < best_cost) {
             best_cost = cost;
@@ -93,6 +102,11 @@ inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, uint32_t parts = 1)
     while (seg < 64 && pl.total / seg > 49152u) seg <<= 1;
     if (seg > pl.half) seg = pl.half;
     msm_plan_levels(pl, seg);
+    const uint64_t N = (uint64_t)pl.n * pl.windows;
+    uint32_t chunk = 32;
+    while (chunk < 256 && (uint64_t)chunk * pl.total < 2 * N) chunk <<= 1;      // about twice the mean bucket load
+    pl.chunk = chunk;
+    pl.vmax = pl.total + (uint32_t)(N / chunk) + 1;
     return pl;
 }
 
@@ -410,13 +424,10 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
     }
 }
 
-// Body of the bucket-accumulation kernel for bucket b: sum of its (signed) affine terms.
-template <class F>
-C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint32_t* end, const uint32_t* vals,
-                                   const Affine<F>* points)
+// Body of the bucket-accumulation kernel for one chunk [lo, hi) of a bucket's sorted list: sum of its (signed) affine terms.
+template <class F> C12_HD Proj<F> msm_accumulate_range_body(uint32_t lo, uint32_t hi, const uint32_t* vals, const Affine<F>* points)
 {
     XYZZ<F> acc = xyzz_inf<F>();
-    uint32_t lo = start[b], hi = end[b];
 #pragma unroll 1
     for (uint32_t j = lo; j < hi; ++j) {
         uint32_t v = vals[j];
@@ -426,6 +437,22 @@ C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint
         xyzz_madd(acc, pt);
     }
     return xyzz_to_proj(acc);
+}
+template <class F>
+C12_HD Proj<F> msm_accumulate_body(uint32_t b, const uint32_t* start, const uint32_t* end, const uint32_t* vals,
+                                   const Affine<F>* points)
+{
+    return msm_accumulate_range_body<F>(start[b], end[b], vals, points);
+}
+// chunks of bucket b (at least one, so that every bucket owns a partial - possibly the identity)
+C12_HD uint32_t msm_chunks(uint32_t m, uint32_t chunk) { return m <= chunk ? 1u : (m + chunk - 1) / chunk; }
+// bucket b from its n partial sums (in chunk order)
+template <class F> C12_HD Proj<F> msm_fold_body(const Proj<F>* partials, uint32_t n)
+{
+    Proj<F> acc = partials[0];
+#pragma unroll 1
+    for (uint32_t j = 1; j < n; ++j) acc = proj_add(acc, partials[j]);
+    return acc;
 }
 
 // ---- batch-affine pre-reduction of the bucket lists -----------------------------------------------------------------

@@ -83,6 +83,11 @@ int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* star
 // order[] = bucket ids sorted by decreasing size (one 8-bit radix pass on min(size, 255)); scratch: 4 * total + hist words
 int launch_bucket_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** order, cudaStream_t s);
 size_t bucket_order_scratch_words(const MsmPlan& pl);
+// chunking of the bucket lists: vstart[b] = first chunk of bucket b (total + 1 entries), vbucket[v] = bucket of chunk v,
+// order[] = chunk ids by decreasing length, padded with 0xffffffff up to pl.vmax
+int launch_chunk_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** vstart, uint32_t** vbucket,
+                       uint32_t** order, cudaStream_t s);
+size_t chunk_order_scratch_words(const MsmPlan& pl);
 
 // p0 of every bucket: input of the exclusive scan that yields the A0 offsets (msm_common.cu)
 size_t ba_offsets_tile_words(const MsmPlan& pl);
@@ -168,17 +173,35 @@ __global__ void __launch_bounds__(128) k_accumulate_reduced(uint32_t total, cons
     buckets[b] = msm_accumulate_reduced_body<F>(b, start, end, vals, pts, rounds, o0, A0, A1);
 }
 
+// Accumulation over CHUNKS of the bucket lists (virtual buckets): thread t takes chunk order[t] - chunks are visited in
+// order of decreasing length (launch_chunk_order), so the 32 lanes of a warp run loops of equal length and the heaviest
+// start first - and leaves a partial sum; k_fold adds up the partials of each bucket.
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                                    const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
-                                                    const uint32_t* __restrict__ order, Proj<F>* __restrict__ buckets)
+__global__ void __launch_bounds__(128) k_accumulate(uint32_t vmax, uint32_t chunk, const uint32_t* __restrict__ start,
+                                                    const uint32_t* __restrict__ end, const uint32_t* __restrict__ vals,
+                                                    const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ order,
+                                                    const uint32_t* __restrict__ vbucket, const uint32_t* __restrict__ vstart,
+                                                    Proj<F>* __restrict__ vpartial)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    // buckets are visited in order of decreasing size (launch_bucket_order), so the 32 lanes of a warp run loops of
-    // (nearly) equal length and the heaviest buckets start first
-    uint32_t b = order[t];
-    buckets[b] = msm_accumulate_body<F>(b, start, end, vals, pts);
+    if (t >= vmax) return;
+    const uint32_t v = order[t];
+    if (v == 0xffffffffu) return;                   // padding behind the last chunk
+    const uint32_t b = vbucket[v];
+    const uint32_t lo = start[b] + (v - vstart[b]) * chunk;
+    uint32_t hi = lo + chunk;
+    if (hi > end[b]) hi = end[b];
+    vpartial[v] = msm_accumulate_range_body<F>(lo, hi, vals, pts);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_fold(uint32_t total, const uint32_t* __restrict__ vstart, const Proj<F>* __restrict__ vpartial,
+                                              Proj<F>* __restrict__ buckets)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    const uint32_t v0 = vstart[b];
+    buckets[b] = msm_fold_body<F>(vpartial + v0, vstart[b + 1] - v0);
 }
 
 // level 0 of the bucket reduction: one thread per (window, segment of seg_len buckets)
@@ -499,6 +522,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
     b += align_up(4 * hist_words) + align_up(4 * tile_words);
     b += 2 * align_up(4 * (size_t)pl.total);
     b += align_up(4 * bucket_order_scratch_words(pl));
+    b += align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
     if (msm_ba_rounds(pl)) {
         b += align_up(4 * ((size_t)pl.total + 1)) + align_up(4 * ba_offsets_tile_words(pl));
@@ -557,6 +581,8 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* start = (uint32_t*)arena_take(4 * (size_t)pl.total);
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)pl.total);
     uint32_t* order_scratch = (uint32_t*)arena_take(4 * bucket_order_scratch_words(pl));
+    uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));
+    Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
     const uint32_t ba_rounds = msm_ba_rounds(pl);
     uint32_t *o0 = nullptr, *o0_tiles = nullptr;
@@ -583,8 +609,11 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_CUDA(cudaEventRecord(c.pev[2], s));
     rc = launch_bucket_bounds(pl, keys, start, end, s);
     if (rc) return rc;
-    uint32_t* order = nullptr;
-    rc = launch_bucket_order(pl, start, end, order_scratch, &order, s);
+    uint32_t *order = nullptr, *vstart = nullptr, *vbucket = nullptr;
+    if (msm_ba_rounds(pl))
+        rc = launch_bucket_order(pl, start, end, order_scratch, &order, s);
+    else
+        rc = launch_chunk_order(pl, start, end, chunk_scratch, &vstart, &vbucket, &order, s);
     if (rc) return rc;
     if (points_ready) C12_CUDA(cudaStreamWaitEvent(s, points_ready, 0));
     C12_CUDA(cudaEventRecord(c.pev[3], s));
@@ -604,7 +633,9 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         k_accumulate_reduced<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, ba_rounds, o0, A0, A1, buckets);
         C12_LAUNCHED();
     } else {
-        k_accumulate<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, buckets);
+        k_accumulate<F><<<cdiv(pl.vmax, 128), 128, 0, s>>>(pl.vmax, pl.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
+        C12_LAUNCHED();
+        k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, vstart, vpartial, buckets);
         C12_LAUNCHED();
     }
     C12_CUDA(cudaEventRecord(c.ev[2], s));

@@ -23,7 +23,7 @@ MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, uint32_t parts)
 }
 
 // parts = 1: no split; MsmTraits<F>::PARTS: the split the device entries use
-template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0)
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0, uint32_t chunk_override = 0)
 {
     using W = Wire<F>;
     if (n_in == 0) {
@@ -60,7 +60,17 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
         }
     std::vector<Proj<F>> buckets(pl.total);
     if (rounds == 0) {
-        for (uint32_t b = 0; b < pl.total; ++b) buckets[b] = msm_accumulate_body<F>(b, start.data(), end.data(), sv.data(), P.data());
+        // k_accumulate over chunks of the bucket lists + k_fold
+        if (chunk_override) pl.chunk = chunk_override;
+        for (uint32_t b = 0; b < pl.total; ++b) {
+            uint32_t m = end[b] - start[b], nch = msm_chunks(m, pl.chunk);
+            std::vector<Proj<F>> parts(nch);
+            for (uint32_t j = 0; j < nch; ++j) {
+                uint32_t lo = start[b] + j * pl.chunk, hi = lo + pl.chunk > end[b] ? end[b] : lo + pl.chunk;
+                parts[j] = msm_accumulate_range_body<F>(lo, hi, sv.data(), P.data());
+            }
+            buckets[b] = msm_fold_body<F>(parts.data(), nch);
+        }
     } else {
         // the batch-affine pre-reduction rounds (k_ba_round), one inversion per pair here instead of one per block
         std::vector<uint32_t> o0(pl.total + 1, 0);
@@ -132,6 +142,11 @@ void hm_fp_op(int op, const uint8_t* a48, const uint8_t* b48, uint8_t* out48)
 
 int hm_g1_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out49) { return msm<Fp>(p, s, n, c, seg, out49); }
 int hm_g2_msm(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t seg, uint8_t* out97) { return msm<Fp2>(p, s, n, c, seg, out97); }
+// the device entries' scalar split with bucket lists cut into chunks of `chunk` entries (k_accumulate + k_fold)
+int hm_g1_msm_chunked(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t chunk, uint8_t* out49)
+{
+    return msm<Fp>(p, s, n, c, 0, out49, MsmTraits<Fp>::PARTS, 0, chunk);
+}
 // with `rounds` batch-affine pre-reduction rounds and the device entries' scalar split
 int hm_g1_msm_ba(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint8_t* out49)
 {

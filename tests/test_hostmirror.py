@@ -209,3 +209,22 @@ def test_msm_batch_affine_rounds(golden_msm):
                 out = ctypes.create_string_buffer(49)
                 assert l.hm_g1_msm_ba(H(e["points"]), H(e["scalars"]), n, c, rounds, out) == 0
                 assert out.raw == (want if want is not None else H(e["result"])), (key, rounds, c)
+
+
+def test_msm_chunked_accumulation(golden_msm):
+    """Bucket lists cut into chunks (k_accumulate over virtual buckets + k_fold), down to chunks of one and three entries."""
+    l = hm.lib()
+    H = bytes.fromhex
+    for case in golden_msm["cases"]:
+        if case["group"] != "g1" or case["n"] > 300:
+            continue
+        pts = hm.g1_fixed_base(H(case["point_scalars"]))
+        for c, chunk in ((2, 1), (3, 3), (5, 4), (8, 32)):
+            out = ctypes.create_string_buffer(49)
+            assert l.hm_g1_msm_chunked(pts, H(case["scalars"]), case["n"], c, chunk, out) == 0
+            assert out.raw == H(case["result"]), (case["n"], c, chunk)
+    e = golden_msm["edge_g1"]
+    out = ctypes.create_string_buffer(49)
+    assert l.hm_g1_msm_chunked(H(e["points"]), H(e["scalars"]), len(H(e["scalars"])) // 32, 3, 2, out) == 0 and out.raw == H(e["result"])
+    # window widths whose top window would be nearly empty are never chosen (G1 pieces are 127 bits: 14, 9, 7, 6, 5 are out)
+    assert {l.hm_choose_window_glv(1 << k) for k in range(4, 25)} <= {4, 8, 10, 11, 12, 13, 15, 16}
