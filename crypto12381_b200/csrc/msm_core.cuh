@@ -7,15 +7,17 @@
 // the same group sum is bit-exact.
 //
 // Every function here is a per-thread BODY (host+device) so the indexing and the algorithm can be executed
-// serially by tests/hostmirror on the CPU; the __global__ wrappers live in msm.cu.
+// serially by tests/hostmirror on the CPU; the __global__ wrappers live in msm_impl.cuh.
 //
-// Plan for n terms with window width c:  W = ceil(256 / c) windows, 2^(c-1) buckets per window.
-//   digit recode : k = sum_w d_w 2^(c w), d_w in [-2^(c-1)+1, 2^(c-1)]   (top window cannot overflow: W c >= 256)
-//   key          : window-local |d_w| - 1, stored at [w*n + i]; value = term index | sign << 31; zero digits get
+// Plan for n caller terms with window width c:
+//   scalar split : k -> `parts` signed pieces of 256 / parts bits (G1: 2 GLV halves, G2: 4 GLS quarters; msm_split), piece q
+//                  of term i is pipeline term q n + i and its point the endomorphism image of P_i (MsmTraits<F>::endo)
+//   digit recode : piece = sum_w d_w 2^(c w), d_w in [-2^(c-1)+1, 2^(c-1)], W = ceil(256 / parts / c) windows
+//   key          : window-local |d_w| - 1, stored at [w*n' + idx]; value = term index | sign << 31; zero digits get
 //                  key = 2^(c-1) (owns no bucket)
 //   (segmented radix sort by key, one segment per window; bucket b = w*2^(c-1) + key owns sorted[start[b] .. end[b]))
-//   accumulate   : one XYZZ accumulator per bucket, mixed additions of the affine terms
-//   reduce       : per window sum_k k * B_k by segmented running sums, then a tree
+//   accumulate   : XYZZ mixed additions of the affine terms, one thread per chunk of a bucket's list, partials folded
+//   reduce       : per window sum_k k * B_k by multi-level segmented running sums
 //   combine      : Horner over windows, c doublings per step
 #pragma once
 #include "ec.cuh"

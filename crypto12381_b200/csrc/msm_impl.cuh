@@ -3,14 +3,17 @@
 // field each so the two compile in parallel.  The per-thread bodies are in msm_core.cuh / scalar_mul.cuh.
 //
 // Pipeline of one MSM (all on the caller's stream, no host synchronisation inside):
-//   k_parse_points   wire bytes -> Montgomery affine points in HBM (canonical + on-curve checks)
-//   k_recode         scalars -> signed window digits -> (window-local key, term|sign) pairs, window-major
-//   radix sort       segmented per window, ceil(c/8) passes of hist / scan / scatter  (sort.cuh)
-//   k_bucket_bounds  [start, end) of every bucket in the sorted pairs
-//   k_accumulate     one thread per bucket: XYZZ mixed additions of its terms        <- the dominant kernel
-//   k_reduce1        one thread per (window, segment): running sums  sum_k k B_k
-//   k_reduce2        one block per window: warp-shuffle tree over the segment sums
-//   k_finish         Horner over windows, affine normalisation, wire encoding
+//   k_recode          scalars -> pieces -> signed window digits -> (window-local key, term|sign) pairs, window-major
+//   radix sort        segmented per window, ceil(c/8) passes of hist / scan / scatter  (sort.cuh)
+//   k_bucket_bounds   [start, end) of every bucket in the sorted pairs
+//   chunk order       long lists cut into chunks, chunk ids sorted by length (msm_common.cu)
+//   k_parse_points    wire bytes -> Montgomery affine points + endomorphism images (canonical + on-curve checks)
+//   k_accumulate      one thread per chunk: XYZZ mixed additions of its terms         <- the dominant kernel
+//   k_fold            partial sums of a bucket's chunks -> the bucket
+//   k_reduce_level0/k_reduce_level  multi-level running sums  sum_k k B_k  (upper levels lane-cooperative)
+//   k_reduce2         warp-shuffle tree sums of each level's segment sums
+//   k_finish          level recombination, Horner over windows (lane-cooperative doublings), normalisation, encoding
+// (optional, c12381_set_msm_batch_affine: k_ba_round pre-reduction rounds + k_accumulate_reduced instead of the chunked pair)
 #pragma once
 #include "common.cuh"
 #include "scalar_mul.cuh"
