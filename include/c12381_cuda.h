@@ -20,6 +20,9 @@
  *     Montgomery residue with R = 2^406; point1 192 B, point2 384 B, fp12 776 B) so the forwarding
  *     translation unit can pass its arguments through unchanged.
  *   - inputs are expected in the r-torsion subgroups (as produced by the reference), scalars reduced mod r.
+ *   - one context per process (one process per GPU), not re-entrant: every entry carves its scratch from the context's
+ *     single arena, so the "_dev" calls of a process must all be enqueued on ONE stream (or be separated by a
+ *     synchronisation of the previous call's stream); the host entries use the context's own stream and block.
  */
 #ifndef C12381_CUDA_H
 #define C12381_CUDA_H
