@@ -63,3 +63,18 @@ def test_host_argument_checks():
         bridge._pairs(bytes(96), bytes(192), 0)
     with pytest.raises(ValueError):
         bridge._pairs(bytes(96), bytes(192 * 2), 1)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under crypto12381_b200/ (or the entry points' product paths) imports,
+    links or executes it, and the library has no dependency on the reference shim."""
+    pkg = os.path.join(ROOT, "crypto12381_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inc", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "libref12381" not in text, os.path.join(dirpath, f)
+    from crypto12381_b200 import _lib
+    if os.path.exists(_lib.LIB_PATH):
+        needed = subprocess.run(["readelf", "-d", _lib.LIB_PATH], capture_output=True, text=True).stdout
+        assert "libref12381" not in needed and "miracl" not in needed.lower()

@@ -31,8 +31,11 @@ if [ "${SKIP_NCU:-0}" = "0" ] && [ $BE -eq 0 ]; then
   echo "ncu full accumulate exit $?" | tee -a $OUT/status.txt
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_pairing_coop -s 1 -c 1 -o $OUT/prof_pairing_coop -f $CMD > $OUT/ncu_full_pair_coop.log 2>&1
   echo "ncu full pairing (cooperative, 2^14 instances) exit $?" | tee -a $OUT/status.txt
+  ncu -i $OUT/prof_pairing_coop.ncu-rep --page raw --csv > $OUT/prof_pairing_coop.raw.csv 2>/dev/null && rm -f $OUT/prof_pairing_coop.ncu-rep
   CMD2="python bench.py --steps 2 --warmup 1 --cpu-sample-log-n 10 --pairing-instances 65536 --g2-log-n 14 --bbs-log-b 0 --sweep-max-log-n 0"
   timeout 1500 ncu --set full --clock-control none --import-source on -k 'regex:k_pairing$' -s 1 -c 1 -o $OUT/prof_pairing -f $CMD2 > $OUT/ncu_full_pair.log 2>&1
   echo "ncu full pairing (thread-per-instance, 2^16 instances) exit $?" | tee -a $OUT/status.txt
+  ncu -i $OUT/prof_pairing.ncu-rep --page raw --csv > $OUT/prof_pairing.raw.csv 2>/dev/null && rm -f $OUT/prof_pairing.ncu-rep   # gpurun_out/ is capped at 64 MiB
+  ncu -i $OUT/prof_accumulate.ncu-rep --page raw --csv > $OUT/prof_accumulate.raw.csv 2>/dev/null
 fi
 cat $OUT/status.txt

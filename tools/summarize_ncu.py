@@ -46,7 +46,10 @@ def launches(src, dst):
 
 
 def full(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if src.endswith(".csv"):     # the raw page exported on the GPU box (ncu -i rep --page raw --csv)
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     H, U = rows[0], rows[1]
     with open(dst, "w") as f:
