@@ -155,6 +155,24 @@ def to_bytes2(points: bytes) -> bytes:
     return out.raw[:G2_COMPRESSED * n]
 
 
+def is_member(points: bytes) -> bytes:
+    """PAIR_G1member for every 96-byte point (one verdict byte each; the identity is not a member, as in the reference)."""
+    ensure_init()
+    n = _count(points, G1_AFFINE, "points")
+    out = _out(n)
+    check(lib().c12381_g1_subgroup_check_batch(points, n, out))
+    return out.raw[:n]
+
+
+def is_member2(points: bytes) -> bytes:
+    """PAIR_G2member for every 192-byte point."""
+    ensure_init()
+    n = _count(points, G2_AFFINE, "points")
+    out = _out(n)
+    check(lib().c12381_g2_subgroup_check_batch(points, n, out))
+    return out.raw[:n]
+
+
 # ---- pairings ------------------------------------------------------------------------------------------------------
 def _pairs(g1s: bytes, g2s: bytes, k: int) -> int:
     if not 1 <= k <= _lib.MAX_PAIRS:

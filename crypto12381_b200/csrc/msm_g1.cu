@@ -17,4 +17,6 @@ int c12381_g1_decompress_batch(const uint8_t* in, size_t n, uint8_t* o) { return
 int c12381_g1_decompress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp>(in, n, o, true, st); }
 int c12381_g1_compress_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_convert_host<Fp>(in, n, o, false); }
 int c12381_g1_compress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp>(in, n, o, false, st); }
+int c12381_g1_subgroup_check_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_subgroup_host<Fp>(in, n, o); }
+int c12381_g1_subgroup_check_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_subgroup_dev<Fp>(in, n, o, st); }
 }

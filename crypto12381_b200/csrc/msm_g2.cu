@@ -17,4 +17,6 @@ int c12381_g2_decompress_batch(const uint8_t* in, size_t n, uint8_t* o) { return
 int c12381_g2_decompress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp2>(in, n, o, true, st); }
 int c12381_g2_compress_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_convert_host<Fp2>(in, n, o, false); }
 int c12381_g2_compress_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_convert_dev<Fp2>(in, n, o, false, st); }
+int c12381_g2_subgroup_check_batch(const uint8_t* in, size_t n, uint8_t* o) { return entry_subgroup_host<Fp2>(in, n, o); }
+int c12381_g2_subgroup_check_batch_dev(const uint8_t* in, size_t n, uint8_t* o, void* st) { return entry_subgroup_dev<Fp2>(in, n, o, st); }
 }

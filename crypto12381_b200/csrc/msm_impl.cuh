@@ -723,6 +723,27 @@ template <class F> int multi_fixed_base_run(const uint8_t* d_bases, size_t m, co
     return C12381_OK;
 }
 
+// verdict[i] = 1 iff points[i] is in the r-torsion subgroup (the identity is not: the reference's convention)
+template <class F>
+__global__ void __launch_bounds__(128) k_subgroup_check(const uint8_t* __restrict__ in, uint32_t n, uint8_t* __restrict__ out, int* flags)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p;
+    if (!Wire<F>::parse(p, in + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
+    out[i] = subgroup_member(p) ? 1 : 0;
+}
+
+template <class F> int subgroup_run(const uint8_t* d_in, size_t n, uint8_t* d_out, cudaStream_t s)
+{
+    Ctx& c = ctx();
+    if (n == 0) return C12381_OK;
+    if (n > 0x7fffffffull) return set_error(C12381_EARG, "subgroup_check: too many points");
+    k_subgroup_check<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, c.d_flags);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
 template <class F> int convert_run(const uint8_t* d_in, size_t n, uint8_t* d_out, bool decompress, cudaStream_t s)
 {
     Ctx& c = ctx();
@@ -904,6 +925,22 @@ template <class F> int entry_convert_host(const uint8_t* in_bytes, size_t n, uin
     return with_staged(in, sz, 1, out, n * (decompress ? Wire<F>::AFFINE : Wire<F>::COMPRESSED), 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
         return convert_run<F>(d_in[0], n, d_out, decompress, s);
     });
+}
+
+template <class F> int entry_subgroup_dev(const uint8_t* d_in, size_t n, uint8_t* d_out, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!d_in || !d_out)) return set_error(C12381_EARG, "subgroup_check: null pointer");
+    return subgroup_run<F>(d_in, n, d_out, pick_stream(stream));
+}
+
+template <class F> int entry_subgroup_host(const uint8_t* in_bytes, size_t n, uint8_t* out)
+{
+    C12_REQUIRE_CTX();
+    if (n && (!in_bytes || !out)) return set_error(C12381_EARG, "subgroup_check: null pointer");
+    const void* in[1] = {in_bytes};
+    size_t sz[1] = {n * Wire<F>::AFFINE};
+    return with_staged(in, sz, 1, out, n, 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) { return subgroup_run<F>(d_in[0], n, d_out, s); });
 }
 
 } // namespace c12

@@ -67,6 +67,34 @@ template <class F> C12_HD bool scalar_mul_body(const uint8_t* point_bytes, const
     return ok;
 }
 
+// ---- subgroup membership (PAIR_G1member / PAIR_G2member, pair_BLS12381.cpp:1034-1065,1068-1130) --------
+// The endomorphism test of Scott (eprint 2021/1130) the reference uses: a point of the curve is in the r-torsion subgroup
+// iff the endomorphism acts on it as its eigenvalue:  G1: (beta X, -Y) == [z^2]P,  G2: -psi(Q) == [z]Q,  z = |x|.
+// As in the reference the identity is NOT a member, and for G1 a point with [z]P == P (low order) is rejected.
+C12_HD Scalar256 scalar_z_abs()
+{
+    Scalar256 z;
+    for (int i = 0; i < 8; ++i) z.v[i] = 0;
+    z.v[0] = (uint32_t)(C12_X_ABS & 0xffffffffull);
+    z.v[1] = (uint32_t)(C12_X_ABS >> 32);
+    return z;
+}
+C12_HD bool subgroup_member(const Affine<Fp>& P)
+{
+    if (affine_is_inf(P)) return false;
+    const Scalar256 z = scalar_z_abs();
+    Proj<Fp> T = proj_scalar_mul(P, z);
+    if (proj_eq(proj_from_affine(P), T)) return false;
+    T = proj_scalar_mul(proj_to_affine(T), z);                       // [z^2]P
+    return proj_eq(proj_from_affine(MsmTraits<Fp>::endo(1, P)), T);
+}
+C12_HD bool subgroup_member(const Affine<Fp2>& Q)
+{
+    if (affine_is_inf(Q)) return false;
+    Proj<Fp2> T = proj_scalar_mul(Q, scalar_z_abs());                // [z]Q
+    return proj_eq(proj_from_affine(MsmTraits<Fp2>::endo(1, Q)), T); // endo(1, Q) = -psi(Q) = [z]Q on G2
+}
+
 template <class F> C12_HD Affine<F> generator();
 template <> C12_HD Affine<Fp> generator<Fp>() { return Affine<Fp>{g1_gen_x_m(), g1_gen_y_m()}; }
 template <> C12_HD Affine<Fp2> generator<Fp2>() { return Affine<Fp2>{g2_gen_x_m(), g2_gen_y_m()}; }

@@ -124,6 +124,15 @@ C12381_API int c12381_g2_decompress_batch_dev(const uint8_t* d_in97, size_t n, u
 C12381_API int c12381_g1_compress_batch_dev(const uint8_t* d_in96, size_t n, uint8_t* d_out49, void* stream);
 C12381_API int c12381_g2_compress_batch_dev(const uint8_t* d_in192, size_t n, uint8_t* d_out97, void* stream);
 
+/* ---- subgroup membership --------------------------------------------------------------------------- */
+/* verdicts[i] = 1 iff the (on-curve) point i lies in the r-torsion subgroup.  Same test and conventions as the reference's
+ * unbridged PAIR_G1member / PAIR_G2member (3rd-party/miracl-core/pair_BLS12381.cpp:1034-1130): the endomorphism test, the
+ * identity is NOT a member.  Off-curve / non-canonical input is C12381_EINPUT. */
+C12381_API int c12381_g1_subgroup_check_batch(const uint8_t* points96, size_t n, uint8_t* verdicts);
+C12381_API int c12381_g2_subgroup_check_batch(const uint8_t* points192, size_t n, uint8_t* verdicts);
+C12381_API int c12381_g1_subgroup_check_batch_dev(const uint8_t* d_points96, size_t n, uint8_t* d_verdicts, void* stream);
+C12381_API int c12381_g2_subgroup_check_batch_dev(const uint8_t* d_points192, size_t n, uint8_t* d_verdicts, void* stream);
+
 /* ---- pairings --------------------------------------------------------------------------------------------- */
 /* B instances, k pairs each (1 <= k <= C12381_MAX_PAIRS): g1s = B*k*96 B, g2s = B*k*192 B, instance-major.
  * miller: out[b] = conj-adjusted product of Miller loops, NOT exponentiated (576 B raw Fp12).

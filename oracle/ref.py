@@ -204,3 +204,17 @@ def fp12_to_bytes(buf, n: int) -> bytes:
     out = ctypes.create_string_buffer(576 * n)
     lib().ref_fp12_to_bytes(buf, _sz(n), out)
     return out.raw
+
+
+def g1_member(points: bytes) -> bytes:
+    n = len(points) // 96
+    out = ctypes.create_string_buffer(max(n, 1))
+    assert lib().ref_g1_member(points, _sz(n), out) == 1
+    return out.raw[:n]
+
+
+def g2_member(points: bytes) -> bytes:
+    n = len(points) // 192
+    out = ctypes.create_string_buffer(max(n, 1))
+    assert lib().ref_g2_member(points, _sz(n), out) == 1
+    return out.raw[:n]

@@ -15,6 +15,7 @@
 //   G2 out  : 97 B compressed MIRACL octet, identity = 97 zero bytes (g2_point.hpp:97-101)
 //   GT      : 576 B FP12_toOctet order (fp12_BLS12381.cpp:923-929)
 #include <crypto12381/miracl_core_interface.hpp>
+#include <miracl-core/pair_BLS12381.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -485,5 +486,25 @@ extern "C"
         auto* P = (mc::point2*)point2s;
         mc::point2 g; mc::get_default_generator(g);
         for (size_t i = 0; i < n; ++i) { mc::add(P[i], g); mc::sub(P[i], g); }
+    }
+
+    // PAIR_G1member / PAIR_G2member (pair_BLS12381.cpp:1034-1130; not bridged by crypto12381): one verdict byte per point
+    int ref_g1_member(const uint8_t* p96, size_t n, uint8_t* out)
+    {
+        for (size_t i = 0; i < n; ++i) {
+            mc::point1 P;
+            if (!g1_from_affine(P, p96 + 96 * i)) return 0;
+            out[i] = (uint8_t)BLS12381::PAIR_G1member(reinterpret_cast<BLS12381::ECP*>(&P));
+        }
+        return 1;
+    }
+    int ref_g2_member(const uint8_t* p192, size_t n, uint8_t* out)
+    {
+        for (size_t i = 0; i < n; ++i) {
+            mc::point2 P;
+            if (!g2_from_affine(P, p192 + 192 * i)) return 0;
+            out[i] = (uint8_t)BLS12381::PAIR_G2member(reinterpret_cast<BLS12381::ECP2*>(&P));
+        }
+        return 1;
     }
 }

@@ -290,4 +290,25 @@ int hm_g2_decompress(const uint8_t* in97, uint32_t n, uint8_t* out192)
     }
     return rc;
 }
+// subgroup membership bodies (k_subgroup_check); returns -1 if a point does not parse
+int hm_g1_member(const uint8_t* p96, uint32_t n, uint8_t* out)
+{
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        Affine<Fp> p;
+        if (!Wire<Fp>::parse(p, p96 + 96 * (size_t)i)) rc = -1;
+        out[i] = subgroup_member(p) ? 1 : 0;
+    }
+    return rc;
+}
+int hm_g2_member(const uint8_t* p192, uint32_t n, uint8_t* out)
+{
+    int rc = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        Affine<Fp2> p;
+        if (!Wire<Fp2>::parse(p, p192 + 192 * (size_t)i)) rc = -1;
+        out[i] = subgroup_member(p) ? 1 : 0;
+    }
+    return rc;
+}
 }

@@ -117,3 +117,17 @@ def test_bbs_plus_sign_verify_batch(gpu):
                   o.g1_mul(o.g1_from_affine_bytes(pp.h[:96]), ms[0]))
     assert len(ms) == 1 and ms[0] == (1 << 248) | int.from_bytes(b"Hello, BBS+!" + bytes(31 - 12), "big")
     assert o.pairing(A, W) == o.pairing(Bp, o.g2_from_affine_bytes(pp.g2))
+
+
+def test_subgroup_membership_batch(gpu):
+    bridge, _ = gpu
+    from test_hostmirror import _curve_points_outside_the_subgroups
+    out1, out2 = _curve_points_outside_the_subgroups()
+    rnd = random.Random(9)
+    ks = b"".join(be32(rnd.randrange(1, R)) for _ in range(200))
+    p1 = bridge.generator_power(ks) + out1 + bytes(96)
+    p2 = bridge.generator_power2(ks[:32 * 50]) + out2 + bytes(192)
+    v1, v2 = bridge.is_member(p1), bridge.is_member2(p2)
+    assert v1 == bytes([1] * 200 + [0] * 3 + [0]) and v2 == bytes([1] * 50 + [0] * 2 + [0])
+    if ref.available():
+        assert ref.g1_member(p1[:-96]) == v1[:-1] and ref.g2_member(p2[:-192]) == v2[:-1]

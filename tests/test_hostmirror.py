@@ -228,3 +228,39 @@ def test_msm_chunked_accumulation(golden_msm):
     assert l.hm_g1_msm_chunked(H(e["points"]), H(e["scalars"]), len(H(e["scalars"])) // 32, 3, 2, out) == 0 and out.raw == H(e["result"])
     # window widths whose top window would be nearly empty are never chosen (G1 pieces are 127 bits: 14, 9, 7, 6, 5 are out)
     assert {l.hm_choose_window_glv(1 << k) for k in range(4, 25)} <= {4, 8, 10, 11, 12, 13, 15, 16}
+
+
+def _curve_points_outside_the_subgroups():
+    """On-curve points with small x: with cofactors of ~2^126 (G1) and ~2^381 (G2) they are not in the r-torsion subgroups."""
+    from oracle import bls12381_oracle as o
+    g1, g2 = [], []
+    x = 1
+    while len(g1) < 3:
+        y = o.fp_sqrt((x * x * x + 4) % o.P)
+        if y is not None:
+            assert o.g1_add(o.g1_mul((x, y), o.R - 1), (x, y)) is not None     # [r]P != O
+            g1.append(o.g1_to_affine_bytes((x, y)))
+        x += 1
+    a = 1
+    while len(g2) < 2:
+        xx = (a, 1)
+        y = o.f2_sqrt(o.f2_add(o.f2_mul(o.f2_sqr(xx), xx), o.G2_B))
+        if y is not None:
+            g2.append(o.g2_to_affine_bytes((xx, y)))
+        a += 1
+    return b"".join(g1), b"".join(g2)
+
+
+def test_subgroup_membership(golden_points):
+    """subgroup_member (the body of k_subgroup_check) against MIRACL's PAIR_G1member / PAIR_G2member."""
+    l = hm.lib()
+    H = bytes.fromhex
+    out1, out2 = g1out, g2out = _curve_points_outside_the_subgroups()
+    p1 = H(golden_points["g1_affine"])[:96 * 4] + out1 + bytes(96)
+    p2 = H(golden_points["g2_affine"])[:192 * 3] + out2 + bytes(192)
+    v1, v2 = ctypes.create_string_buffer(len(p1) // 96), ctypes.create_string_buffer(len(p2) // 192)
+    assert l.hm_g1_member(p1, len(p1) // 96, v1) == 0 and l.hm_g2_member(p2, len(p2) // 192, v2) == 0
+    assert v1.raw == bytes([1] * 4 + [0] * 3 + [0]) and v2.raw == bytes([1] * 3 + [0] * 2 + [0])
+    from oracle import ref
+    if ref.available():
+        assert ref.g1_member(p1[:-96]) == v1.raw[:-1] and ref.g2_member(p2[:-192]) == v2.raw[:-1]
