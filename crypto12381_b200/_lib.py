@@ -59,6 +59,10 @@ SIGNATURES = {
     "c12381_g2_subgroup_check_batch": (_i, [_p, _sz, _p]),
     "c12381_g1_subgroup_check_batch_dev": (_i, [_p, _sz, _p, _p]),
     "c12381_g2_subgroup_check_batch_dev": (_i, [_p, _sz, _p, _p]),
+    "c12381_sha3_512_batch": (_i, [_p, _sz, _sz, _p]),
+    "c12381_hash_to_zp_batch": (_i, [_p, _sz, _sz, _p]),
+    "c12381_sha3_512_batch_dev": (_i, [_p, _sz, _sz, _p, _p]),
+    "c12381_hash_to_zp_batch_dev": (_i, [_p, _sz, _sz, _p, _p]),
     "c12381_miller_batch": (_i, [_p, _p, _sz, _i, _p]),
     "c12381_final_exp_batch": (_i, [_p, _sz, _p]),
     "c12381_pairing_product_batch": (_i, [_p, _p, _sz, _i, _p]),

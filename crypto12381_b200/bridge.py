@@ -173,6 +173,23 @@ def is_member2(points: bytes) -> bytes:
     return out.raw[:n]
 
 
+# ---- hash(...) : SHA3-512 over serialised bytes, and hash(...) -> Zp (set.hpp:317-460, zp_number.hpp:538-547), batched ------
+def sha3_512(messages: bytes, message_len: int) -> bytes:
+    ensure_init()
+    B = _count(messages, message_len, "messages") if message_len else 0
+    out = _out(64 * B)
+    check(lib().c12381_sha3_512_batch(messages, message_len, B, out))
+    return out.raw[:64 * B]
+
+
+def hash_to_zp(messages: bytes, message_len: int) -> bytes:
+    ensure_init()
+    B = _count(messages, message_len, "messages") if message_len else 0
+    out = _out(32 * B)
+    check(lib().c12381_hash_to_zp_batch(messages, message_len, B, out))
+    return out.raw[:32 * B]
+
+
 # ---- pairings ------------------------------------------------------------------------------------------------------
 def _pairs(g1s: bytes, g2s: bytes, k: int) -> int:
     if not 1 <= k <= _lib.MAX_PAIRS:

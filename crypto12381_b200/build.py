@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libc12381_cuda.so")
-UNITS = ["ctx", "msm_common", "msm_g1", "msm_g2", "pairing", "miracl_pod"]
+UNITS = ["ctx", "msm_common", "msm_g1", "msm_g2", "pairing", "miracl_pod", "hash"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xptxas", "-v"]
 

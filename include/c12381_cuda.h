@@ -133,6 +133,16 @@ C12381_API int c12381_g2_subgroup_check_batch(const uint8_t* points192, size_t n
 C12381_API int c12381_g1_subgroup_check_batch_dev(const uint8_t* d_points96, size_t n, uint8_t* d_verdicts, void* stream);
 C12381_API int c12381_g2_subgroup_check_batch_dev(const uint8_t* d_points192, size_t n, uint8_t* d_verdicts, void* stream);
 
+/* ---- Fiat-Shamir hashing in batch -------------------------------------------------------------------- */
+/* B messages of msg_len bytes each, back to back.  sha3_512: the 64-byte SHA3-512 digests - what hash_state yields for the
+ * serialised bytes it absorbed (include/crypto12381/set.hpp:317-392 -> sha3_init / sha3_process / sha3_hash,
+ * src/miracl_core_interface.cpp:12-25 -> 3rd-party/miracl-core/hash.cpp:480-554).  hash_to_zp: that digest read as a
+ * big-endian 512-bit integer reduced mod r, 32 B big-endian (Zp's from_hash, zp_number.hpp:538-547). */
+C12381_API int c12381_sha3_512_batch(const uint8_t* msgs, size_t msg_len, size_t B, uint8_t* out64);
+C12381_API int c12381_hash_to_zp_batch(const uint8_t* msgs, size_t msg_len, size_t B, uint8_t* out32);
+C12381_API int c12381_sha3_512_batch_dev(const uint8_t* d_msgs, size_t msg_len, size_t B, uint8_t* d_out64, void* stream);
+C12381_API int c12381_hash_to_zp_batch_dev(const uint8_t* d_msgs, size_t msg_len, size_t B, uint8_t* d_out32, void* stream);
+
 /* ---- pairings --------------------------------------------------------------------------------------------- */
 /* B instances, k pairs each (1 <= k <= C12381_MAX_PAIRS): g1s = B*k*96 B, g2s = B*k*192 B, instance-major.
  * miller: out[b] = conj-adjusted product of Miller loops, NOT exponentiated (576 B raw Fp12).

@@ -11,6 +11,7 @@
 #include "../../crypto12381_b200/csrc/scalar_mul.cuh"
 #include "../../crypto12381_b200/csrc/pairing.cuh"
 #include "../../crypto12381_b200/csrc/miracl_pod.cuh"
+#include "../../crypto12381_b200/csrc/hash.cuh"
 
 using namespace c12;
 
@@ -311,4 +312,7 @@ int hm_g2_member(const uint8_t* p192, uint32_t n, uint8_t* out)
     }
     return rc;
 }
+// SHA3-512 / hash-to-Zp bodies (k_sha3_512)
+void hm_sha3_512(const uint8_t* msg, uint32_t len, uint8_t* out64) { sha3_512(msg, len, out64); }
+void hm_hash_to_zp(const uint8_t* msg, uint32_t len, uint8_t* out32) { hash_to_zp_body(msg, len, out32); }
 }

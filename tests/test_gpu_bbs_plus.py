@@ -131,3 +131,17 @@ def test_subgroup_membership_batch(gpu):
     assert v1 == bytes([1] * 200 + [0] * 3 + [0]) and v2 == bytes([1] * 50 + [0] * 2 + [0])
     if ref.available():
         assert ref.g1_member(p1[:-96]) == v1[:-1] and ref.g2_member(p2[:-192]) == v2[:-1]
+
+
+def test_sha3_512_and_hash_to_zp_batch(gpu):
+    """Batched Fiat-Shamir hashing against hashlib (FIPS 202) and, for the digest, the reference's own SHA3 through its bridge."""
+    import hashlib
+    bridge, _ = gpu
+    rnd = random.Random(14)
+    for L, B in ((0, 3), (49, 1000), (72, 17), (145, 513), (49 + 97 + 576, 64)):
+        msgs = bytes(rnd.randrange(256) for _ in range(L * B))
+        want = [hashlib.sha3_512(msgs[L * i:L * (i + 1)]).digest() for i in range(B)]
+        if L:
+            assert bridge.sha3_512(msgs, L) == b"".join(want)
+            assert bridge.hash_to_zp(msgs, L) == b"".join((int.from_bytes(d, "big") % R).to_bytes(32, "big") for d in want)
+    assert bridge.sha3_512(b"", 0) == b""

@@ -264,3 +264,21 @@ def test_subgroup_membership(golden_points):
     from oracle import ref
     if ref.available():
         assert ref.g1_member(p1[:-96]) == v1.raw[:-1] and ref.g2_member(p2[:-192]) == v2.raw[:-1]
+
+
+def test_sha3_512_and_hash_to_zp():
+    """The bodies of k_sha3_512 against hashlib and the reference's only hashing vector (unit-tests/miracl_core_interface.cpp:10-33)."""
+    import hashlib
+    l = hm.lib()
+    rnd = random.Random(13)
+    empty = ctypes.create_string_buffer(64)
+    l.hm_sha3_512(b"", 0, empty)
+    assert empty.raw.hex().startswith("a69f73cca23a9ac5c8b567dc185a756e97c982164fe25859e0d1dcc1475c80a6")
+    for n in (0, 1, 31, 71, 72, 73, 143, 144, 145, 576, 1000):
+        msg = bytes(rnd.randrange(256) for _ in range(n))
+        d, z = ctypes.create_string_buffer(64), ctypes.create_string_buffer(32)
+        l.hm_sha3_512(msg, n, d)
+        l.hm_hash_to_zp(msg, n, z)
+        want = hashlib.sha3_512(msg).digest()
+        assert d.raw == want, n
+        assert z.raw == (int.from_bytes(want, "big") % ps.R).to_bytes(32, "big"), n
