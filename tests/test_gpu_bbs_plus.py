@@ -145,3 +145,29 @@ def test_sha3_512_and_hash_to_zp_batch(gpu):
             assert bridge.sha3_512(msgs, L) == b"".join(want)
             assert bridge.hash_to_zp(msgs, L) == b"".join((int.from_bytes(d, "big") % R).to_bytes(32, "big") for d in want)
     assert bridge.sha3_512(b"", 0) == b""
+
+
+def test_bbs_plus_aggregate_verification(gpu):
+    """The random-linear-combination batch check agrees with the per-signature verdicts: accepts a valid batch, rejects one
+    with a single tampered signature (whatever its position)."""
+    bridge, bbs = gpu
+    rnd = random.Random(10)
+    n = 10
+    gens = bridge.to_bytes(bridge.generator_power(b"".join(be32(rnd.randrange(1, R)) for _ in range(n + 2))))
+    g2 = bridge.to_bytes2(bridge.generator_power2(be32(rnd.randrange(1, R))))
+    pp = bbs.PublicParameters(gens[:49] + g2 + gens[49:98], [gens[49 * i:49 * i + 49] for i in range(2, n + 2)])
+    gamma = rnd.randrange(1, R)
+    pk = bridge.multiply2(pp.g2, be32(gamma))
+    B = 300
+    msgs = [bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 31 * n))) for _ in range(B)]
+    xs, rs = [rnd.randrange(R) for _ in range(B)], [rnd.randrange(R) for _ in range(B)]
+    sigs = bbs.sign_batch(pp, gamma.to_bytes(48, "big"), msgs, xs, rs)
+    assert bbs.verify_batch_aggregate(pp, pk, msgs, sigs, b"seed-1") is True
+    for pos in (0, 137, B - 1):
+        bad = list(sigs)
+        bad[pos] = sigs[pos][:49] + ((xs[pos] + 1) % R).to_bytes(48, "big") + sigs[pos][97:]
+        assert bbs.verify_batch_aggregate(pp, pk, msgs, bad, b"seed-2") is False
+        assert bbs.verify_batch(pp, pk, msgs, bad) == [i != pos for i in range(B)]
+    swapped = list(msgs)
+    swapped[5], swapped[6] = msgs[6], msgs[5]
+    assert bbs.verify_batch_aggregate(pp, pk, swapped, sigs, b"seed-3") is False
