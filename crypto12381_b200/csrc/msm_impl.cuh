@@ -420,24 +420,32 @@ __global__ void __launch_bounds__(128) k_scalar_mul(const uint8_t* __restrict__ 
 // device; a scalar is recoded into 32 signed 8-bit digits and g^x is 32 mixed additions - no doublings.
 constexpr uint32_t FB_WINDOWS = 32, FB_HALF = 128;
 
-// bases = nullptr: the default generator (one table); else m wire-format affine bases, table j at [j * 4096]
+// Table construction in two steps.  k_fixed_base_windows: thread (j, w) -> W[j][w] = 2^(8w) base_j (8w doublings: the
+// only long dependent chain, 384 threads for 12 bases).  k_fixed_base_table: thread (j, w, d) -> d W[j][w] by
+// double-and-add over the 8 bits of d (at most 7 + 7 point operations), normalised to affine.
+// bases = nullptr: the default generator (one table); else m wire-format affine bases, table j at [j * 4096].
 template <class F>
-__global__ void __launch_bounds__(128) k_fixed_base_table(const uint8_t* __restrict__ bases, uint32_t m, Affine<F>* __restrict__ table, int* flags)
+__global__ void __launch_bounds__(64) k_fixed_base_windows(const uint8_t* __restrict__ bases, uint32_t m, Proj<F>* __restrict__ wbase, int* flags)
+{
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m * FB_WINDOWS) return;
+    const uint32_t j = t / FB_WINDOWS, w = t % FB_WINDOWS;
+    Affine<F> base = generator<F>();
+    if (bases && !Wire<F>::parse(base, bases + (size_t)Wire<F>::AFFINE * j)) atomicOr(flags, FLAG_BAD_POINT);
+    Proj<F> acc = proj_from_affine(base);
+#pragma unroll 1
+    for (uint32_t i = 0; i < 8 * w; ++i) acc = proj_dbl(acc);
+    wbase[t] = acc;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_fixed_base_table(uint32_t m, const Proj<F>* __restrict__ wbase, Affine<F>* __restrict__ table)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m * FB_WINDOWS * FB_HALF) return;
-    const uint32_t j = t / (FB_WINDOWS * FB_HALF), e = t % (FB_WINDOWS * FB_HALF);
-    const uint32_t w = e / FB_HALF, d = e % FB_HALF + 1;
-    Affine<F> base = generator<F>();
-    if (bases && !Wire<F>::parse(base, bases + (size_t)Wire<F>::AFFINE * j)) atomicOr(flags, FLAG_BAD_POINT);
-    Scalar256 k;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) k.v[i] = 0;
-    // d << 8w  (d <= 128 needs 8 bits)
-    const uint32_t bit = 8 * w;
-    k.v[bit >> 5] = d << (bit & 31u);
-    if ((bit & 31u) > 24 && (bit >> 5) + 1 < 8) k.v[(bit >> 5) + 1] = d >> (32 - (bit & 31u));
-    table[t] = proj_to_affine(proj_scalar_mul(base, k));
+    const uint32_t d = t % FB_HALF + 1;
+    const Proj<F> base = wbase[t / FB_HALF];
+    table[t] = proj_to_affine(proj_mul_small(base, d));
 }
 
 // acc += k * (the base of `table`), k < r as 32 signed 8-bit digits: 32 mixed additions, no doublings
@@ -694,9 +702,12 @@ template <class F> int fixed_base_run(const uint8_t* d_scalars, size_t n, uint8_
     if (n == 0) return C12381_OK;
     if (n > 0x7fffffffull) return set_error(C12381_EARG, "fixed_base: too many terms");
     Affine<F>*& table = fixed_base_table_slot<F>();
-    if (!table) {   // first use on this context: build the window table (4,096 scalar multiplications, once)
-        C12_CUDA(cudaMalloc(&table, sizeof(Affine<F>) * FB_WINDOWS * FB_HALF));
-        k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(nullptr, 1, table, c.d_flags);
+    if (!table) {   // first use on this context: build the window table once
+        C12_CUDA(cudaMalloc(&table, sizeof(Affine<F>) * FB_WINDOWS * FB_HALF + sizeof(Proj<F>) * FB_WINDOWS));
+        Proj<F>* wbase = reinterpret_cast<Proj<F>*>(table + FB_WINDOWS * FB_HALF);
+        k_fixed_base_windows<F><<<cdiv(FB_WINDOWS, 64), 64, 0, s>>>(nullptr, 1, wbase, c.d_flags);
+        C12_LAUNCHED();
+        k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(1, wbase, table);
         C12_LAUNCHED();
         C12_CUDA(cudaStreamSynchronize(s));   // later calls may come on other streams
     }
@@ -707,7 +718,10 @@ template <class F> int fixed_base_run(const uint8_t* d_scalars, size_t n, uint8_
 
 // out[b] = sum_j scalars[b * m + j] * bases[j] for m caller-supplied bases shared by all B instances (window tables are
 // built per call in the caller's arena reservation: multi_fixed_scratch<F>(m) bytes)
-template <class F> size_t multi_fixed_scratch(size_t m) { return align_up(sizeof(Affine<F>) * m * FB_WINDOWS * FB_HALF) + 4096; }
+template <class F> size_t multi_fixed_scratch(size_t m)
+{
+    return align_up(sizeof(Affine<F>) * m * FB_WINDOWS * FB_HALF) + align_up(sizeof(Proj<F>) * m * FB_WINDOWS) + 4096;
+}
 template <class F> int multi_fixed_base_run(const uint8_t* d_bases, size_t m, const uint8_t* d_scalars, size_t B, uint8_t* d_out, cudaStream_t s)
 {
     Ctx& c = ctx();
@@ -715,8 +729,11 @@ template <class F> int multi_fixed_base_run(const uint8_t* d_bases, size_t m, co
     if (m == 0 || m > 4096) return set_error(C12381_EARG, "multi_fixed_base: between 1 and 4096 bases");
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "multi_fixed_base: too many instances");
     Affine<F>* table = (Affine<F>*)arena_take(sizeof(Affine<F>) * m * FB_WINDOWS * FB_HALF);
-    if (!table) return set_error(C12381_ECUDA, "multi_fixed_base: scratch arena bound too small");
-    k_fixed_base_table<F><<<cdiv(m * FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(d_bases, (uint32_t)m, table, c.d_flags);
+    Proj<F>* wbase = (Proj<F>*)arena_take(sizeof(Proj<F>) * m * FB_WINDOWS);
+    if (!wbase) return set_error(C12381_ECUDA, "multi_fixed_base: scratch arena bound too small");
+    k_fixed_base_windows<F><<<cdiv(m * FB_WINDOWS, 64), 64, 0, s>>>(d_bases, (uint32_t)m, wbase, c.d_flags);
+    C12_LAUNCHED();
+    k_fixed_base_table<F><<<cdiv(m * FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>((uint32_t)m, wbase, table);
     C12_LAUNCHED();
     k_fixed_base<F><<<cdiv(B, 128), 128, 0, s>>>(d_scalars, (uint32_t)B, (uint32_t)m, table, d_out, c.d_flags);
     C12_LAUNCHED();

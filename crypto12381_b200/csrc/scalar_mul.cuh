@@ -53,13 +53,51 @@ template <class F> C12_HD Proj<F> proj_scalar_mul(const Affine<F>& p, const Scal
     return acc;
 }
 
+// k * P for P in the r-torsion subgroup through the scalar split of the MSM (msm_split: G1 two GLV halves, G2 four GLS
+// quarters) and a joint double-and-add over the 2^parts - 1 subset sums of the endomorphism images - what the reference
+// does with glv() + ECP_mul2 and gs() + ECP2_mul4 (pair_BLS12381.cpp:759-983).  128 (G1) / 64 (G2) doublings instead of 256.
+template <class F> C12_HD Proj<F> proj_scalar_mul_split(const Affine<F>& p, const Scalar256& k)
+{
+    if (affine_is_inf(p)) return proj_inf<F>();
+    constexpr uint32_t PARTS = MsmTraits<F>::PARTS, NT = 1u << PARTS, BITS = 256 / PARTS;
+    ScalarParts sp;
+    msm_split(k, PARTS, sp);
+    Affine<F> base[PARTS];
+    base[0] = p;
+    for (uint32_t q = 1; q < PARTS; ++q) base[q] = MsmTraits<F>::endo(q, p);
+    for (uint32_t q = 0; q < PARTS; ++q)
+        if (sp.neg[q]) base[q].y = neg(base[q].y);
+    Proj<F> tab[NT];
+    tab[0] = proj_inf<F>();
+#pragma unroll 1
+    for (uint32_t m = 1; m < NT; ++m) {
+        uint32_t j = 0;
+        while (!((m >> j) & 1u)) ++j;
+        const uint32_t rest = m ^ (1u << j);
+        tab[m] = rest ? proj_add_affine_nz(tab[rest], base[j]) : proj_from_affine(base[j]);
+    }
+    Proj<F> acc = proj_inf<F>();
+    bool started = false;
+#pragma unroll 1
+    for (int bit = (int)BITS - 1; bit >= 0; --bit) {
+        if (started) acc = proj_dbl(acc);
+        uint32_t m = 0;
+        for (uint32_t q = 0; q < PARTS; ++q) m |= ((sp.mag[q][bit >> 5] >> (bit & 31)) & 1u) << q;
+        if (m) {
+            acc = started ? proj_add(acc, tab[m]) : tab[m];
+            started = true;
+        }
+    }
+    return acc;
+}
+
 // affine_out = false: Wire<F>::COMPRESSED bytes; true: Wire<F>::AFFINE bytes
 template <class F> C12_HD bool scalar_mul_body(const uint8_t* point_bytes, const uint8_t* scalar_be32, uint8_t* out, bool affine_out = false)
 {
     Affine<F> p;
     bool ok = Wire<F>::parse(p, point_bytes);
     Scalar256 k = scalar_from_be32(scalar_be32);
-    Proj<F> r = proj_scalar_mul(p, k);
+    Proj<F> r = proj_scalar_mul_split(p, k);
     if (affine_out)
         Wire<F>::serialize(out, proj_to_affine(r));
     else
