@@ -40,18 +40,25 @@ C12_HD Fp2 select(bool c, const Fp2& x, const Fp2& y)
 // would otherwise inline ~2,000 SASS instructions per use and thrash the instruction cache.  Operands and result
 // travel BY VALUE (in registers): by-reference parameters of a non-inlined function would force every caller to
 // park both operands in local memory first.
+// -DC12_FP2_INLINE_MULS: the three (two) independent Montgomery products are inlined into the Fp2 product so that ptxas
+// can interleave their carry chains (A/B knob for the latency-bound kernels, profiles/).
+#if defined(C12_FP2_INLINE_MULS)
+#define C12_FP2_MUL fp_mul_inl
+#else
+#define C12_FP2_MUL fp_mul
+#endif
 C12_HD Fp2 fp2_mul_body(const Fp2& x, const Fp2& y)
 {
-    Fp t0 = fp_mul(x.a, y.a);
-    Fp t1 = fp_mul(x.b, y.b);
-    Fp t2 = fp_mul(fp_add(x.a, x.b), fp_add(y.a, y.b));
+    Fp t0 = C12_FP2_MUL(x.a, y.a);
+    Fp t1 = C12_FP2_MUL(x.b, y.b);
+    Fp t2 = C12_FP2_MUL(fp_add(x.a, x.b), fp_add(y.a, y.b));
     return Fp2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
 }
 // (a+b)(a-b) + 2ab i : 2 Fp products
 C12_HD Fp2 fp2_sqr_body(const Fp2& x)
 {
-    Fp t0 = fp_mul(fp_add(x.a, x.b), fp_sub(x.a, x.b));
-    Fp t1 = fp_mul(x.a, x.b);
+    Fp t0 = C12_FP2_MUL(fp_add(x.a, x.b), fp_sub(x.a, x.b));
+    Fp t1 = C12_FP2_MUL(x.a, x.b);
     return Fp2{t0, fp_dbl(t1)};
 }
 #if defined(__CUDA_ARCH__)

@@ -1,4 +1,8 @@
 // G2 instantiation of the MSM / scalar-multiplication pipeline and its C-ABI entries (include/c12381_cuda.h).
+// In this translation unit the Montgomery products inside an Fp2 product are inlined so that ptxas interleaves their carry
+// chains: measured +9 % on the G2 bucket accumulation (profiles/r01ab_fp2_inline_ab.txt); the register-capped cooperative
+// pairing kernels lose 20 % with the same setting, so pairing.cu keeps the calls.
+#define C12_FP2_INLINE_MULS 1
 #include "msm_impl.cuh"
 using namespace c12;
 

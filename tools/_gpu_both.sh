@@ -1,8 +1,6 @@
 mkdir -p gpurun_out/$TAG
-timeout 600 python tools/_sweep_probe.py 2>&1 | tee gpurun_out/$TAG/sweep_probe.txt | tail -20 | cut -c1-230
-TAG=$TAG SKIP_NCU=1 bash tools/_gpu_quick.sh
-python - <<PY
-import json
-d=json.load(open("gpurun_out/$TAG/bench.json"))
-print(" sweep", [(s["log_n"], round(s["ms"],3), "%.3g" % s["points_per_s"], s["window_bits"]) for s in d.get("secondary_g1_sweep",[])])
-PY
+for V in "" fp2inl; do
+echo "variant=$V" | tee -a gpurun_out/$TAG/ab.txt
+C12381_LIB_VARIANT=$V timeout 600 python tools/_pairing_bench.py 4 1,16384,65536 2>&1 | tee -a gpurun_out/$TAG/ab.txt | tail -6
+C12381_LIB_VARIANT=$V timeout 600 python tools/_msm_bench.py 2>&1 | grep "rounds=0" | cut -c1-250 | tee -a gpurun_out/$TAG/ab.txt
+done
