@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_gt_pow(const uint8_t* __restri
 #define C12_PAIR_WARPS 4            // warps per block: 20 instances, 57,600 B of shared memory; three blocks per SM
 #endif
 #ifndef C12_PAIR_BLOCKS
-#define C12_PAIR_BLOCKS 3           // resident blocks per SM the register allocation is bounded for
+#define C12_PAIR_BLOCKS 2           // resident blocks per SM the register allocation is bounded for (3 measured 10 % slower)
 #endif
 constexpr int PC_WARPS = C12_PAIR_WARPS;
 constexpr int PC_THREADS = PC_WARPS * 32;
