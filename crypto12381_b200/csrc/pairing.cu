@@ -199,11 +199,19 @@ __global__ void __launch_bounds__(PC_THREADS, C12_PAIR_BLOCKS) k_gt_pow_coop(con
 }
 
 // Two implementations of every entry: thread-per-instance (pairing.cuh bodies) and six-lanes-per-instance
-// (pairing_coop.cuh).  At large batch sizes they measure within 5 % of each other (profiles/r01n: 1.88 M against
-// 1.81 M pairings/s at 2^16 x 4), the former slightly ahead; below ~16 instances per SM the cooperative kernels win by
-// having six times the parallelism per instance (a single pairing is ~2.5x faster).  C12381_PAIRING=scalar|coop forces
-// one of them.
-constexpr size_t PAIRING_COOP_BELOW = 16384 + 1;
+// (pairing_coop.cuh).  Measured (profiles/r01ac, r01t): the cooperative kernels run at ~1.8 M pairings/s from 2^14 four-pair
+// instances up and have six times the parallelism per instance (a single product: 9 ms against 47 ms); the
+// thread-per-instance kernel is latency-bound per thread, ~70 ms per wave of SMs x 256 threads however full the wave is,
+// i.e. 2.18 M/s x the fill of its last wave.  So: thread-per-instance when the batch fills its waves to >= 84 %, the
+// cooperative kernels otherwise.  C12381_PAIRING=scalar|coop or c12381_set_pairing_kernel force one of them.
+static bool scalar_fills_its_waves(size_t B)
+{
+    static int sms = 0;
+    if (!sms && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx().device) != cudaSuccess) sms = 148;
+    const size_t wave = (size_t)sms * 256;
+    const size_t waves = (B + wave - 1) / wave;
+    return B >= 16384 && (double)B >= 0.84 * (double)(waves * wave);
+}
 
 static int g_pairing_kernel = -1;   // 0 automatic, 1 thread-per-instance, 2 cooperative (c12381_set_pairing_kernel)
 
@@ -215,7 +223,7 @@ static bool use_scalar_kernels(size_t B)
     }
     if (g_pairing_kernel == 1) return true;
     if (g_pairing_kernel == 2) return false;
-    return B >= PAIRING_COOP_BELOW;
+    return scalar_fills_its_waves(B);
 }
 
 static int pc_configure()
