@@ -1,6 +1,6 @@
 """GPU box: phases of the host-pointer G1 MSM entry (two-phase accumulation behind the upload)."""
 import os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from crypto12381_b200 import _lib, device as dv
 _lib.init(0)

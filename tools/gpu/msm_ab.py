@@ -1,6 +1,6 @@
 """MSM-only A/B on the GPU box: batch-affine rounds 0/1/2 at n = 2^20 (G1) and 2^18 (G2)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from crypto12381_b200 import _lib, device as dv
 _lib.init(0)

@@ -1,7 +1,7 @@
 """Pairing-only benchmark (GPU box): both kernel families over a range of batch sizes.
 python tools/_pairing_bench.py [k]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from crypto12381_b200 import _lib, device as dv
 k = int(sys.argv[1]) if len(sys.argv) > 1 else 4

@@ -1,6 +1,6 @@
 """GPU box: per-phase times of the G1 MSM across the small end of the sweep."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from crypto12381_b200 import _lib, device as dv
 _lib.init(0)
