@@ -63,6 +63,10 @@ SIGNATURES = {
     "c12381_hash_to_zp_batch": (_i, [_p, _sz, _sz, _p]),
     "c12381_sha3_512_batch_dev": (_i, [_p, _sz, _sz, _p, _p]),
     "c12381_hash_to_zp_batch_dev": (_i, [_p, _sz, _sz, _p, _p]),
+    "c12381_hash_to_g1_batch": (_i, [_p, _sz, _sz, _p]),
+    "c12381_map_to_g1_batch": (_i, [_p, _sz, _p]),
+    "c12381_hash_to_g1_batch_dev": (_i, [_p, _sz, _sz, _p, _p]),
+    "c12381_map_to_g1_batch_dev": (_i, [_p, _sz, _p, _p]),
     "c12381_miller_batch": (_i, [_p, _p, _sz, _i, _p]),
     "c12381_final_exp_batch": (_i, [_p, _sz, _p]),
     "c12381_pairing_product_batch": (_i, [_p, _p, _sz, _i, _p]),

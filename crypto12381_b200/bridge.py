@@ -190,6 +190,24 @@ def hash_to_zp(messages: bytes, message_len: int) -> bytes:
     return out.raw[:32 * B]
 
 
+def hash_to_g1(messages: bytes, message_len: int) -> bytes:
+    """`hash(...) -> G1` per message: G1Point::from_hash (g1_point.hpp:219-234); 49 B compressed each."""
+    ensure_init()
+    B = _count(messages, message_len, "messages") if message_len else 0
+    out = _out(G1_COMPRESSED * B)
+    check(lib().c12381_hash_to_g1_batch(messages, message_len, B, out))
+    return out.raw[:G1_COMPRESSED * B]
+
+
+def map_to_g1(elements: bytes) -> bytes:
+    """map_to_point + multiply_cofactor (src/miracl_core_interface.cpp:154-162) of field elements, 48 B big-endian each."""
+    ensure_init()
+    B = _count(elements, 48, "elements")
+    out = _out(G1_COMPRESSED * B)
+    check(lib().c12381_map_to_g1_batch(elements, B, out))
+    return out.raw[:G1_COMPRESSED * B]
+
+
 # ---- pairings ------------------------------------------------------------------------------------------------------
 def _pairs(g1s: bytes, g2s: bytes, k: int) -> int:
     if not 1 <= k <= _lib.MAX_PAIRS:

@@ -142,6 +142,16 @@ C12381_API int c12381_sha3_512_batch(const uint8_t* msgs, size_t msg_len, size_t
 C12381_API int c12381_hash_to_zp_batch(const uint8_t* msgs, size_t msg_len, size_t B, uint8_t* out32);
 C12381_API int c12381_sha3_512_batch_dev(const uint8_t* d_msgs, size_t msg_len, size_t B, uint8_t* d_out64, void* stream);
 C12381_API int c12381_hash_to_zp_batch_dev(const uint8_t* d_msgs, size_t msg_len, size_t B, uint8_t* d_out32, void* stream);
+/* hash_to_g1: what `hash(...) -> G1` yields for each message - G1Point::from_hash (include/crypto12381/g1_point.hpp:219-234): the
+ * SHA3-512 digest reduced mod p (from_bytes(big2&) + fixed_time_mod, src/miracl_core_interface.cpp:91-99), map_to_point (:154-157 ->
+ * ECP_map2point, 3rd-party/miracl-core/ecp_BLS12381.cpp:1276,1493-1627: simplified SWU on the 11-isogenous curve, Z = 11, then the
+ * isogeny) and multiply_cofactor (:159-162 -> ECP_cfp, times 1 - x).  49 B compressed per message.  map_to_g1: the last two steps for
+ * B field elements given as 48 B big-endian integers < p (else C12381_EINPUT); the two inputs with Z^2 u^4 + Z u^2 = 0 give the
+ * identity, as in the reference. */
+C12381_API int c12381_hash_to_g1_batch(const uint8_t* msgs, size_t msg_len, size_t B, uint8_t* out49);
+C12381_API int c12381_map_to_g1_batch(const uint8_t* u48, size_t B, uint8_t* out49);
+C12381_API int c12381_hash_to_g1_batch_dev(const uint8_t* d_msgs, size_t msg_len, size_t B, uint8_t* d_out49, void* stream);
+C12381_API int c12381_map_to_g1_batch_dev(const uint8_t* d_u48, size_t B, uint8_t* d_out49, void* stream);
 
 /* ---- pairings --------------------------------------------------------------------------------------------- */
 /* B instances, k pairs each (1 <= k <= C12381_MAX_PAIRS): g1s = B*k*96 B, g2s = B*k*192 B, instance-major.

@@ -633,3 +633,76 @@ def gt_to_bytes(f):  # FP12_toOctet: c, b, a (MC/fp12_BLS12381.cpp:923-929)
 
 def gt_from_bytes(b):
     return (f4_from_bytes(b[384:576]), f4_from_bytes(b[192:384]), f4_from_bytes(b[:192]))
+
+
+# ---------------------------------------------------------------------------------------------
+# Hash to G1: G1Point::from_hash (include/crypto12381/g1_point.hpp:219-234)
+#   SHA3-512 digest -> big2 -> fixed_time_mod p -> ECP_map2point (MC/ecp_BLS12381.cpp:1276,1493-1627: simplified SWU on
+#   the isogenous curve E': y^2 = x^3 + A'x + B', Z = 11, then the 11-isogeny to E, projective) -> ECP_cfp (:1252-1273,
+#   times CURVE_Cof = 1 - x).  Value-level restatement: the reference's constant-time selections and its shared
+#   inversion/square-root exponentiation compute exactly the RFC 9380 map with sgn0 = parity (FP_sign).
+# ---------------------------------------------------------------------------------------------
+from .iso11_g1 import ISO_A, ISO_B, SSWU_Z, H_EFF, ISO_XNUM, ISO_XDEN, ISO_YNUM, ISO_YDEN  # noqa: E402
+
+
+def sswu_iso_curve(u):
+    """Point (x, y) on E' for the field element u (MC/ecp_BLS12381.cpp:1509-1566)."""
+    u %= P
+    zu2 = SSWU_Z * u * u % P
+    tv1 = (zu2 * zu2 + zu2) % P
+    if tv1 == 0:
+        # u = 0 or Z u^2 = -1: the reference has no exceptional branch; its shared denominator A'(Z^2u^4 + Zu^2) is zero,
+        # FP_inv(0) = 0 zeroes the projective Z and the result is the identity (checked against the compiled reference)
+        return None
+    x1 = (-ISO_B) * pow(ISO_A, -1, P) % P * (1 + pow(tv1, -1, P)) % P
+    gx1 = (x1 * x1 * x1 + ISO_A * x1 + ISO_B) % P
+    y = fp_sqrt(gx1)
+    x = x1
+    if y is None:
+        x = zu2 * x1 % P
+        y = fp_sqrt((x * x * x + ISO_A * x + ISO_B) % P)
+        assert y is not None
+    if fp_sign(y) != fp_sign(u):
+        y = (-y) % P
+    return (x, y)
+
+
+def _horner(coeffs, x, monic=False):
+    acc = 1 if monic else 0
+    for c in coeffs:
+        acc = (acc * x + c) % P
+    return acc
+
+
+def iso11_map(pt):
+    """The 11-isogeny E' -> E (MC/ecp_BLS12381.cpp:1568-1627), affine value; None if a denominator vanishes."""
+    if pt is None:
+        return None
+    x, y = pt
+    xn, xd = _horner(ISO_XNUM, x), _horner(ISO_XDEN, x, monic=True)
+    yn, yd = _horner(ISO_YNUM, x), _horner(ISO_YDEN, x, monic=True)
+    if xd == 0 or yd == 0:
+        return None
+    return (xn * pow(xd, -1, P) % P, y * yn % P * pow(yd, -1, P) % P)
+
+
+def g1_mul_raw(p, k):
+    """k*P without reducing k mod r (the point need not have order r)."""
+    acc = None
+    while k:
+        if k & 1:
+            acc = g1_add(acc, p)
+        p = g1_add(p, p)
+        k >>= 1
+    return acc
+
+
+def map_to_g1(u):
+    """map_to_point + multiply_cofactor (src/miracl_core_interface.cpp:154-162)."""
+    return g1_mul_raw(iso11_map(sswu_iso_curve(u)), H_EFF)
+
+
+def hash_to_g1(msg: bytes):
+    """G1Point::from_hash over the bytes a hash_state absorbed (g1_point.hpp:219-234)."""
+    import hashlib
+    return map_to_g1(int.from_bytes(hashlib.sha3_512(msg).digest(), "big") % P)

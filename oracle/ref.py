@@ -218,3 +218,17 @@ def g2_member(points: bytes) -> bytes:
     out = ctypes.create_string_buffer(max(n, 1))
     assert lib().ref_g2_member(points, _sz(n), out) == 1
     return out.raw[:n]
+
+
+def hash_to_g1(msgs: bytes, msg_len: int, n: int, threads: int = 1) -> bytes:
+    """G1Point::from_hash of the SHA3-512 digest of each message; n x 49 B compressed."""
+    out = ctypes.create_string_buffer(49 * n)
+    lib().ref_hash_to_g1(msgs, _sz(msg_len), _sz(n), out, _int(threads))
+    return out.raw
+
+
+def map_to_g1(u48: bytes, n: int) -> bytes:
+    """map_to_point + multiply_cofactor of n field elements (48 B big-endian, < p); n x 49 B compressed."""
+    out = ctypes.create_string_buffer(49 * n)
+    lib().ref_map_to_g1(u48, _sz(n), out)
+    return out.raw

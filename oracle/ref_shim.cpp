@@ -507,4 +507,47 @@ extern "C"
         }
         return 1;
     }
+
+    // G1Point::from_hash (g1_point.hpp:219-234) for the SHA3-512 digest of each message: digest -> big2 -> fixed_time_mod p ->
+    // residue -> map_to_point (ECP_map2point, SSWU + 11-isogeny) -> multiply_cofactor (ECP_cfp); compressed 49 B each.
+    void ref_hash_to_g1(const uint8_t* msgs, size_t len, size_t n, uint8_t* out49, int threads)
+    {
+        static const unsigned char P_BYTES[48] = {
+            0x1a, 0x01, 0x11, 0xea, 0x39, 0x7f, 0xe6, 0x9a, 0x4b, 0x1b, 0xa7, 0xb6, 0x43, 0x4b, 0xac, 0xd7,
+            0x64, 0x77, 0x4b, 0x84, 0xf3, 0x85, 0x12, 0xbf, 0x67, 0x30, 0xd2, 0xa0, 0xf6, 0xb0, 0xf6, 0x24,
+            0x1e, 0xab, 0xff, 0xfe, 0xb1, 0x53, 0xff, 0xff, 0xb9, 0xfe, 0xff, 0xff, 0xff, 0xff, 0xaa, 0xab};
+        parallel_for(n, threads, [&](size_t lo, size_t hi, int) {
+            mc::big p;
+            mc::from_bytes(p, (const char*)P_BYTES);
+            for (size_t i = lo; i < hi; ++i)
+            {
+                mc::sha3_state st;
+                mc::sha3_init(st, 64);
+                for (size_t j = 0; j < len; ++j) mc::sha3_process(st, msgs[i * len + j]);
+                char digest[64];
+                mc::sha3_hash(st, digest);
+                mc::big2 d; mc::big x; mc::fp u; mc::point1 P;
+                mc::from_bytes(d, digest, 64);
+                mc::fixed_time_mod(x, d, p, 64 * 8 - 381);
+                mc::residue(u, x);
+                mc::map_to_point(P, u);
+                mc::multiply_cofactor(P);
+                g1_to_c49(out49 + 49 * i, P);
+            }
+        });
+    }
+
+    // map_to_point + multiply_cofactor for field elements given as 48-byte big-endian integers < p
+    void ref_map_to_g1(const uint8_t* u48, size_t n, uint8_t* out49)
+    {
+        for (size_t i = 0; i < n; ++i)
+        {
+            mc::big x; mc::fp u; mc::point1 P;
+            mc::from_bytes(x, (const char*)(u48 + 48 * i));
+            mc::residue(u, x);
+            mc::map_to_point(P, u);
+            mc::multiply_cofactor(P);
+            g1_to_c49(out49 + 49 * i, P);
+        }
+    }
 }

@@ -35,5 +35,10 @@ def golden_pairing():
     return load_golden("pairing.json")
 
 
+@pytest.fixture(scope="session")
+def golden_hashing():
+    return load_golden("hashing.json")
+
+
 def chunks(b, size):
     return [b[i:i + size] for i in range(0, len(b), size)]

@@ -315,4 +315,7 @@ int hm_g2_member(const uint8_t* p192, uint32_t n, uint8_t* out)
 // SHA3-512 / hash-to-Zp bodies (k_sha3_512)
 void hm_sha3_512(const uint8_t* msg, uint32_t len, uint8_t* out64) { sha3_512(msg, len, out64); }
 void hm_hash_to_zp(const uint8_t* msg, uint32_t len, uint8_t* out32) { hash_to_zp_body(msg, len, out32); }
+// hash-to-G1 bodies (k_hash_to_g1)
+void hm_hash_to_g1(const uint8_t* msg, uint32_t len, uint8_t* out49) { hash_to_g1_body(msg, len, out49); }
+int hm_map_to_g1(const uint8_t* u48, uint8_t* out49) { return map_to_g1_body(u48, out49) ? 0 : 1; }
 }

@@ -147,6 +147,33 @@ def test_sha3_512_and_hash_to_zp_batch(gpu):
     assert bridge.sha3_512(b"", 0) == b""
 
 
+def test_hash_to_g1_batch(gpu, golden_hashing):
+    """`hash(...) -> G1` in batch (G1Point::from_hash, g1_point.hpp:219-234) against vectors from the compiled reference, the
+    reference itself on fresh messages, and - at a size the CPU cannot follow - subgroup membership of every output."""
+    bridge, _ = gpu
+    g = golden_hashing
+    H = bytes.fromhex
+    for m, want in zip(g["messages"], g["points"]):
+        assert bridge.hash_to_g1(H(m), len(H(m))) == H(want)
+    assert bridge.map_to_g1(H(g["elements"])) == H(g["mapped"])
+    with pytest.raises(Exception):
+        bridge.map_to_g1(o.P.to_bytes(48, "big"))      # u >= p is refused
+    rnd = random.Random(15)
+    L, B = 97, 300
+    msgs = bytes(rnd.randrange(256) for _ in range(L * B))
+    got = bridge.hash_to_g1(msgs, L)
+    if ref.available():
+        assert got == ref.hash_to_g1(msgs, L, B, ref.hardware_threads())
+    else:
+        from oracle import bls12381_oracle as o
+        assert got[:49 * 8] == b"".join(o.g1_compress(o.hash_to_g1(msgs[L * i:L * (i + 1)])) for i in range(8))
+    B = 1 << 14
+    msgs = bytes(rnd.randrange(256) for _ in range(32 * B))
+    pts = bridge.from_bytes(bridge.hash_to_g1(msgs, 32))
+    assert bridge.is_member(pts) == bytes([1] * B)
+    assert bridge.hash_to_g1(b"", 0) == b""
+
+
 def test_bbs_plus_aggregate_verification(gpu):
     """The random-linear-combination batch check agrees with the per-signature verdicts: accepts a valid batch, rejects one
     with a single tampered signature (whatever its position)."""

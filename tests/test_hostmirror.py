@@ -282,3 +282,21 @@ def test_sha3_512_and_hash_to_zp():
         want = hashlib.sha3_512(msg).digest()
         assert d.raw == want, n
         assert z.raw == (int.from_bytes(want, "big") % ps.R).to_bytes(32, "big"), n
+
+
+def test_hash_to_g1(golden_hashing):
+    """The bodies of k_hash_to_g1 (digest mod p, SSWU with one shared exponentiation, 11-isogeny, cofactor) against vectors from the
+    compiled reference (G1Point::from_hash, g1_point.hpp:219-234), the exceptional inputs included."""
+    H = bytes.fromhex
+    l = hm.lib()
+    g = golden_hashing
+    for m, want in zip(g["messages"], g["points"]):
+        msg, out = H(m), ctypes.create_string_buffer(49)
+        l.hm_hash_to_g1(msg, len(msg), out)
+        assert out.raw == H(want)
+    for u, want in zip(chunks(H(g["elements"]), 48), chunks(H(g["mapped"]), 49)):
+        out = ctypes.create_string_buffer(49)
+        assert l.hm_map_to_g1(u, out) == 0
+        assert out.raw == want
+    out = ctypes.create_string_buffer(49)
+    assert l.hm_map_to_g1(ps.P.to_bytes(48, "big"), out) == 1     # u >= p is refused

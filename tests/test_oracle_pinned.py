@@ -135,3 +135,26 @@ def test_against_compiled_reference_fresh_seeds():
     assert ref.pairing_product_batch(a1, a2, 2, 1) == b"".join(
         o.gt_to_bytes(o.pairing_product(list(zip(g1[2 * i:2 * i + 2], g2[2 * i:2 * i + 2])))) for i in range(3))
     assert ref.random_scalars("same seed", 3) == ref.random_scalars("same seed", 3)  # unit-tests/random.cpp:8-20
+
+
+def test_hash_to_g1_golden(golden_hashing):
+    """G1Point::from_hash restated (sswu_iso_curve / iso11_map / cofactor) against vectors from the compiled reference, including
+    the inputs without an SSWU image (u = 0, Z u^2 = -1), where the reference yields the identity."""
+    g = golden_hashing
+    for m, want in zip(g["messages"], g["points"]):
+        assert o.g1_compress(o.hash_to_g1(H(m))) == H(want)
+    us = [int.from_bytes(c, "big") for c in chunks(H(g["elements"]), 48)]
+    assert b"".join(o.g1_compress(o.map_to_g1(u)) for u in us) == H(g["mapped"])
+    assert H(g["mapped"])[:49 * 3] == bytes(49 * 3)
+    # structure: the SSWU point is on E', its image on E, the result in the r-torsion subgroup
+    q = o.sswu_iso_curve(us[7])
+    assert (q[1] * q[1] - q[0] ** 3 - o.ISO_A * q[0] - o.ISO_B) % o.P == 0
+    assert o.g1_on_curve(o.iso11_map(q)) and o.g1_mul_raw(o.map_to_g1(us[7]), o.R) is None
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
+def test_hash_to_g1_against_compiled_reference():
+    import random
+    rnd = random.Random(99)
+    msgs = bytes(rnd.randrange(256) for _ in range(8 * 50))
+    assert ref.hash_to_g1(msgs, 50, 8, 2) == b"".join(o.g1_compress(o.hash_to_g1(m)) for m in chunks(msgs, 50))

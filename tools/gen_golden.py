@@ -135,6 +135,24 @@ def main():
     pair["bilinear_lhs_gt"] = hx(ref.pairing_product_batch(gx, gy, 1, 1))
     with open(os.path.join(OUT, "pairing.json"), "w") as f:
         json.dump(pair, f, indent=1)
+    # --- hashing to G1 (G1Point::from_hash, g1_point.hpp:219-234) ---------------------------------------------------
+    import random
+    rnd = random.Random(381)
+    P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    hashing = {"messages": [], "points": []}
+    for n in (1, 3, 32, 71, 72, 73, 145, 300):
+        msg = bytes(rnd.randrange(256) for _ in range(n))
+        hashing["messages"].append(hx(msg))
+        hashing["points"].append(hx(ref.hash_to_g1(msg, n, 1)))
+    # field elements: 0 and +-sqrt(-1/11) (the inputs without an SSWU image: the reference yields the identity), small and random ones
+    s = pow((-pow(11, -1, P)) % P, (P + 1) // 4, P)
+    assert 11 * s * s % P == P - 1
+    us = [0, s, P - s, 1, 2, P - 1] + [rnd.randrange(P) for _ in range(10)]
+    u48 = b"".join(u.to_bytes(48, "big") for u in us)
+    hashing["elements"] = hx(u48)
+    hashing["mapped"] = hx(ref.map_to_g1(u48, len(us)))
+    with open(os.path.join(OUT, "hashing.json"), "w") as f:
+        json.dump(hashing, f, indent=1)
     print("golden vectors written to", OUT)
 
 
