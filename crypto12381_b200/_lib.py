@@ -79,6 +79,8 @@ SIGNATURES = {
     "c12381_gt_pow_batch": (_i, [_p, _p, _sz, _p]),
     "c12381_gt_mul_batch_dev": (_i, [_p, _p, _sz, _p, _p]),
     "c12381_gt_pow_batch_dev": (_i, [_p, _p, _sz, _p, _p]),
+    "c12381_gt_pow_gs_batch": (_i, [_p, _p, _sz, _p]),
+    "c12381_gt_pow_gs_batch_dev": (_i, [_p, _p, _sz, _p, _p]),
     "c12381_sum_of_products_miracl": (_i, [_p, _i, _p, _p]),
     "c12381_multiply_point1_miracl": (_i, [_p, _p]),
     "c12381_double_multiply_miracl": (_i, [_p, _p, _p, _p]),

@@ -285,6 +285,17 @@ def gt_pow(bases: bytes, exponents: bytes) -> bytes:
     return out.raw[:GT_BYTES * n]
 
 
+def gt_pow_gs(bases: bytes, exponents: bytes) -> bytes:
+    """PAIR_GTpow with the Galbraith-Scott split (pair_BLS12381.cpp:985-1026), batched; bases must lie in GT (order r)."""
+    ensure_init()
+    n = _count(bases, GT_BYTES, "bases")
+    if _count(exponents, SCALAR, "exponents") != n:
+        raise ValueError("gt_pow_gs: bases and exponents differ in length")
+    out = _out(GT_BYTES * n)
+    check(lib().c12381_gt_pow_gs_batch(bases, exponents, n, out))
+    return out.raw[:GT_BYTES * n]
+
+
 # ---- the reference's PODs, passed through unchanged (what the forwarding TU does) ------------------------------------
 def sum_of_products_pod(result_point1, n: int, points_point1, numbers_big) -> None:
     ensure_init()

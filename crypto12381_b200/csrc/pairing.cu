@@ -58,6 +58,15 @@ __global__ void __launch_bounds__(PAIR_THREADS) k_gt_pow(const uint8_t* __restri
     gt_pow_body(a + 576ull * b, s32 + 32ull * b, out + 576ull * b);
 }
 
+__global__ void __launch_bounds__(PAIR_THREADS) k_gt_pow_gs(const uint8_t* __restrict__ a, const uint8_t* __restrict__ s32, uint32_t B,
+                                                            uint8_t* __restrict__ out, int* flags)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    if (!scalar_is_canonical(scalar_from_be32(s32 + 32ull * b))) atomicOr(flags, FLAG_BAD_SCALAR);
+    gt_pow_gs_body(a + 576ull * b, s32 + 32ull * b, out + 576ull * b);
+}
+
 // ---- lane-cooperative kernels (pairing_coop.cuh): six lanes per instance, five instances per warp ---------------------
 #ifndef C12_PAIR_WARPS
 #define C12_PAIR_WARPS 4            // warps per block: 20 instances, 57,600 B of shared memory; three blocks per SM
@@ -317,10 +326,15 @@ static int gt_mul_run(const uint8_t* a, const uint8_t* b, size_t B, uint8_t* d_o
     C12_LAUNCHED();
     return C12381_OK;
 }
-static int gt_pow_run(const uint8_t* a, const uint8_t* sc, size_t B, uint8_t* d_out, cudaStream_t s)
+static int gt_pow_run(const uint8_t* a, const uint8_t* sc, size_t B, uint8_t* d_out, cudaStream_t s, bool gs = false)
 {
     if (B == 0) return C12381_OK;
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "gt_pow: too many instances");
+    if (gs) {
+        k_gt_pow_gs<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, sc, (uint32_t)B, d_out, ctx().d_flags);
+        C12_LAUNCHED();
+        return C12381_OK;
+    }
     if (use_scalar_kernels(B)) {
         k_gt_pow<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, sc, (uint32_t)B, d_out, ctx().d_flags);
         C12_LAUNCHED();
@@ -384,6 +398,20 @@ int c12381_gt_pow_batch(const uint8_t* a576, const uint8_t* scalars32, size_t B,
     const void* in[2] = {a576, scalars32};
     size_t sz[2] = {B * 576, B * 32};
     return with_staged(in, sz, 2, out576, B * 576, 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) { return gt_pow_run(d_in[0], d_in[1], B, d_out, s); });
+}
+int c12381_gt_pow_gs_batch(const uint8_t* a576, const uint8_t* scalars32, size_t B, uint8_t* out576)
+{
+    C12_REQUIRE_CTX();
+    if (B && (!a576 || !scalars32 || !out576)) return set_error(C12381_EARG, "gt_pow_gs: null pointer");
+    const void* in[2] = {a576, scalars32};
+    size_t sz[2] = {B * 576, B * 32};
+    return with_staged(in, sz, 2, out576, B * 576, 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) { return gt_pow_run(d_in[0], d_in[1], B, d_out, s, true); });
+}
+int c12381_gt_pow_gs_batch_dev(const uint8_t* a, const uint8_t* sc, size_t B, uint8_t* o, void* stream)
+{
+    C12_REQUIRE_CTX();
+    if (B && (!a || !sc || !o)) return set_error(C12381_EARG, "gt_pow_gs: null pointer");
+    return gt_pow_run(a, sc, B, o, pick_stream(stream), true);
 }
 int c12381_gt_pow_batch_dev(const uint8_t* a, const uint8_t* sc, size_t B, uint8_t* o, void* stream)
 {

@@ -177,6 +177,17 @@ def gt_pow_batch(a, scalars, out=None):
     return out
 
 
+def gt_pow_gs_batch(a, scalars, out=None):
+    """a[b]^scalars[b] for a in GT through the Galbraith-Scott split (c12381_gt_pow_gs_batch_dev)."""
+    ensure_init()
+    n = _chk(a, "a").numel() // GT_BYTES
+    _chk(scalars, "scalars")
+    if out is None:
+        out = _new(n * GT_BYTES, a)
+    check(lib().c12381_gt_pow_gs_batch_dev(a.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
+    return out
+
+
 def _multi_fixed(fn_name, point_bytes, bases, scalars, out=None):
     ensure_init()
     _chk(bases, "bases"), _chk(scalars, "scalars")

@@ -181,6 +181,12 @@ C12381_API int c12381_gt_mul_batch(const uint8_t* a576, const uint8_t* b576, siz
 C12381_API int c12381_gt_pow_batch(const uint8_t* a576, const uint8_t* scalars32, size_t B, uint8_t* out576);
 C12381_API int c12381_gt_mul_batch_dev(const uint8_t* d_a576, const uint8_t* d_b576, size_t B, uint8_t* d_out576, void* stream);
 C12381_API int c12381_gt_pow_batch_dev(const uint8_t* d_a576, const uint8_t* d_scalars32, size_t B, uint8_t* d_out576, void* stream);
+/* out[b] = a[b]^scalars[b] for a in GT (order r: pairing values and their products / powers) through the Galbraith-Scott
+ * split of the exponent - the value of the reference's unbridged PAIR_GTpow built with USE_GS_GT
+ * (3rd-party/miracl-core/pair_BLS12381.cpp:985-1026): four 63-bit exponents over a, a^p, a^(p^2), a^(p^3), 62 cyclotomic
+ * squarings instead of 254.  Equal to c12381_gt_pow_batch on GT; NOT valid for other unitary elements. */
+C12381_API int c12381_gt_pow_gs_batch(const uint8_t* a576, const uint8_t* scalars32, size_t B, uint8_t* out576);
+C12381_API int c12381_gt_pow_gs_batch_dev(const uint8_t* d_a576, const uint8_t* d_scalars32, size_t B, uint8_t* d_out576, void* stream);
 
 /* ---- drop-in entries on the reference's PODs (batch of 1 per call; host pointers) --------------------------- */
 /* void sum_of_products(point1& result, int n, point1* points, const big* numbers)  (miracl_core_interface.hpp:143) */

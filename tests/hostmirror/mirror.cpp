@@ -199,6 +199,11 @@ void hm_gt_pow(const uint8_t* a, const uint8_t* s32, uint32_t B, uint8_t* out576
     for (uint32_t i = 0; i < B; ++i) gt_pow_body(a + 576 * (size_t)i, s32 + 32 * (size_t)i, out576 + 576 * (size_t)i);
 }
 
+void hm_gt_pow_gs(const uint8_t* a, const uint8_t* s32, uint32_t B, uint8_t* out576)
+{
+    for (uint32_t i = 0; i < B; ++i) gt_pow_gs_body(a + 576 * (size_t)i, s32 + 32 * (size_t)i, out576 + 576 * (size_t)i);
+}
+
 // reference PODs <-> wire formats (bodies of the k_pod_* kernels)
 int hm_pod_points_to_wire(int g2, const uint8_t* pods, uint32_t n, uint8_t* wire)
 {

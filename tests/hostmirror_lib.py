@@ -101,6 +101,13 @@ def gt_mul(a, b):
     return out.raw
 
 
+def gt_pow_gs(a, s):
+    B = len(a) // 576
+    out = ctypes.create_string_buffer(576 * B)
+    lib().hm_gt_pow_gs(a, s, B, out)
+    return out.raw
+
+
 def gt_pow(a, s):
     B = len(a) // 576
     out = ctypes.create_string_buffer(576 * B)

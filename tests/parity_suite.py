@@ -5,6 +5,7 @@ from conftest import chunks, load_golden
 
 H = bytes.fromhex
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+X_ABS = 0xD201000000010000
 P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
 ONE_GT = bytes(575) + b"\x01"
 
@@ -76,6 +77,11 @@ def check_pairing(be):
     assert be.product(H(g["mixed_g1"]), H(g["mixed_g2"]), 4) == H(g["mixed_quad_gt"])
     gts = H(g["single_gt"])
     assert be.gt_pow(gts, H(g["gt_pow_scalars"])) == H(g["gt_pow"])
+    # PAIR_GTpow through the Galbraith-Scott split: same values on GT, edge exponents included
+    assert be.gt_pow_gs(gts, H(g["gt_pow_scalars"])) == H(g["gt_pow"])
+    edge = [0, 1, 2, R - 1, X_ABS, X_ABS ** 2 % R, X_ABS ** 3 % R, (X_ABS // 2 + 1) * (1 + X_ABS + X_ABS ** 2 + X_ABS ** 3) % R]
+    es = b"".join(be32(e) for e in edge)
+    assert be.gt_pow_gs(gts, es) == be.gt_pow(gts, es)
     assert be.gt_mul(gts[:576 * 4], gts[576 * 4:]) == H(g["gt_mul"])
     # pair*pair == product of two independent pairings (unit-tests/liner_pair.cpp:66-79)
     assert be.gt_mul(gts[:576], gts[576:1152]) == H(g["double_gt"])[:576]
@@ -84,3 +90,4 @@ def check_pairing(be):
     x, y = int.from_bytes(xy[:32], "big"), int.from_bytes(xy[32:], "big")
     lhs = be.product(be.fixed_base1(xy[:32]), be.fixed_base2(xy[32:]), 1)
     assert lhs == H(g["bilinear_lhs_gt"]) == be.gt_pow(H(g["generator_gt"]), be32(x * y % R))
+    assert lhs == be.gt_pow_gs(H(g["generator_gt"]), be32(x * y % R))

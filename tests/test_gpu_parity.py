@@ -34,6 +34,7 @@ def cuda():
         final_exp = staticmethod(bridge.pair_final_exponentiation)
         gt_mul = staticmethod(bridge.gt_multiply)
         gt_pow = staticmethod(bridge.gt_pow)
+        gt_pow_gs = staticmethod(bridge.gt_pow_gs)
         miller = staticmethod(bridge.miller_batch)
         product = staticmethod(bridge.pairing_product_batch)
 
@@ -159,7 +160,7 @@ def test_pairing_products_vs_reference(cuda, k, pairing_kernel):
     assert gt == ref.pairing_product_batch(g1, g2, k, 1, t)
     assert cuda.final_exp(cuda.miller(g1, g2, k)) == gt
     e = ref.random_scalars("gt-exp", B)
-    assert cuda.gt_pow(gt, e) == ref.gt_pow_batch(gt, e, t)
+    assert cuda.gt_pow(gt, e) == ref.gt_pow_batch(gt, e, t) == cuda.gt_pow_gs(gt, e)
     assert cuda.gt_mul(gt, gt[576:] + gt[:576]) == ref.gt_mul_batch(gt, gt[576:] + gt[:576])
 
 

@@ -26,6 +26,7 @@ class MirrorBackend:
     final_exp = staticmethod(hm.final_exp)
     gt_mul = staticmethod(hm.gt_mul)
     gt_pow = staticmethod(hm.gt_pow)
+    gt_pow_gs = staticmethod(hm.gt_pow_gs)
 
     @staticmethod
     def msm1(points, scalars, c=0):
