@@ -37,6 +37,13 @@ struct Fp2 {
 #if defined(__CUDA_ARCH__)
 #include "fp_ptx.inc"
 #endif
+// -DC12_FP_SQR_DEDICATED: squarings through the dedicated routine (66 doubled cross products + 12 diagonal ones + a separate
+// reduction: 234 multiply-adds) instead of the interleaved product with both operands equal (300); A/B knob, profiles/.
+#if defined(C12_FP_SQR_DEDICATED)
+#define C12_FP_SQR_PTX fp_sqr_dedicated_ptx
+#else
+#define C12_FP_SQR_PTX fp_sqr_ptx
+#endif
 
 #define C12_P_LIMBS                                                                                               \
     {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u,      \
@@ -58,8 +65,18 @@ inline void cond_sub_p(uint32_t (&r)[12], const uint32_t (&t)[13])
     bool ge = ((int64_t)t[12] + borrow) >= 0;
     for (int i = 0; i < 12; ++i) r[i] = ge ? s[i] : t[i];
 }
+#if defined(C12_COUNT_FP_MUL)
+inline unsigned long long& mont_mul_counter()   // host mirror only: Montgomery products executed (the algorithmic work unit of DESIGN.md)
+{
+    static unsigned long long n = 0;
+    return n;
+}
+#endif
 inline void mont_mul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12])
 {
+#if defined(C12_COUNT_FP_MUL)
+    ++mont_mul_counter();
+#endif
     uint32_t t[14] = {0};
     for (int i = 0; i < 12; ++i) {
         uint64_t c = 0;
@@ -107,7 +124,7 @@ __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b)
 __device__ __noinline__ Fp fp_sqr_call(Fp a)
 {
     Fp r;
-    fp_sqr_ptx(r.v, a.v);
+    C12_FP_SQR_PTX(r.v, a.v);
     return r;
 }
 #endif
@@ -127,7 +144,7 @@ C12_HD Fp fp_sqr_inl(const Fp& a)
 {
     Fp r;
 #if defined(__CUDA_ARCH__)
-    fp_sqr_ptx(r.v, a.v);
+    C12_FP_SQR_PTX(r.v, a.v);
 #else
     host::mont_mul(r.v, a.v, a.v);
 #endif

@@ -4,13 +4,32 @@
 // multiply(fp12&) / pow(fp12&) (reference: src/miracl_core_interface.cpp:251-289).
 #include <stdlib.h>
 
+// Measured defaults of this translation unit (profiles/r01ah_pairing_lockstep_ab.txt; -DC12_PAIR_NO_LOCKSTEP restores the old build):
+//  * block-wide barriers keep the warps of a block at the same place of the straight-line code (pairing.cuh, C12_BLOCK_ALIGN):
+//    ncu had shown instruction-fetch stalls growing with every extra resident warp (sm__icc hit rate 93 % -> 74 % from 8 to 12
+//    warps per SM);
+//  * with the instruction cache shared that way, the three Montgomery products of an Fp2 product can be inlined so that their
+//    carry chains interleave (slower without the barriers: three times the code).
+// Together +25 % on the thread-per-instance kernels (2.06 -> 2.57 M pairings/s at full waves), +4 % on the cooperative ones.
+#if !defined(C12_PAIR_NO_LOCKSTEP)
+#if !defined(C12_PAIR_LOCKSTEP)
+#define C12_PAIR_LOCKSTEP 1
+#endif
+#if !defined(C12_FP2_INLINE_MULS)
+#define C12_FP2_INLINE_MULS 1
+#endif
+#endif
+
 #include "msm_impl.cuh"
 #include "pairing.cuh"
 #include "pairing_coop.cuh"
 
 namespace c12 {
 
-constexpr int PAIR_THREADS = 64;
+#ifndef C12_PAIR_THREADS
+#define C12_PAIR_THREADS 128      // two blocks per SM at 255 registers
+#endif
+constexpr int PAIR_THREADS = C12_PAIR_THREADS;
 #ifndef C12_PAIR_MIN_BLOCKS
 #define C12_PAIR_MIN_BLOCKS 1      // blocks per SM the register allocation is bounded for (A/B knob, profiles/)
 #endif
@@ -20,6 +39,22 @@ __global__ void __launch_bounds__(PAIR_THREADS, C12_PAIR_MIN_BLOCKS) k_pairing(c
                                                           uint32_t k, int mode, uint8_t* __restrict__ out, int* flags)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+#if defined(C12_PAIR_LOCKSTEP)
+    // every thread of the block goes through the bodies (they hold block-wide barriers): the tail threads redo the last instance
+    const bool tail = b >= B;
+    if (tail) b = B - 1;
+    uint8_t buf[576];
+    bool ok = pairing_product_body(g1 + 96ull * b * k, g2 + 192ull * b * k, k, mode == 2 ? 1 : mode, buf);
+    if (tail) return;
+    if (!ok) atomicOr(flags, FLAG_BAD_POINT);
+    if (mode == 2) {
+        uint32_t acc = buf[575] ^ 1u;
+        for (int i = 0; i < 575; ++i) acc |= buf[i];
+        out[b] = acc == 0 ? 1 : 0;
+    } else {
+        for (int i = 0; i < 576; ++i) out[576ull * b + i] = buf[i];
+    }
+#else
     if (b >= B) return;
     if (mode == 2) {
         uint8_t buf[576];
@@ -32,13 +67,23 @@ __global__ void __launch_bounds__(PAIR_THREADS, C12_PAIR_MIN_BLOCKS) k_pairing(c
         return;
     }
     if (!pairing_product_body(g1 + 96ull * b * k, g2 + 192ull * b * k, k, mode, out + 576ull * b)) atomicOr(flags, FLAG_BAD_POINT);
+#endif
 }
 
 __global__ void __launch_bounds__(PAIR_THREADS) k_final_exp(const uint8_t* __restrict__ in, uint32_t B, uint8_t* __restrict__ out)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+#if defined(C12_PAIR_LOCKSTEP)
+    const bool tail = b >= B;
+    if (tail) b = B - 1;
+    uint8_t buf[576];
+    final_exp_body(in + 576ull * b, buf);
+    if (tail) return;
+    for (int i = 0; i < 576; ++i) out[576ull * b + i] = buf[i];
+#else
     if (b >= B) return;
     final_exp_body(in + 576ull * b, out + 576ull * b);
+#endif
 }
 
 __global__ void __launch_bounds__(PAIR_THREADS) k_gt_mul(const uint8_t* __restrict__ a, const uint8_t* __restrict__ bb, uint32_t B,
@@ -210,16 +255,16 @@ __global__ void __launch_bounds__(PC_THREADS, C12_PAIR_BLOCKS) k_gt_pow_coop(con
 // Two implementations of every entry: thread-per-instance (pairing.cuh bodies) and six-lanes-per-instance
 // (pairing_coop.cuh).  Measured (profiles/r01ac, r01t): the cooperative kernels run at ~1.8 M pairings/s from 2^14 four-pair
 // instances up and have six times the parallelism per instance (a single product: 9 ms against 47 ms); the
-// thread-per-instance kernel is latency-bound per thread, ~70 ms per wave of SMs x 256 threads however full the wave is,
-// i.e. 2.18 M/s x the fill of its last wave.  So: thread-per-instance when the batch fills its waves to >= 84 %, the
-// cooperative kernels otherwise.  C12381_PAIRING=scalar|coop or c12381_set_pairing_kernel force one of them.
+// thread-per-instance kernel is latency-bound per thread, ~59 ms per wave of SMs x 256 threads however full the wave is,
+// i.e. 2.57 M/s x the fill of its last wave (profiles/r01ah).  So: thread-per-instance when the batch fills its waves to
+// >= 76 %, the cooperative kernels otherwise.  C12381_PAIRING=scalar|coop or c12381_set_pairing_kernel force one of them.
 static bool scalar_fills_its_waves(size_t B)
 {
     static int sms = 0;
     if (!sms && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx().device) != cudaSuccess) sms = 148;
     const size_t wave = (size_t)sms * 256;
     const size_t waves = (B + wave - 1) / wave;
-    return B >= 16384 && (double)B >= 0.84 * (double)(waves * wave);
+    return B >= 16384 && (double)B >= 0.76 * (double)(waves * wave);
 }
 
 static int g_pairing_kernel = -1;   // 0 automatic, 1 thread-per-instance, 2 cooperative (c12381_set_pairing_kernel)

@@ -14,6 +14,17 @@
 #pragma once
 #include "scalar_mul.cuh"
 
+// -DC12_PAIR_LOCKSTEP (device, thread-per-instance kernels): a block-wide barrier at the top of every Miller-loop iteration and
+// of every exponentiation step.  Every thread runs the same instruction stream (the loop bits are public constants), so the
+// barrier only keeps the warps of a block at the same place in the ~100 KB of straight-line code, where they share
+// instruction-cache lines instead of evicting each other's (ncu: no_instruction stalls, sm__icc hit rate; profiles/).
+// Kernels built with it must bring EVERY thread of a block through the bodies (no early return).
+#if defined(C12_PAIR_LOCKSTEP) && defined(__CUDA_ARCH__)
+#define C12_BLOCK_ALIGN() __syncthreads()
+#else
+#define C12_BLOCK_ALIGN() ((void)0)
+#endif
+
 namespace c12 {
 
 struct Fp4 {
@@ -141,6 +152,7 @@ C12_HD_NOINLINE Fp12 pow_x_abs(const Fp12& x)
     Fp12 r = x;
 #pragma unroll 1
     for (int i = 62; i >= 0; --i) {
+        C12_BLOCK_ALIGN();
         r = usqr(r);
         if ((e >> i) & 1ull) r = mul(r, x);
     }
@@ -284,9 +296,11 @@ C12_HD_NOINLINE Fp12 miller_loop(const Affine<Fp>* P, const Affine<Fp2>* Q, uint
     const uint64_t pos = 0x1201000000010000ull, negm = 0x4000000000000000ull;
 #pragma unroll 1
     for (int i = 64; i >= 1; --i) {
+        C12_BLOCK_ALIGN();
         r = sqr(r);
 #pragma unroll 1
         for (uint32_t j = 0; j < k; ++j) {
+            C12_BLOCK_ALIGN();      // k is uniform over the block; the live test below is not
             if (!live[j]) continue;
             LineCoeffs l = pair_double(A[j]);
             r = mul_line(r, mul_fp(l.aa, P[j].y), l.bb, mul_fp(l.cc, P[j].x));
@@ -295,6 +309,7 @@ C12_HD_NOINLINE Fp12 miller_loop(const Affine<Fp>* P, const Affine<Fp2>* Q, uint
         if (bt != 0) {
 #pragma unroll 1
             for (uint32_t j = 0; j < k; ++j) {
+                C12_BLOCK_ALIGN();
                 if (!live[j]) continue;
                 Proj<Fp2> T = B[j];
                 if (bt < 0) T.y = neg(T.y);

@@ -265,6 +265,7 @@ __device__ void pow_x(Lane L, Fp2* acc, const Fp2* base)
     copy12(L, acc, base);
 #pragma unroll 1
     for (int i = 62; i >= 0; --i) {
+        C12_BLOCK_ALIGN();
         cyclo_sqr(L, acc);
         if ((e >> i) & 1ull) full_mul(L, acc, acc, base);
     }
@@ -391,6 +392,7 @@ __device__ void miller_coop(Lane L, const PairIn* pin, int kk)
     const uint64_t pos = 0x1201000000010000ull, negm = 0x4000000000000000ull;
 #pragma unroll 1
     for (int i = 64; i >= 1; --i) {
+        C12_BLOCK_ALIGN();
         if (i != 64) full_sqr(L, s->f, s->f);     // f = 1 before the first step
         if (mine) point_double_line(s->t + 3 * j, s->x + 3 * j, px, py, L.on);
         __syncwarp();

@@ -324,3 +324,13 @@ void hm_hash_to_zp(const uint8_t* msg, uint32_t len, uint8_t* out32) { hash_to_z
 void hm_hash_to_g1(const uint8_t* msg, uint32_t len, uint8_t* out49) { hash_to_g1_body(msg, len, out49); }
 int hm_map_to_g1(const uint8_t* u48, uint8_t* out49) { return map_to_g1_body(u48, out49) ? 0 : 1; }
 }
+
+#if defined(C12_COUNT_FP_MUL)
+// tools/count_fp_mul.py: Montgomery products executed by the kernel bodies (host build with -DC12_COUNT_FP_MUL)
+extern "C" unsigned long long hm_fp_mul_count(int reset)
+{
+    unsigned long long n = c12::host::mont_mul_counter();
+    if (reset) c12::host::mont_mul_counter() = 0;
+    return n;
+}
+#endif
