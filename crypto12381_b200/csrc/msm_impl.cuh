@@ -179,14 +179,60 @@ __global__ void __launch_bounds__(128) k_accumulate_reduced(uint32_t total, cons
 // Accumulation over CHUNKS of the bucket lists (virtual buckets): thread t takes chunk order[t] - chunks are visited in
 // order of decreasing length (launch_chunk_order), so the 32 lanes of a warp run loops of equal length and the heaviest
 // start first - and leaves a partial sum; k_fold adds up the partials of each bucket.
+// Block shape (measured, profiles/r01aj_acc_lockstep_ab.txt): 128 threads x 3 resident blocks over Fp, 64 threads x 6 over Fp2.
+// The warps of a block walk the loop TOGETHER (one barrier per addition, -DC12_ACC_NO_LOCKSTEP removes it): the straight-line
+// mixed addition is ~60 KB of code, and warps that drift apart each stream it through the instruction cache on their own (ncu:
+// no_instruction stalls 1.0 per issued instruction before, profiles/r01z_k_accumulate_full.md).  Same additions, same order.
+#if !defined(C12_ACC_NO_LOCKSTEP) && !defined(C12_ACC_LOCKSTEP)
+#define C12_ACC_LOCKSTEP 1
+#endif
+template <class F> struct AccShape {
+#if defined(C12_ACC_THREADS)
+    static constexpr int THREADS = C12_ACC_THREADS, MIN_BLOCKS = 1;
+#else
+    static constexpr int THREADS = sizeof(F) == sizeof(Fp) ? 128 : 64, MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? 3 : 6;
+#endif
+};
 template <class F>
-__global__ void __launch_bounds__(128) k_accumulate(uint32_t vmax, uint32_t chunk, const uint32_t* __restrict__ start,
+__global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MIN_BLOCKS) k_accumulate(uint32_t vmax, uint32_t chunk, const uint32_t* __restrict__ start,
                                                     const uint32_t* __restrict__ end, const uint32_t* __restrict__ vals,
                                                     const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ order,
                                                     const uint32_t* __restrict__ vbucket, const uint32_t* __restrict__ vstart,
                                                     Proj<F>* __restrict__ vpartial)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#if defined(C12_ACC_LOCKSTEP)
+    // every thread of the block stays in the loop up to the block's longest chunk (chunks are length-ordered: nearly equal)
+    const uint32_t v = t < vmax ? order[t] : 0xffffffffu;
+    uint32_t lo = 0, hi = 0;
+    if (v != 0xffffffffu) {
+        const uint32_t b = vbucket[v];
+        lo = start[b] + (v - vstart[b]) * chunk;
+        hi = lo + chunk;
+        if (hi > end[b]) hi = end[b];
+    }
+    __shared__ uint32_t s_len;
+    if (threadIdx.x == 0) s_len = 0;
+    __syncthreads();
+    atomicMax(&s_len, hi - lo);
+    __syncthreads();
+    const uint32_t len = s_len;
+    XYZZ<F> acc = xyzz_inf<F>();
+#pragma unroll 1
+    for (uint32_t i = 0; i < len; ++i) {
+        __syncthreads();
+        const uint32_t j = lo + i;
+        if (j < hi) {
+            uint32_t w = vals[j];
+            Affine<F> pt = pts[w & 0x7fffffffu];
+            if (!affine_is_inf(pt)) {
+                if (w >> 31) pt.y = neg(pt.y);
+                xyzz_madd(acc, pt);
+            }
+        }
+    }
+    if (v != 0xffffffffu) vpartial[v] = xyzz_to_proj(acc);
+#else
     if (t >= vmax) return;
     const uint32_t v = order[t];
     if (v == 0xffffffffu) return;                   // padding behind the last chunk
@@ -195,6 +241,7 @@ __global__ void __launch_bounds__(128) k_accumulate(uint32_t vmax, uint32_t chun
     uint32_t hi = lo + chunk;
     if (hi > end[b]) hi = end[b];
     vpartial[v] = msm_accumulate_range_body<F>(lo, hi, vals, pts);
+#endif
 }
 
 template <class F>
@@ -644,7 +691,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         k_accumulate_reduced<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, ba_rounds, o0, A0, A1, buckets);
         C12_LAUNCHED();
     } else {
-        k_accumulate<F><<<cdiv(pl.vmax, 128), 128, 0, s>>>(pl.vmax, pl.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
+        k_accumulate<F><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
         C12_LAUNCHED();
         k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, vstart, vpartial, buckets);
         C12_LAUNCHED();
