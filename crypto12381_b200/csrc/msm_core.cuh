@@ -108,8 +108,11 @@ inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, uint32_t parts = 1)
     pl.half = 1u << (c - 1);
     pl.total = pl.windows * pl.half;
     // level-0 segment length: a power of two in [4, 64] that keeps the level-0 grid within one wave (~48 Ki threads)
+#ifndef C12_MSM_SEG_WAVE
+#define C12_MSM_SEG_WAVE 49152u
+#endif
     uint32_t seg = 4;
-    while (seg < 64 && pl.total / seg > 49152u) seg <<= 1;
+    while (seg < 64 && pl.total / seg > C12_MSM_SEG_WAVE) seg <<= 1;
     if (seg > pl.half) seg = pl.half;
     msm_plan_levels(pl, seg);
     const uint64_t N = (uint64_t)pl.n * pl.windows;

@@ -259,8 +259,8 @@ template <class F>
 __global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? 3 : 1) k_reduce_level0(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ scratch)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= pl.segs) return;
     uint32_t w = blockIdx.y;
+    if (t >= pl.segs) return;
     uint32_t lo = t * pl.seg_len, hi = lo + pl.seg_len;
     if (hi > pl.half) hi = pl.half;
     Proj<F> sum, run;
