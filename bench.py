@@ -308,6 +308,9 @@ def run_ours(args):
                    "instances": B * world, "pairs_per_instance": k, "ms": ms,
                    "fp_mul_per_instance_ref_count": 31600, "gmacs": B * 31600 * MAC_PER_FP_MUL / (ms * 1e-3) / 1e9}
             sec["frac_of_int32_mad_peak"] = sec["gmacs"] / line["roofline"]["peak"]
+            if k == 4:      # the kernel bodies' own count (tools/count_fp_mul.py, host build with -DC12_COUNT_FP_MUL)
+                sec["fp_mul_per_instance_kernel_count"] = 30751
+                sec["frac_of_int32_mad_peak_kernel_count"] = sec["frac_of_int32_mad_peak"] * 30751 / 31600
             try:
                 from oracle import ref
                 if ref.available():

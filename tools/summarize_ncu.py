@@ -19,7 +19,7 @@ KEEP = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__occup
         "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "local_load", "local_store", "l1tex__t_bytes_pipe_lsu_mem_local", "smsp__inst_executed_op_local"]
+        "sm__icc_request_hit_rate", "local_load", "local_store", "l1tex__t_bytes_pipe_lsu_mem_local", "smsp__inst_executed_op_local"]
 
 
 def launches(src, dst):
