@@ -82,17 +82,37 @@ __device__ __forceinline__ Fp2 fp2_sqr_body(const Fp2& x)
     return r;
 }
 #else
+// The Karatsuba operands a + b (and a - b + p in the squaring) are NOT reduced on the device: the Montgomery product takes
+// operands below 2p (4p^2 / R + p < 2p since p < R / 8; emulated in tools/gen_fp_ptx.py) and reduces its result fully, so the
+// values are the same and 26 instructions per sum are saved.  -DC12_FP2_REDUCED_SUMS restores the reduced sums (A/B).
+#if defined(__CUDA_ARCH__) && !defined(C12_FP2_REDUCED_SUMS)
+__device__ __forceinline__ Fp fp_add_wide(const Fp& a, const Fp& b)
+{
+    Fp r;
+    fp_add_noreduce_ptx(r.v, a.v, b.v);
+    return r;
+}
+__device__ __forceinline__ Fp fp_sub_wide(const Fp& a, const Fp& b)   // a - b + p, in [1, 2p)
+{
+    Fp r;
+    fp_sub_addp_ptx(r.v, a.v, b.v);
+    return r;
+}
+#else
+C12_HD Fp fp_add_wide(const Fp& a, const Fp& b) { return fp_add(a, b); }
+C12_HD Fp fp_sub_wide(const Fp& a, const Fp& b) { return fp_sub(a, b); }
+#endif
 C12_HD Fp2 fp2_mul_body(const Fp2& x, const Fp2& y)
 {
     Fp t0 = C12_FP2_MUL(x.a, y.a);
     Fp t1 = C12_FP2_MUL(x.b, y.b);
-    Fp t2 = C12_FP2_MUL(fp_add(x.a, x.b), fp_add(y.a, y.b));
+    Fp t2 = C12_FP2_MUL(fp_add_wide(x.a, x.b), fp_add_wide(y.a, y.b));
     return Fp2{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
 }
 // (a+b)(a-b) + 2ab i : 2 Fp products
 C12_HD Fp2 fp2_sqr_body(const Fp2& x)
 {
-    Fp t0 = C12_FP2_MUL(fp_add(x.a, x.b), fp_sub(x.a, x.b));
+    Fp t0 = C12_FP2_MUL(fp_add_wide(x.a, x.b), fp_sub_wide(x.a, x.b));
     Fp t1 = C12_FP2_MUL(x.a, x.b);
     return Fp2{t0, fp_dbl(t1)};
 }

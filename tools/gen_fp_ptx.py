@@ -609,6 +609,14 @@ def check():
     for x in (RMONT - 1, RMONT - 2, P, P + 1, 2 * P - 1):
         for y in (0, 1, P - 1, rnd.randrange(P)):
             assert run2(mul, y, x) == x * y * rinv % P
+    # BOTH operands below 2p (unreduced sums of two field elements: the Karatsuba operands of fp2.cuh): 4p^2/R + p < 2p
+    wide = [2 * P - 1, 2 * P - 2, P, P + 1] + [rnd.randrange(2 * P) for _ in range(200)]
+    for x in wide[:8]:
+        for y in wide[:8]:
+            assert run2(mul, x, y) == x * y * rinv % P
+    for _ in range(1000):
+        x, y = rnd.choice(wide), rnd.choice(wide)
+        assert run2(mul, x, y) == x * y * rinv % P
     counts = {}
     for op, _ in mul.ins:
         counts[op.split(".")[0]] = counts.get(op.split(".")[0], 0) + 1
