@@ -66,6 +66,11 @@ inline void cond_sub_p(uint32_t (&r)[12], const uint32_t (&t)[13])
     for (int i = 0; i < 12; ++i) r[i] = ge ? s[i] : t[i];
 }
 #if defined(C12_COUNT_FP_MUL)
+inline unsigned long long& addsub_counter()     // host mirror only: field additions / subtractions / negations executed
+{
+    static unsigned long long n = 0;
+    return n;
+}
 inline unsigned long long& mont_mul_counter()   // host mirror only: Montgomery products executed (the algorithmic work unit of DESIGN.md)
 {
     static unsigned long long n = 0;
@@ -172,6 +177,9 @@ C12_HD Fp fp_sqr(const Fp& a)
 C12_HD Fp fp_add(const Fp& a, const Fp& b)
 {
     Fp r;
+#if defined(C12_COUNT_FP_MUL) && !defined(__CUDA_ARCH__)
+    ++host::addsub_counter();
+#endif
 #if defined(__CUDA_ARCH__)
     fp_add_ptx(r.v, a.v, b.v);
 #else
@@ -191,6 +199,9 @@ C12_HD Fp fp_add(const Fp& a, const Fp& b)
 C12_HD Fp fp_sub(const Fp& a, const Fp& b)
 {
     Fp r;
+#if defined(C12_COUNT_FP_MUL) && !defined(__CUDA_ARCH__)
+    ++host::addsub_counter();
+#endif
 #if defined(__CUDA_ARCH__)
     fp_sub_ptx(r.v, a.v, b.v);
 #else
@@ -215,6 +226,9 @@ C12_HD Fp fp_sub(const Fp& a, const Fp& b)
 C12_HD Fp fp_neg(const Fp& a)
 {
     Fp r;
+#if defined(C12_COUNT_FP_MUL) && !defined(__CUDA_ARCH__)
+    ++host::addsub_counter();
+#endif
 #if defined(__CUDA_ARCH__)
     fp_neg_ptx(r.v, a.v);
 #else

@@ -327,6 +327,12 @@ int hm_map_to_g1(const uint8_t* u48, uint8_t* out49) { return map_to_g1_body(u48
 
 #if defined(C12_COUNT_FP_MUL)
 // tools/count_fp_mul.py: Montgomery products executed by the kernel bodies (host build with -DC12_COUNT_FP_MUL)
+extern "C" unsigned long long hm_fp_addsub_count(int reset)
+{
+    unsigned long long n = c12::host::addsub_counter();
+    if (reset) c12::host::addsub_counter() = 0;
+    return n;
+}
 extern "C" unsigned long long hm_fp_mul_count(int reset)
 {
     unsigned long long n = c12::host::mont_mul_counter();

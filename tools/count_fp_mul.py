@@ -11,6 +11,7 @@ LIB = "/tmp/libhostmirror_count.so"
 subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DC12_COUNT_FP_MUL", "-o", LIB, SRC])
 l = ctypes.CDLL(LIB)
 l.hm_fp_mul_count.restype = ctypes.c_ulonglong
+l.hm_fp_addsub_count.restype = ctypes.c_ulonglong
 g = json.load(open(os.path.join(ROOT, "tests", "golden", "pairing.json")))
 g1, g2 = bytes.fromhex(g["g1"]), bytes.fromhex(g["g2"])
 out = ctypes.create_string_buffer(576 * 8)
@@ -19,7 +20,9 @@ for k in (1, 2, 4):
     B = 8 // k
     for mode, name in ((0, "miller"), (1, "product")):
         l.hm_fp_mul_count(1)
+        l.hm_fp_addsub_count(1)
         assert l.hm_pairing_product(g1, g2, B, k, mode, out) == 0
         res[f"{name}_k{k}"] = l.hm_fp_mul_count(1) / B
+        res[f"{name}_k{k}_addsub"] = l.hm_fp_addsub_count(1) / B
 res["final_exp"] = res["product_k1"] - res["miller_k1"]
 print(json.dumps(res, indent=1))
