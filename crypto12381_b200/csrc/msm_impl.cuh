@@ -467,22 +467,27 @@ __global__ void __launch_bounds__(128) k_scalar_mul(const uint8_t* __restrict__ 
 // device; a scalar is recoded into 32 signed 8-bit digits and g^x is 32 mixed additions - no doublings.
 constexpr uint32_t FB_WINDOWS = 32, FB_HALF = 128;
 
-// Table construction in two steps.  k_fixed_base_windows: thread (j, w) -> W[j][w] = 2^(8w) base_j (8w doublings: the
-// only long dependent chain, 384 threads for 12 bases).  k_fixed_base_table: thread (j, w, d) -> d W[j][w] by
+// Table construction in two steps.  k_fixed_base_windows: warp j -> W[j][w] = 2^(8w) base_j for w = 0..31 (the only long
+// dependent chain: 248 lane-cooperative doublings).  k_fixed_base_table: thread (j, w, d) -> d W[j][w] by
 // double-and-add over the 8 bits of d (at most 7 + 7 point operations), normalised to affine.
 // bases = nullptr: the default generator (one table); else m wire-format affine bases, table j at [j * 4096].
 template <class F>
-__global__ void __launch_bounds__(64) k_fixed_base_windows(const uint8_t* __restrict__ bases, uint32_t m, Proj<F>* __restrict__ wbase, int* flags)
+__global__ void __launch_bounds__(32) k_fixed_base_windows(const uint8_t* __restrict__ bases, uint32_t m, Proj<F>* __restrict__ wbase, int* flags)
 {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m * FB_WINDOWS) return;
-    const uint32_t j = t / FB_WINDOWS, w = t % FB_WINDOWS;
+    // one warp per base: W[j][w] = 2^(8w) base_j is ONE chain of 248 doublings, so it runs on the lane-cooperative doubling
+    // (two product latencies each, as in k_finish) instead of 32 threads redoing ever longer prefixes of it on their own
+    const uint32_t j = blockIdx.x, lane = threadIdx.x;
     Affine<F> base = generator<F>();
-    if (bases && !Wire<F>::parse(base, bases + (size_t)Wire<F>::AFFINE * j)) atomicOr(flags, FLAG_BAD_POINT);
+    if (bases && !Wire<F>::parse(base, bases + (size_t)Wire<F>::AFFINE * j) && lane == 0) atomicOr(flags, FLAG_BAD_POINT);
     Proj<F> acc = proj_from_affine(base);
 #pragma unroll 1
-    for (uint32_t i = 0; i < 8 * w; ++i) acc = proj_dbl(acc);
-    wbase[t] = acc;
+    for (uint32_t w = 0; w < FB_WINDOWS; ++w) {
+        if (lane == 0) wbase[j * FB_WINDOWS + w] = acc;
+        if (w + 1 < FB_WINDOWS) {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) acc = coop_dbl(acc, 0xffffffffu);
+        }
+    }
 }
 
 template <class F>
@@ -752,7 +757,7 @@ template <class F> int fixed_base_run(const uint8_t* d_scalars, size_t n, uint8_
     if (!table) {   // first use on this context: build the window table once
         C12_CUDA(cudaMalloc(&table, sizeof(Affine<F>) * FB_WINDOWS * FB_HALF + sizeof(Proj<F>) * FB_WINDOWS));
         Proj<F>* wbase = reinterpret_cast<Proj<F>*>(table + FB_WINDOWS * FB_HALF);
-        k_fixed_base_windows<F><<<cdiv(FB_WINDOWS, 64), 64, 0, s>>>(nullptr, 1, wbase, c.d_flags);
+        k_fixed_base_windows<F><<<1, 32, 0, s>>>(nullptr, 1, wbase, c.d_flags);
         C12_LAUNCHED();
         k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(1, wbase, table);
         C12_LAUNCHED();
@@ -778,7 +783,7 @@ template <class F> int multi_fixed_base_run(const uint8_t* d_bases, size_t m, co
     Affine<F>* table = (Affine<F>*)arena_take(sizeof(Affine<F>) * m * FB_WINDOWS * FB_HALF);
     Proj<F>* wbase = (Proj<F>*)arena_take(sizeof(Proj<F>) * m * FB_WINDOWS);
     if (!wbase) return set_error(C12381_ECUDA, "multi_fixed_base: scratch arena bound too small");
-    k_fixed_base_windows<F><<<cdiv(m * FB_WINDOWS, 64), 64, 0, s>>>(d_bases, (uint32_t)m, wbase, c.d_flags);
+    k_fixed_base_windows<F><<<(unsigned)m, 32, 0, s>>>(d_bases, (uint32_t)m, wbase, c.d_flags);
     C12_LAUNCHED();
     k_fixed_base_table<F><<<cdiv(m * FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>((uint32_t)m, wbase, table);
     C12_LAUNCHED();
