@@ -218,13 +218,26 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MIN_BLOCKS)
     __syncthreads();
     const uint32_t len = s_len;
     XYZZ<F> acc = xyzz_inf<F>();
+    uint32_t wnext = lo < hi ? vals[lo] : 0u;
 #pragma unroll 1
     for (uint32_t i = 0; i < len; ++i) {
         __syncthreads();
         const uint32_t j = lo + i;
         if (j < hi) {
-            uint32_t w = vals[j];
+            const uint32_t w = wnext;
             Affine<F> pt = pts[w & 0x7fffffffu];
+#if defined(C12_ACC_PREFETCH)
+            // the index of the NEXT term is read one addition ahead and its point is pulled towards the SM while this one is added:
+            // the block's warps reach their gathers together, so nothing else on the block hides that latency
+            if (j + 1 < hi) {
+                wnext = vals[j + 1];
+                const char* nx = reinterpret_cast<const char*>(pts + (wnext & 0x7fffffffu));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + sizeof(Affine<F>) - 4));
+            }
+#else
+            if (j + 1 < hi) wnext = vals[j + 1];
+#endif
             if (!affine_is_inf(pt)) {
                 if (w >> 31) pt.y = neg(pt.y);
                 xyzz_madd(acc, pt);
