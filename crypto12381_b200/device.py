@@ -237,6 +237,30 @@ def g2_compress_batch(data, out=None):
     return _convert("c12381_g2_compress_batch_dev", G2_AFFINE, G2_COMPRESSED, data, out)
 
 
+def _hash(fn_name, out_bytes, msgs, msg_len, out=None):
+    ensure_init()
+    n = _chk(msgs, "msgs").numel() // msg_len if msg_len else 0
+    if out is None:
+        out = _new(n * out_bytes, msgs)
+    check(getattr(lib(), fn_name)(msgs.data_ptr(), msg_len, n, out.data_ptr(), _stream()))
+    return out
+
+
+def sha3_512_batch(msgs, msg_len, out=None):
+    """SHA3-512 of every msg_len-byte message (c12381_sha3_512_batch_dev); n x 64 B."""
+    return _hash("c12381_sha3_512_batch_dev", 64, msgs, msg_len, out)
+
+
+def hash_to_zp_batch(msgs, msg_len, out=None):
+    """`hash(...) -> Zp` per message (c12381_hash_to_zp_batch_dev); n x 32 B big-endian."""
+    return _hash("c12381_hash_to_zp_batch_dev", 32, msgs, msg_len, out)
+
+
+def hash_to_g1_batch(msgs, msg_len, out=None):
+    """`hash(...) -> G1` per message (c12381_hash_to_g1_batch_dev); n x 49 B compressed."""
+    return _hash("c12381_hash_to_g1_batch_dev", G1_COMPRESSED, msgs, msg_len, out)
+
+
 def launch_count() -> int:
     return int(lib().c12381_launch_count())
 

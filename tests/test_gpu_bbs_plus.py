@@ -169,8 +169,16 @@ def test_hash_to_g1_batch(gpu, golden_hashing):
         assert got[:49 * 8] == b"".join(o.g1_compress(o.hash_to_g1(msgs[L * i:L * (i + 1)])) for i in range(8))
     B = 1 << 14
     msgs = bytes(rnd.randrange(256) for _ in range(32 * B))
-    pts = bridge.from_bytes(bridge.hash_to_g1(msgs, 32))
+    enc = bridge.hash_to_g1(msgs, 32)
+    pts = bridge.from_bytes(enc)
     assert bridge.is_member(pts) == bytes([1] * B)
+    # the device-pointer entries (CUDA tensors in, CUDA tensors out) give the same bytes
+    from crypto12381_b200 import device as dv
+    t = torch.frombuffer(bytearray(msgs), dtype=torch.uint8).cuda()
+    assert bytes(dv.hash_to_g1_batch(t, 32).cpu().numpy()) == enc
+    assert bytes(dv.hash_to_zp_batch(t, 32).cpu().numpy()) == bridge.hash_to_zp(msgs, 32)
+    assert bytes(dv.sha3_512_batch(t, 32).cpu().numpy()) == bridge.sha3_512(msgs, 32)
+    dv.sync_status()
     assert bridge.hash_to_g1(b"", 0) == b""
 
 
