@@ -392,6 +392,50 @@ def run_ours(args):
         dv.sync_status()
         line["secondary_g1_sweep"] = sweep
         del sw_p, sw_s
+    # secondary: batched scalar multiplication: g^x from the fixed-base table and P^k, rank 0 only,
+    # device-resident; CPU beside it: the reference's multiply (PAIR_G1mul) on a sample over all host threads
+    if not args.no_secondary and args.sweep_max_log_n >= 10 and rank == 0:
+        try:
+            nb = 1 << 18
+            xs_t = torch.from_numpy(rand_scalars(nb, 8100)).reshape(-1).to(dev)
+            ks_t = torch.from_numpy(rand_scalars(nb, 8200)).reshape(-1).to(dev)
+
+            def timed_ms(fn, reps=3):
+                fn()
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(reps):
+                    out = fn()
+                a1.record()
+                torch.cuda.synchronize()
+                return a0.elapsed_time(a1) / reps, out
+
+            ms_fb, pts_t = timed_ms(lambda: dv.g1_fixed_base_mul_batch(xs_t))
+            ms_mul, enc_t = timed_ms(lambda: dv.g1_mul_batch(pts_t, ks_t))
+            ms_fb2, pts2_t = timed_ms(lambda: dv.g2_fixed_base_mul_batch(xs_t[:32 * (nb // 4)]))
+            ms_mul2, _ = timed_ms(lambda: dv.g2_mul_batch(pts2_t, ks_t[:32 * (nb // 4)]))
+            dv.sync_status()
+            sm = {"g1_fixed_base_per_s": nb / (ms_fb * 1e-3), "g1_mul_per_s": nb / (ms_mul * 1e-3),
+                  "g2_fixed_base_per_s": (nb // 4) / (ms_fb2 * 1e-3), "g2_mul_per_s": (nb // 4) / (ms_mul2 * 1e-3),
+                  "batch": {"g1": nb, "g2": nb // 4}, "unit": "scalar multiplications/s",
+                  "ms": {"g1_fixed_base": ms_fb, "g1_mul": ms_mul, "g2_fixed_base": ms_fb2, "g2_mul": ms_mul2}}
+            try:
+                from oracle import ref
+                if ref.available():
+                    m = 64 * ref.hardware_threads()
+                    pb, kb = bytes(pts_t[:96 * m].cpu().numpy()), bytes(ks_t[:32 * m].cpu().numpy())
+                    tc = time.perf_counter()
+                    want = ref.g1_mul_batch(pb, kb, ref.hardware_threads())
+                    dtc = time.perf_counter() - tc
+                    sm["cpu_baseline"] = {"value": m / dtc, "unit": "G1 scalar multiplications/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                          "sample": f"{m} x multiply(point1&, big) -> PAIR_G1mul over {ref.hardware_threads()} host threads",
+                                          "bit_exact_vs_gpu_on_sample": want == bytes(enc_t[:49 * m].cpu().numpy())}
+            except Exception as e:
+                sm["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+            line["secondary_scalar_mul"] = sm
+        except Exception as e:      # a secondary must never cost the headline line
+            line["secondary_scalar_mul"] = {"error": str(e)}
     # secondary 3: BBS+ batch verification (BASELINE configs[4]): 2^16 signatures x 10 message blocks over all ranks,
     # instances split across ranks with no collective; the timed region is the whole device pipeline of bbs_plus.verify_batch_device
     if not args.no_secondary and args.bbs_log_b > 0:

@@ -19,7 +19,10 @@
 namespace c12 {
 
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;
+#ifndef C12_SORT_ITEMS
+#define C12_SORT_ITEMS 16
+#endif
+constexpr int SORT_ITEMS = C12_SORT_ITEMS;   // items per thread (tile = 256 x this); A/B knob
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 
