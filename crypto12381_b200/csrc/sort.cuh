@@ -20,9 +20,9 @@ namespace c12 {
 
 constexpr int SORT_THREADS = 256;
 #ifndef C12_SORT_ITEMS
-#define C12_SORT_ITEMS 16
+#define C12_SORT_ITEMS 8
 #endif
-constexpr int SORT_ITEMS = C12_SORT_ITEMS;   // items per thread (tile = 256 x this); A/B knob
+constexpr int SORT_ITEMS = C12_SORT_ITEMS;   // items per thread (tile = 256 x this).  Measured at n = 2^20: 16 -> 0.55 ms, 8 -> 0.43, 6 -> 0.42, 4 -> 0.47 (profiles/r01ay)
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 
@@ -125,8 +125,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(uint32_t* __restric
 
 // ---- stable scatter ------------------------------------------------------------------------------------------
 // Ranks every item of the tile stably (warp match/ballot + per-warp counters), then STAGES the tile in shared memory in
-// digit order before writing: a tile of 4,096 items over 256 digits holds ~16 items per digit, so consecutive threads
-// write runs of ~64 contiguous bytes instead of 4,096 isolated 4-byte words (the direct scatter moved 8x the sectors).
+// digit order before writing: a tile of 2,048 items over 256 digits holds ~8 items per digit, so consecutive threads
+// write runs of ~32 contiguous bytes (one sector) instead of isolated 4-byte words (the direct scatter moved 8x the sectors).
+// Smaller tiles rank faster (more blocks in flight per SM) than they lose in run length: see SORT_ITEMS.
 __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t* __restrict__ keys_in,
                                                                   const uint32_t* __restrict__ vals_in,
                                                                   uint32_t* __restrict__ keys_out,
