@@ -25,9 +25,15 @@
 namespace c12 {
 
 constexpr uint32_t MSM_MAX_LEVELS = 8;
-constexpr uint32_t MSM_LEVEL_LEN = 8;      // segment length of reduction levels >= 1 (a power of two)
-constexpr uint32_t MSM_LEVEL_LOG = 3;
-constexpr uint32_t MSM_REDUCE2_SPLIT = 8;  // tree-sum jobs per window over the level-0 sums
+#ifndef C12_MSM_LEVEL_LOG
+#define C12_MSM_LEVEL_LOG 3
+#endif
+#ifndef C12_MSM_REDUCE2_SPLIT
+#define C12_MSM_REDUCE2_SPLIT 8
+#endif
+constexpr uint32_t MSM_LEVEL_LOG = C12_MSM_LEVEL_LOG;
+constexpr uint32_t MSM_LEVEL_LEN = 1u << MSM_LEVEL_LOG;   // segment length of reduction levels >= 1 (a power of two)
+constexpr uint32_t MSM_REDUCE2_SPLIT = C12_MSM_REDUCE2_SPLIT;  // tree-sum jobs per window over the level-0 sums (a power of two <= 32)
 constexpr uint32_t MSM_WPART_SLOTS = MSM_REDUCE2_SPLIT + MSM_MAX_LEVELS;
 
 struct MsmPlan {
