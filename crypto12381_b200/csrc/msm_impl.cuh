@@ -188,7 +188,10 @@ __global__ void __launch_bounds__(128) k_accumulate_reduced(uint32_t total, cons
 #endif
 template <class F> struct AccShape {
 #if defined(C12_ACC_THREADS)
-    static constexpr int THREADS = C12_ACC_THREADS, MIN_BLOCKS = 1;
+#if !defined(C12_ACC_MIN_BLOCKS)
+#define C12_ACC_MIN_BLOCKS 1
+#endif
+    static constexpr int THREADS = C12_ACC_THREADS, MIN_BLOCKS = C12_ACC_MIN_BLOCKS;
 #else
     static constexpr int THREADS = sizeof(F) == sizeof(Fp) ? 128 : 64, MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? 3 : 6;
 #endif
