@@ -17,6 +17,12 @@
 using namespace crypto12381;
 using namespace crypto12381::detail::miracl_core;
 
+// ABI-additive entry of the replacement bridge (integration/miracl_core_interface_b200.cpp) - not in the reference header
+namespace crypto12381::detail::miracl_core
+{
+    void sum_of_products(point2& result, int n, point2* points, const big* numbers) noexcept;
+}
+
 // the reference's MIRACL-backed definitions, renamed by objcopy
 namespace refcpu
 {
@@ -188,6 +194,26 @@ int main()
         multiply(py, y);
         add(a, py);
         CHECK(same(ps, a));                                  // P^(x+y) == P^x * P^y (unit-tests/g2_point.cpp:51-78)
+    }
+
+    // ---- the additive G2 seam: sum_of_products(point2&) == the reference's per-term multiply + add loop ------
+    {
+        const int n = 37;
+        std::vector<point2> pts(n);
+        std::vector<big> nums(n);
+        point2 want;
+        get_infinity(want);
+        for (int i = 0; i < n; ++i)
+        {
+            random_g2(pts[i], random);
+            random_scalar(nums[i], random);
+            point2 t = pts[i];
+            refcpu::multiply(t, nums[i]);                    // g2_point.hpp:202-217 as the reference runs it
+            add(want, t);                                    // :225-236
+        }
+        point2 got;
+        sum_of_products(got, n, pts.data(), reinterpret_cast<const big*>(nums.data()));
+        CHECK(same(got, want));
     }
 
     // ---- pairings --------------------------------------------------------------------------------------------------

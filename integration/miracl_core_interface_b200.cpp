@@ -44,6 +44,14 @@ namespace crypto12381::detail::miracl_core
         must(c12381_sum_of_products_miracl(&result, n, points, numbers), "sum_of_products");
     }
 
+    // ABI-ADDITIVE: the G2 counterpart of the seam above, not declared by the reference header -
+    // what a lazy G2Pow / Π over G2 (g2_point.hpp:202-236, today n x PAIR_G2mul + n x ECP2_add) would call.  One G2 MSM launch.
+    void sum_of_products(point2& result, int n, point2* points, const big* numbers) noexcept
+    {
+        ensure_context();
+        must(c12381_sum_of_products2_miracl(&result, n, points, numbers), "sum_of_products(point2)");
+    }
+
     // G1Pow -> G1Point (g1_point.hpp:296-310), select g^x (:355-369); reference body -> PAIR_G1mul
     void multiply(point1& object, const big& value) noexcept
     {
