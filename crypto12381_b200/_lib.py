@@ -88,6 +88,7 @@ SIGNATURES = {
     "c12381_sum_of_products2_miracl": (_i, [_p, _i, _p, _p]),
     "c12381_pair_ate_miracl": (_i, [_p, _p, _p]),
     "c12381_pair_double_ate_miracl": (_i, [_p, _p, _p, _p, _p]),
+    "c12381_pair_multi_ate_miracl": (_i, [_p, ctypes.c_int, _p, _p]),
     "c12381_pair_final_exponentiation_miracl": (_i, [_p]),
     "c12381_fp12_multiply_miracl": (_i, [_p, _p]),
     "c12381_fp12_pow_miracl": (_i, [_p, _p, _p]),

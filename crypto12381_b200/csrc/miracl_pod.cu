@@ -132,11 +132,12 @@ template <class F> int pod_mul(void* object, const void* value)
     });
 }
 
-// k-pair Miller product on PODs (k = 1: pair_ate, k = 2: pair_double_ate)
+// k-pair Miller product on PODs (k = 1: pair_ate, k = 2: pair_double_ate, up to C12381_MAX_PAIRS for the n-pairing entry)
 int pod_miller(void* result_fp12, const void* const* p2s, const void* const* p1s, int k)
 {
     C12_REQUIRE_CTX();
-    uint8_t h1[2 * POD_P1], h2[2 * POD_P2];
+    if (k < 1 || k > C12381_MAX_PAIRS) return set_error(C12381_EARG, "pair_multi_ate: between 1 and C12381_MAX_PAIRS pairs");
+    uint8_t h1[C12381_MAX_PAIRS * POD_P1], h2[C12381_MAX_PAIRS * POD_P2];
     for (int j = 0; j < k; ++j) {
         if (!p1s[j] || !p2s[j] || !result_fp12) return set_error(C12381_EARG, "pair_ate: null pointer");
         memcpy(h1 + (size_t)POD_P1 * j, p1s[j], POD_P1);
@@ -145,8 +146,8 @@ int pod_miller(void* result_fp12, const void* const* p2s, const void* const* p1s
     const void* in[2] = {h1, h2};
     size_t sz[2] = {(size_t)POD_P1 * k, (size_t)POD_P2 * k};
     return with_staged(in, sz, 2, result_fp12, POD_FP12, 65536, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
-        uint8_t* w1 = (uint8_t*)arena_take(96 * 2);
-        uint8_t* w2 = (uint8_t*)arena_take(192 * 2);
+        uint8_t* w1 = (uint8_t*)arena_take(96 * C12381_MAX_PAIRS);
+        uint8_t* w2 = (uint8_t*)arena_take(192 * C12381_MAX_PAIRS);
         uint8_t* f = (uint8_t*)arena_take(576);
         int rc = pods_to_wire<Fp>(d_in[0], (uint32_t)k, w1, s);
         if (!rc) rc = pods_to_wire<Fp2>(d_in[1], (uint32_t)k, w2, s);
@@ -193,6 +194,17 @@ int c12381_pair_double_ate_miracl(void* result_fp12, const void* p2, const void*
     const void* a2[2] = {p2, q2};
     const void* a1[2] = {p1, q1};
     return pod_miller(result_fp12, a2, a1, 2);
+}
+
+int c12381_pair_multi_ate_miracl(void* result_fp12, int n, const void* p2s_point2, const void* p1s_point1)
+{
+    if (n < 1 || n > C12381_MAX_PAIRS || !p2s_point2 || !p1s_point1) return set_error(C12381_EARG, "pair_multi_ate: between 1 and C12381_MAX_PAIRS pairs");
+    const void *a2[C12381_MAX_PAIRS], *a1[C12381_MAX_PAIRS];
+    for (int j = 0; j < n; ++j) {
+        a2[j] = (const uint8_t*)p2s_point2 + (size_t)POD_P2 * j;
+        a1[j] = (const uint8_t*)p1s_point1 + (size_t)POD_P1 * j;
+    }
+    return pod_miller(result_fp12, a2, a1, n);
 }
 
 int c12381_pair_final_exponentiation_miracl(void* object_fp12)

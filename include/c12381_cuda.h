@@ -203,6 +203,10 @@ C12381_API int c12381_sum_of_products2_miracl(void* result_point2, int n, const 
 C12381_API int c12381_pair_ate_miracl(void* result_fp12, const void* p2_point2, const void* p1_point1);
 /* void pair_double_ate(fp12& result, point2& p2, point1& p1, point2& q2, point1& q1)  (:203) */
 C12381_API int c12381_pair_double_ate_miracl(void* result_fp12, const void* p2, const void* p1, const void* q2, const void* q1);
+/* ABI-additive: the product of n <= C12381_MAX_PAIRS Miller loops with shared squarings, p2s = point2[n], p1s = point1[n];
+ * what a `pair * pair * ...` chain (liner_pair.hpp:219-230,291-303: pair_double_ate two at a time + multiply(fp12&, fp12&)) folds to,
+ * and the value of MIRACL's unbridged PAIR_initmp / PAIR_another / PAIR_miller (pair_BLS12381.cpp:181-207,352-422). */
+C12381_API int c12381_pair_multi_ate_miracl(void* result_fp12, int n, const void* p2s_point2, const void* p1s_point1);
 /* void pair_final_exponentiation(fp12& object)  (:201) */
 C12381_API int c12381_pair_final_exponentiation_miracl(void* object_fp12);
 /* void multiply(fp12& result, fp12& value): result *= value  (:189) */

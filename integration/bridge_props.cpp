@@ -21,6 +21,7 @@ using namespace crypto12381::detail::miracl_core;
 namespace crypto12381::detail::miracl_core
 {
     void sum_of_products(point2& result, int n, point2* points, const big* numbers) noexcept;
+    void pair_multi_ate(fp12& result, int n, point2* p2s, point1* p1s) noexcept;
 }
 
 // the reference's MIRACL-backed definitions, renamed by objcopy
@@ -213,6 +214,29 @@ int main()
         }
         point2 got;
         sum_of_products(got, n, pts.data(), reinterpret_cast<const big*>(nums.data()));
+        CHECK(same(got, want));
+    }
+
+    // ---- the additive n-pairing seam: one Miller product == the reference's pair_ate values multiplied together -----
+    for (int n : {1, 3, 4, 7})
+    {
+        std::vector<point1> p1s(n);
+        std::vector<point2> p2s(n);
+        fp12 want;
+        for (int i = 0; i < n; ++i)
+        {
+            random_g1(p1s[i], random);
+            random_g2(p2s[i], random);
+            point1 p = p1s[i];
+            point2 q = p2s[i];
+            fp12 m;
+            refcpu::pair_ate(m, q, p);
+            if (i == 0) want = m; else refcpu::multiply(want, m);
+        }
+        fp12 got;
+        pair_multi_ate(got, n, p2s.data(), p1s.data());
+        refcpu::pair_final_exponentiation(want);
+        refcpu::pair_final_exponentiation(got);
         CHECK(same(got, want));
     }
 

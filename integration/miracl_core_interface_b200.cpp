@@ -52,6 +52,14 @@ namespace crypto12381::detail::miracl_core
         must(c12381_sum_of_products2_miracl(&result, n, points, numbers), "sum_of_products(point2)");
     }
 
+    // ABI-ADDITIVE: the Miller value of a whole `pair * pair * ...` chain (liner_pair.hpp:219-230,291-303), n <= 8 pairs
+    // with shared squarings - what the DSL folds two at a time through pair_double_ate and multiply(fp12&, fp12&) today.
+    void pair_multi_ate(fp12& result, int n, point2* p2s, point1* p1s) noexcept
+    {
+        ensure_context();
+        must(c12381_pair_multi_ate_miracl(&result, n, p2s, p1s), "pair_multi_ate");
+    }
+
     // G1Pow -> G1Point (g1_point.hpp:296-310), select g^x (:355-369); reference body -> PAIR_G1mul
     void multiply(point1& object, const big& value) noexcept
     {
