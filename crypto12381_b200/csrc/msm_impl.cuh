@@ -193,7 +193,10 @@ template <class F> struct AccShape {
 #endif
     static constexpr int THREADS = C12_ACC_THREADS, MIN_BLOCKS = C12_ACC_MIN_BLOCKS;
 #else
-    static constexpr int THREADS = sizeof(F) == sizeof(Fp) ? 128 : 64, MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? 3 : 6;
+#if !defined(C12_ACC2_MIN_BLOCKS)
+#define C12_ACC2_MIN_BLOCKS 6
+#endif
+    static constexpr int THREADS = sizeof(F) == sizeof(Fp) ? 128 : 64, MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? 3 : C12_ACC2_MIN_BLOCKS;
 #endif
 };
 template <class F>
