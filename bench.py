@@ -13,7 +13,13 @@ seeded synthetic (point, scalar) terms per GPU.  With N GPUs every rank owns 2^2
   roofline   dominant kernel k_accumulate against the integer-multiply peak measured live by c12381_probe
   cpu_baseline   the reference's own CPU path (oracle/_ref: MIRACL ECP_muln via the unmodified bridge) on a
              bounded sample of the same points, all host threads, rank 0 only
-  secondary  batched 4-pair pairing products (BASELINE configs[3]) as pairings/s, same run
+  secondary  batched 4-pair pairing products (BASELINE configs[3]) as pairings/s, G2 MSM (configs[2]), the G1 sweep
+             (configs[1]), BBS+ batch verification (configs[4]), same run
+Everything that defines the BASELINE metric is ALSO written as flat scalar keys inside `roofline` (pairings_per_s,
+hbm_phase_frac, g2_msm_points_per_s, bbs_verifications_per_s, strong_* ...): nested objects do not survive the driver's
+record.  strong_*: ONE 2^20-term sum split over the N ranks (strong scaling) beside the weak-scaling headline.
+multi_rank_result_ok: rank 0 recomputes the expected total of the all-ranks sum from the seeds (sum s_i k_i mod r, then
+g^total through the fixed-base kernel) and compares it with the merged result.
 `--impl reference` times only the reference CPU path (rank 0), same metric/unit/config."""
 from __future__ import annotations
 
@@ -34,6 +40,7 @@ UNIT = "points/s"
 FP_MUL_PER_BUCKET_ADD = 10      # XYZZ mixed addition: 8 M + 2 S
 MAC_PER_FP_MUL = 300            # 12x12 product + 12x12 reduction + 12 quotient digits
 R_TOP = 0x73
+PAIRING_FP_MUL_KERNEL_COUNT = 30751   # Montgomery products per 4-pair product + final exponentiation (tools/count_fp_mul.py)
 
 
 def parse():
@@ -44,8 +51,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--pairing-instances", type=int, default=1 << 16)
-    ap.add_argument("--cpu-sample-log-n", type=int, default=18)
-    ap.add_argument("--g2-log-n", type=int, default=18)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=20)
+    ap.add_argument("--g2-log-n", type=int, default=20)
+    ap.add_argument("--strong-log-n", type=int, default=20)
     ap.add_argument("--bbs-log-b", type=int, default=16)
     ap.add_argument("--sweep-max-log-n", type=int, default=24)
     ap.add_argument("--no-secondary", action="store_true")
@@ -98,6 +106,50 @@ def rand_scalars(n, seed):
     return a
 
 
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def dot_mod_r(k, s):
+    """sum_i k_i s_i mod r for two (n, 32) uint8 arrays of big-endian scalars: 16-bit limbs, the 16 x 16 limb-pair sums as ONE
+    float64 matrix product (every partial sum stays below 2^53: products < 2^32, at most 2^20 rows per block), exact."""
+    import numpy as np
+    total = 0
+    for lo in range(0, k.shape[0], 1 << 20):
+        kk = k[lo:lo + (1 << 20)].reshape(-1, 16, 2).astype(np.float64)
+        ss = s[lo:lo + (1 << 20)].reshape(-1, 16, 2).astype(np.float64)
+        kl = kk[:, ::-1, 0] * 256.0 + kk[:, ::-1, 1]        # limb a: bits [16 a, 16 a + 16)
+        sl = ss[:, ::-1, 0] * 256.0 + ss[:, ::-1, 1]
+        m = kl.T @ sl                                      # m[a, b] = sum_i k_ia s_ib < 2^52
+        for a in range(16):
+            for b in range(16):
+                total += int(m[a, b]) << (16 * (a + b))
+    return total % R_ORDER
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and, by first touch, its pinned buffers) to the CPUs next to its GPU; best effort."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"], text=True).strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]
+        path = f"/sys/bus/pci/devices/{bus}"
+        with open(f"{path}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        if cpus:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or os.sched_getaffinity(0))
+        with open(f"{path}/numa_node") as f:
+            return int(f.read().strip())
+    except Exception:
+        return None
+
+
 # ---- the reference arm ---------------------------------------------------------------------------------------------
 def reference_points(n, seed):
     """n seeded points k_i*G made by the REFERENCE on the host (all threads): the CPU arm needs no GPU."""
@@ -128,14 +180,23 @@ def run_reference(args):
     if not ref.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libref12381.so was not built (needs /root/reference at build time)"}))
         return
-    n = 1 << args.cpu_sample_log_n
+    # the workload its config names: a 2^log_n-term sum per step (ECP_muln is linear in n; ~4.4 s per step on 16 threads).  The
+    # driver's --steps/--warmup are honoured up to a budget of ~150 s of CPU time; `steps_run` says what was actually timed.
+    n = 1 << args.log_n
     pts = reference_points(n, 1000)
     ss = rand_scalars(n, 2000).tobytes()
-    v, dt, threads, _ = time_reference(pts, ss, max(1, args.steps), max(1, args.warmup))
-    sample = f"2^{args.cpu_sample_log_n}-term G1 sum per step (bounded sample of the 2^{args.log_n} workload), sum_of_products -> MIRACL ECP_muln, chunked over {threads} host threads"
+    t0 = time.perf_counter()
+    ref.g1_msm(pts, ss, 0, ref.hardware_threads())          # first pass: warm-up and the per-step cost
+    per = time.perf_counter() - t0
+    budget = 150.0
+    steps = max(1, min(args.steps, int(budget / per) - 1))
+    warm = max(0, min(args.warmup - 1, int((budget - steps * per) / per) - 1))
+    v, dt, threads, _ = time_reference(pts, ss, steps, warm)
+    sample = (f"the full 2^{args.log_n}-term G1 sum per step, sum_of_products -> MIRACL ECP_muln chunked over {threads} host threads; "
+              f"{steps} timed step(s) after {warm + 1} warm-up pass(es) (bounded to ~{budget:.0f} s of the {args.steps}/{args.warmup} asked for)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64 (7x58-bit limbs, CPU)",
-            "data": "synthetic", "config": config(args, world),
+            "steps_run": steps, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64 (7x58-bit limbs, CPU)", "data": "synthetic", "config": config(args, world),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -143,6 +204,7 @@ def run_reference(args):
 
 # ---- our arm ----------------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -151,30 +213,61 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this path has no CPU fallback (use --impl reference for the CPU arm)")
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from crypto12381_b200 import _lib, device as dv
-    from crypto12381_b200.distributed import g1_msm_sharded
+    from crypto12381_b200.distributed import g1_msm_sharded, g1_msm_sharded_host, g2_msm_sharded
     _lib.init(local)
     lib = _lib.lib()
     n = 1 << args.log_n
     dev = torch.device("cuda", local)
 
-    # synthetic seeded inputs: points k_i*G made on the GPU by the fixed-base kernel (setup, untimed)
-    h_k = torch.from_numpy(rand_scalars(n, 1000 + rank)).reshape(-1)
-    h_s = torch.from_numpy(rand_scalars(n, 2000 + rank)).reshape(-1).pin_memory()
-    d_s = h_s.to(dev)
-    d_p = dv.g1_fixed_base_mul_batch(h_k.to(dev))
-    dv.sync_status()
-    h_p = d_p.cpu().pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    out = torch.empty(49, dtype=torch.uint8, device=dev)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, reps, flush_each=True):
+        """mean CUDA-event ms of fn() over reps calls, L2 flushed before each, barrier on both sides, max over ranks"""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        barrier()
+        out = None
+        for a, b in evs:
+            if flush_each:
+                flush.fill_(1)
+            a.record()
+            out = fn()
+            b.record()
+        barrier()
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs) / reps), out
+
+    def expected_g1(ks, ss):
+        """compressed g^(sum k_i s_i): what any evaluation order of the sum must serialise to"""
+        tot = dot_mod_r(ks, ss)
+        pt = dv.g1_fixed_base_mul_batch(torch.frombuffer(bytearray(tot.to_bytes(32, "big")), dtype=torch.uint8).to(dev))
+        return bytes(dv.g1_compress_batch(pt).cpu().numpy())
+
+    def expected_g2(ks, ss):
+        tot = dot_mod_r(ks, ss)
+        pt = dv.g2_fixed_base_mul_batch(torch.frombuffer(bytearray(tot.to_bytes(32, "big")), dtype=torch.uint8).to(dev))
+        return bytes(dv.g2_compress_batch(pt).cpu().numpy())
+
+    # synthetic seeded inputs: points k_i*G made on the GPU by the fixed-base kernel (setup, untimed)
+    k_np, s_np = rand_scalars(n, 1000 + rank), rand_scalars(n, 2000 + rank)
+    h_s = torch.from_numpy(s_np).reshape(-1).pin_memory()
+    d_s = h_s.to(dev)
+    d_p = dv.g1_fixed_base_mul_batch(torch.from_numpy(k_np).reshape(-1).to(dev))
+    dv.sync_status()
+    h_p = d_p.cpu().pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
         return g1_msm_sharded(d_p, d_s)
@@ -186,7 +279,7 @@ def run_ours(args):
     sampler.start()
     time.sleep(0.3)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    acc_ms, tot_ms = [], []
+    acc_ms, tot_ms, phase_acc = [], [], {}
     l0 = int(lib.c12381_launch_count())
     barrier()
     t0 = time.time()
@@ -199,34 +292,61 @@ def run_ours(args):
         st = dv.last_msm_stats()
         acc_ms.append(st["accumulate_ms"])
         tot_ms.append(st["total_ms"])
+        for kph, vph in st["phases_ms"].items():
+            phase_acc.setdefault(kph, []).append(vph)
     barrier()
     t1 = time.time()
     launches = int(lib.c12381_launch_count()) - l0
-    step_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
-    t = torch.tensor([step_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms = float(t.item())
+    step_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / args.steps)
     clocks = sampler.stop(t0, t1)
     result = bytes(res.cpu().numpy())
     stats = dv.last_msm_stats()
+    local_ms = statistics.mean(tot_ms)              # this rank's pipeline alone (no collective): a 2^log_n sum on ONE GPU
 
-    # e2e: host-pointer C-ABI call, pinned host buffers, H2D + D2H inside the timed region (per rank, its own shard)
-    import ctypes
-    h_out = torch.empty(49, dtype=torch.uint8).pin_memory()
+    # e2e: HOST buffers in, host bytes out, every step: pinned H2D of the rank's 128 MiB shard, the pipeline, (N > 1: the all-gather
+    # and merge of the partials,) the D2H of the result.  N = 1: the host-pointer C-ABI call c12381_g1_msm itself.
     for _ in range(2):
-        _lib.check(lib.c12381_g1_msm(h_p.data_ptr(), h_s.data_ptr(), n, h_out.data_ptr()))
+        e2e_out = g1_msm_sharded_host(h_p, h_s)
     barrier()
     te = time.perf_counter()
     for _ in range(args.steps):
-        _lib.check(lib.c12381_g1_msm(h_p.data_ptr(), h_s.data_ptr(), n, h_out.data_ptr()))
-    e2e_ms = (time.perf_counter() - te) / args.steps * 1e3
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item())
-    if world == 1:
-        assert bytes(h_out.numpy()) == result, "host-pointer and device-pointer entries disagree"
+        e2e_out = g1_msm_sharded_host(h_p, h_s)
+    e2e_ms = max_over_ranks((time.perf_counter() - te) / args.steps * 1e3)
+    e2e_ok = e2e_out == result
+
+    # the merged result against the seeds, over ALL ranks' inputs
+    multi_ok = None
+    if rank == 0:
+        try:
+            ks_all = np.concatenate([k_np] + [rand_scalars(n, 1000 + r) for r in range(1, world)])
+            ss_all = np.concatenate([s_np] + [rand_scalars(n, 2000 + r) for r in range(1, world)])
+            multi_ok = expected_g1(ks_all, ss_all) == result
+            del ks_all, ss_all
+        except Exception as e:
+            multi_ok = f"check failed to run: {e}"
+
+    # strong scaling: ONE 2^strong_log_n-term sum split over the ranks (rank r owns the first n_s / N of its terms)
+    ns_total = 1 << args.strong_log_n
+    ns = max(1, ns_total // world)
+    strong = None
+    if ns <= n:
+        sp, ssc = d_p[:96 * ns], d_s[:32 * ns]
+        for _ in range(3):
+            g1_msm_sharded(sp, ssc)
+        strong_ms, sres = timed(lambda: g1_msm_sharded(sp, ssc), max(5, args.steps // 2))
+        single_ms = None
+        if ns_total <= n:      # the same total on ONE GPU, this run, this rank: the denominator of the speed-up
+            for _ in range(2):
+                dv.g1_msm(d_p[:96 * ns_total], d_s[:32 * ns_total])
+            single_ms, _ = timed(lambda: dv.g1_msm(d_p[:96 * ns_total], d_s[:32 * ns_total]), max(5, args.steps // 2))
+        strong = {"n_total": ns * world, "ms": strong_ms, "single_gpu_ms": single_ms, "result": bytes(sres.cpu().numpy())}
+        if rank == 0:
+            try:
+                ks_all = np.concatenate([k_np[:ns]] + [rand_scalars(n, 1000 + r)[:ns] for r in range(1, world)])
+                ss_all = np.concatenate([s_np[:ns]] + [rand_scalars(n, 2000 + r)[:ns] for r in range(1, world)])
+                strong["ok"] = expected_g1(ks_all, ss_all) == strong["result"]
+            except Exception as e:
+                strong["ok"] = f"check failed to run: {e}"
 
     line = None
     if rank == 0:
@@ -250,7 +370,11 @@ def run_ours(args):
                     "peak_source": "measured live: c12381_probe kind 2 (mad.wide.u32 chains) / kind 1 (mad.lo.cc+madc.hi.cc pairs), same GPU, same run",
                     "algorithmic": f"{adds} bucket additions/launch x {FP_MUL_PER_BUCKET_ADD} Fp-mul x {MAC_PER_FP_MUL} MAC",
                     "kernel_ms": acc, "kernel_share_of_step": acc / statistics.mean(tot_ms), "window_bits": stats["window_bits"],
-                    "fp_mul_gops": probes["fp_mul"]["gops"], "fp_sqr_gops": probes["fp_sqr"]["gops"], "probes": probes}
+                    "fp_mul_gops": probes["fp_mul"]["gops"], "fp_sqr_gops": probes["fp_sqr"]["gops"],
+                    "imad_gops": probes["imad"]["gops"], "imad_wide_gops": probes["imad_wide"]["gops"], "madc_pair_gops": probes["madc_pairs"]["gops"],
+                    # SURVEY §8(d)'s algorithmic unit beside the executed one: 6 Fp-mul per batch-affine addition
+                    "frac_algorithmic_6mul": adds * 6 * MAC_PER_FP_MUL / (acc * 1e-3) / 1e9 / peak_gmacs,
+                    "frac_of_step_executed": adds * FP_MUL_PER_BUCKET_ADD * MAC_PER_FP_MUL / (statistics.mean(tot_ms) * 1e-3) / 1e9 / peak_gmacs}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 hbm = json.load(f)["hbm_gbs"]
@@ -258,114 +382,159 @@ def run_ours(args):
         except Exception:
             hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
         passes = (stats["window_bits"] + 7) // 8
-        ph = stats["phases_ms"]
+        ph = {kph: statistics.mean(v) for kph, v in phase_acc.items()}
         sort_bytes = adds * 8 * 2 * passes      # (key, index) pairs read and written once per radix pass
-        roofline["phases_ms"] = ph
-        roofline["hbm_phase"] = {"what": "segmented radix sort of the (bucket key, term index) pairs: bucket scatter", "algorithmic_bytes": sort_bytes,
-                                 "ms": ph["sort"], "achieved_gbs": sort_bytes / (ph["sort"] * 1e-3) / 1e9 if ph["sort"] > 0 else None,
-                                 "peak_gbs": hbm, "frac": (sort_bytes / (ph["sort"] * 1e-3) / 1e9 / hbm) if ph["sort"] > 0 else None,
-                                 "peak_source": hbm_src, "radix_passes": passes}
+        for kph, vph in ph.items():
+            roofline["ms_" + kph] = vph
+        roofline["ms_tail"] = ph["reduce1"] + ph["reduce2"] + ph["finish"]
+        if ph["sort"] > 0:
+            roofline.update({"hbm_phase_what": "segmented radix sort of the (bucket key, term index) pairs (bucket scatter)",
+                             "hbm_phase_bytes": sort_bytes, "hbm_phase_ms": ph["sort"], "hbm_phase_gbs": sort_bytes / (ph["sort"] * 1e-3) / 1e9,
+                             "hbm_phase_peak_gbs": hbm, "hbm_phase_frac": sort_bytes / (ph["sort"] * 1e-3) / 1e9 / hbm,
+                             "hbm_phase_peak_source": hbm_src, "hbm_phase_radix_passes": passes})
+        roofline["multi_rank_result_ok"] = multi_ok
+        roofline["e2e_result_ok"] = e2e_ok
+        roofline["single_gpu_pipeline_ms"] = local_ms
+        if strong:
+            roofline.update({"strong_n_total": strong["n_total"], "strong_ms": strong["ms"], "strong_points_per_s": strong["n_total"] / (strong["ms"] * 1e-3),
+                             "strong_single_gpu_ms": strong["single_gpu_ms"],
+                             "strong_speedup": (strong["single_gpu_ms"] / strong["ms"]) if strong["single_gpu_ms"] else None,
+                             "strong_result_ok": strong.get("ok")})
         cpu = None
         try:
             from oracle import ref
             if ref.available():
-                m = 1 << args.cpu_sample_log_n
+                m = min(n, 1 << args.cpu_sample_log_n)
                 pts, ss = bytes(h_p[:96 * m].numpy()), bytes(h_s[:32 * m].numpy())
                 v, dt, threads, cpu_out = time_reference(pts, ss, 1, 0)
                 # same inputs, so the sample doubles as a parity check of the CUDA path against the reference
                 got = bytes(dv.g1_msm(d_p[:96 * m], d_s[:32 * m]).cpu().numpy())
                 cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "reference", "bit_exact_vs_gpu_on_sample": got == cpu_out,
-                       "sample": f"first 2^{args.cpu_sample_log_n} terms of rank 0's inputs, one pass ({dt:.2f} s), sum_of_products -> MIRACL ECP_muln chunked over {threads} host threads (oracle/_ref, -O2)"}
+                       "sample": f"first 2^{int(np.log2(m))} terms of rank 0's inputs ({'the whole headline sum' if m == n else 'a bounded sample'}), one pass ({dt:.2f} s), "
+                                 f"sum_of_products -> MIRACL ECP_muln chunked over {threads} host threads (oracle/_ref, -O2)"}
+                roofline["cpu_bit_exact_full_sum"] = bool(got == cpu_out) if m == n else None
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        e2e_call = ("c12381_g1_msm (host pointers, pinned)" if world == 1 else
+                    "distributed.g1_msm_sharded_host: c12381_g1_msm_partial (host pointers, pinned) per rank, NCCL all-gather of the 96-byte partials, "
+                    "c12381_g1_sum_dev, D2H of the 49-byte result")
         line = {"metric": METRIC, "value": n * world / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (12x32-bit limbs, Montgomery R=2^384)",
                 "data": "synthetic", "config": config(args, world), "clocks": clocks,
                 "e2e": {"value": n * world / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": 49, "ms_per_step": e2e_ms,
-                        "call": "c12381_g1_msm (host pointers, pinned), per rank on its own shard"},
+                        "call": e2e_call, "numa_node_bound": numa},
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "result_hex": result.hex()}
 
+    def secondary(name, fn):
+        """a secondary must never cost the headline line"""
+        try:
+            fn()
+        except Exception as e:
+            if rank == 0:
+                line[name] = {"error": f"{type(e).__name__}: {e}"}
+            try:
+                dv.sync_status()
+            except Exception:
+                pass
+
     # secondary: batched 4-pair pairing products (BASELINE configs[3]); instances sharded over ranks, no collective
-    if not args.no_secondary:
+    def sec_pairing():
         B, k = max(1, args.pairing_instances // world), 4
         a = torch.from_numpy(rand_scalars(B * k, 3000 + rank)).reshape(-1).to(dev)
         b = torch.from_numpy(rand_scalars(B * k, 4000 + rank)).reshape(-1).to(dev)
         g1, g2 = dv.g1_fixed_base_mul_batch(a), dv.g2_fixed_base_mul_batch(b)
         gt = torch.empty(B * 576, dtype=torch.uint8, device=dev)
         dv.pairing_product_batch(g1, g2, k, gt)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dv.pairing_product_batch(g1, g2, k, gt)
-        e1.record()
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            ms = float(t.item())
-            sec = {"metric": "pairings_per_s", "value": B * world * k / (ms * 1e-3), "unit": "pairings/s", "products_per_s": B * world / (ms * 1e-3),
-                   "instances": B * world, "pairs_per_instance": k, "ms": ms,
-                   "fp_mul_per_instance_ref_count": 31600, "gmacs": B * 31600 * MAC_PER_FP_MUL / (ms * 1e-3) / 1e9}
-            sec["frac_of_int32_mad_peak"] = sec["gmacs"] / line["roofline"]["peak"]
-            if k == 4:      # the kernel bodies' own count (tools/count_fp_mul.py, host build with -DC12_COUNT_FP_MUL)
-                sec["fp_mul_per_instance_kernel_count"] = 30751
-                sec["frac_of_int32_mad_peak_kernel_count"] = sec["frac_of_int32_mad_peak"] * 30751 / 31600
-            try:
-                from oracle import ref
-                if ref.available():
-                    m = min(B, 4 * ref.hardware_threads())
-                    p1, p2 = bytes(g1[:96 * k * m].cpu().numpy()), bytes(g2[:192 * k * m].cpu().numpy())
-                    tc = time.perf_counter()
-                    want = ref.pairing_product_batch(p1, p2, k, 1, ref.hardware_threads())
-                    dtc = time.perf_counter() - tc
-                    sec["cpu_baseline"] = {"value": m * k / dtc, "unit": "pairings/s", "cores": ref.hardware_threads(), "kind": "reference",
-                                           "sample": f"{m} instances x {k} pairs", "bit_exact_vs_gpu_on_sample": want == bytes(gt[:576 * m].cpu().numpy())}
-            except Exception as e:
-                sec["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
-            line["secondary"] = sec
-    # secondary 2: G2 MSM (BASELINE configs[2]), n = 2^18 per GPU, partial -> all-gather -> merge as for G1
-    if not args.no_secondary:
-        from crypto12381_b200.distributed import g2_msm_sharded
+        ms, _ = timed(lambda: dv.pairing_product_batch(g1, g2, k, gt), 2, flush_each=False)
+        if rank != 0:
+            return
+        sec = {"metric": "pairings_per_s", "value": B * world * k / (ms * 1e-3), "unit": "pairings/s", "products_per_s": B * world / (ms * 1e-3),
+               "instances": B * world, "pairs_per_instance": k, "ms": ms,
+               "fp_mul_per_instance_ref_count": 31600, "gmacs": B * world * 31600 * MAC_PER_FP_MUL / (ms * 1e-3) / 1e9}
+        peak = line["roofline"]["peak"] * world
+        sec["frac_of_int32_mad_peak"] = sec["gmacs"] / peak
+        sec["fp_mul_per_instance_kernel_count"] = PAIRING_FP_MUL_KERNEL_COUNT    # tools/count_fp_mul.py, host build with -DC12_COUNT_FP_MUL
+        sec["frac_of_int32_mad_peak_kernel_count"] = sec["frac_of_int32_mad_peak"] * PAIRING_FP_MUL_KERNEL_COUNT / 31600
+        try:
+            from oracle import ref
+            if ref.available():
+                m = min(B, 4 * ref.hardware_threads())
+                p1, p2 = bytes(g1[:96 * k * m].cpu().numpy()), bytes(g2[:192 * k * m].cpu().numpy())
+                tc = time.perf_counter()
+                want = ref.pairing_product_batch(p1, p2, k, 1, ref.hardware_threads())
+                dtc = time.perf_counter() - tc
+                sec["cpu_baseline"] = {"value": m * k / dtc, "unit": "pairings/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                       "sample": f"{m} instances x {k} pairs", "bit_exact_vs_gpu_on_sample": want == bytes(gt[:576 * m].cpu().numpy())}
+        except Exception as e:
+            sec["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+        line["secondary"] = sec
+        cb = sec.get("cpu_baseline", {})
+        line["roofline"].update({"pairings_per_s": sec["value"], "pairing_products_per_s": sec["products_per_s"], "pairing_instances": B * world,
+                                 "pairing_ms": ms, "pairing_frac_of_mad_peak": sec["frac_of_int32_mad_peak_kernel_count"],
+                                 "pairing_frac_of_mad_peak_ref_count": sec["frac_of_int32_mad_peak"],
+                                 "pairing_cpu_pairings_per_s": cb.get("value"), "pairing_cpu_cores": cb.get("cores"),
+                                 "pairing_bit_exact_vs_cpu_sample": cb.get("bit_exact_vs_gpu_on_sample")})
+
+    # secondary: G2 MSM (BASELINE configs[2]) at n = 2^g2_log_n per GPU (weak) and 2^g2_log_n in total (strong), partial ->
+    # all-gather -> merge as for G1; the merged result checked against the seeds
+    def sec_g2():
         n2 = 1 << args.g2_log_n
-        k2 = torch.from_numpy(rand_scalars(n2, 5000 + rank)).reshape(-1).to(dev)
-        s2 = torch.from_numpy(rand_scalars(n2, 6000 + rank)).reshape(-1).to(dev)
-        p2 = dv.g2_fixed_base_mul_batch(k2)
+        k2n, s2n = rand_scalars(n2, 5000 + rank), rand_scalars(n2, 6000 + rank)
+        s2 = torch.from_numpy(s2n).reshape(-1).to(dev)
+        p2 = dv.g2_fixed_base_mul_batch(torch.from_numpy(k2n).reshape(-1).to(dev))
         for _ in range(2):
-            r2 = g2_msm_sharded(p2, s2)
-        barrier()
-        reps = 3
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.fill_(1)
-        e0.record()
-        for _ in range(reps):
-            r2 = g2_msm_sharded(p2, s2)
-        e1.record()
-        barrier()
+            g2_msm_sharded(p2, s2)
+        ms, r2 = timed(lambda: g2_msm_sharded(p2, s2), 3)
         st2 = dv.last_msm_stats()
-        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            ms = float(t.item())
-            g2 = {"metric": "g2_msm_points_per_s", "value": n2 * world / (ms * 1e-3), "unit": "points/s", "n_per_gpu": n2, "ms": ms,
-                  "window_bits": st2["window_bits"], "phases_ms": st2["phases_ms"], "result_hex": bytes(r2.cpu().numpy()).hex()}
-            try:
-                from oracle import ref
-                if ref.available():
-                    m = 1 << 11
-                    tc = time.perf_counter()
-                    want = ref.g2_msm(bytes(p2[:192 * m].cpu().numpy()), bytes(s2[:32 * m].cpu().numpy()), ref.hardware_threads())
-                    dtc = time.perf_counter() - tc
-                    got = bytes(dv.g2_msm(p2[:192 * m], s2[:32 * m]).cpu().numpy())
-                    g2["cpu_baseline"] = {"value": m / dtc, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
-                                          "sample": f"first 2^11 terms: per-term PAIR_G2mul + ECP2_add loop (g2_point.hpp:202-236) over {ref.hardware_threads()} host threads",
-                                          "bit_exact_vs_gpu_on_sample": want == got}
-            except Exception as e:
-                g2["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
-            line["secondary_g2_msm"] = g2
+        r2b = bytes(r2.cpu().numpy())
+        ns2 = max(1, n2 // world)
+        for _ in range(2):
+            g2_msm_sharded(p2[:192 * ns2], s2[:32 * ns2])
+        ms_strong, r2s = timed(lambda: g2_msm_sharded(p2[:192 * ns2], s2[:32 * ns2]), 3)
+        if rank != 0:
+            return
+        adds2 = st2["bucket_adds"]
+        acc2 = st2["accumulate_ms"]
+        g2 = {"metric": "g2_msm_points_per_s", "value": n2 * world / (ms * 1e-3), "unit": "points/s", "n_per_gpu": n2, "ms": ms,
+              "window_bits": st2["window_bits"], "phases_ms": st2["phases_ms"], "result_hex": r2b.hex(),
+              "strong": {"n_total": ns2 * world, "ms": ms_strong, "points_per_s": ns2 * world / (ms_strong * 1e-3)},
+              # Fp2 XYZZ mixed addition: 8 Fp2-mul + 2 Fp2-sqr = 8 x 3 + 2 x 2 = 28 Fp-mul
+              "accumulate_ms": acc2, "accumulate_frac_of_mad_peak": adds2 * 28 * MAC_PER_FP_MUL / (acc2 * 1e-3) / 1e9 / line["roofline"]["peak"]}
+        try:
+            ks_all = np.concatenate([k2n] + [rand_scalars(n2, 5000 + r) for r in range(1, world)])
+            ss_all = np.concatenate([s2n] + [rand_scalars(n2, 6000 + r) for r in range(1, world)])
+            g2["multi_rank_result_ok"] = expected_g2(ks_all, ss_all) == r2b
+            ks_all = np.concatenate([k2n[:ns2]] + [rand_scalars(n2, 5000 + r)[:ns2] for r in range(1, world)])
+            ss_all = np.concatenate([s2n[:ns2]] + [rand_scalars(n2, 6000 + r)[:ns2] for r in range(1, world)])
+            g2["strong"]["result_ok"] = expected_g2(ks_all, ss_all) == bytes(r2s.cpu().numpy())
+        except Exception as e:
+            g2["multi_rank_result_ok"] = f"check failed to run: {e}"
+        try:
+            from oracle import ref
+            if ref.available():
+                m = min(n2, 1 << 13)
+                tc = time.perf_counter()
+                want = ref.g2_msm(bytes(p2[:192 * m].cpu().numpy()), bytes(s2[:32 * m].cpu().numpy()), ref.hardware_threads())
+                dtc = time.perf_counter() - tc
+                got = bytes(dv.g2_msm(p2[:192 * m], s2[:32 * m]).cpu().numpy())
+                g2["cpu_baseline"] = {"value": m / dtc, "unit": "points/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                      "sample": f"first {m} terms: per-term PAIR_G2mul + ECP2_add loop (g2_point.hpp:202-236) over {ref.hardware_threads()} host threads",
+                                      "bit_exact_vs_gpu_on_sample": want == got}
+        except Exception as e:
+            g2["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+        line["secondary_g2_msm"] = g2
+        cb = g2.get("cpu_baseline", {})
+        line["roofline"].update({"g2_msm_points_per_s": g2["value"], "g2_msm_n_per_gpu": n2, "g2_msm_ms": ms, "g2_msm_accumulate_ms": acc2,
+                                 "g2_msm_frac_of_mad_peak": g2["accumulate_frac_of_mad_peak"], "g2_msm_tail_ms": sum(st2["phases_ms"][x] for x in ("reduce1", "reduce2", "finish")),
+                                 "g2_msm_multi_rank_result_ok": g2.get("multi_rank_result_ok"),
+                                 "g2_msm_strong_n_total": ns2 * world, "g2_msm_strong_ms": ms_strong, "g2_msm_strong_points_per_s": g2["strong"]["points_per_s"],
+                                 "g2_msm_strong_result_ok": g2["strong"].get("result_ok"),
+                                 "g2_msm_cpu_points_per_s": cb.get("value"), "g2_msm_bit_exact_vs_cpu_sample": cb.get("bit_exact_vs_gpu_on_sample")})
+
     # secondary: the G1 sweep of BASELINE configs[1], n = 2^10 .. 2^24 (rank 0 only, device-resident, same pipeline)
-    if not args.no_secondary and args.sweep_max_log_n >= 10 and rank == 0:
+    def sec_sweep():
+        if args.sweep_max_log_n < 10 or rank != 0:
+            return
         gsw = torch.Generator(device=dev).manual_seed(9000)
         nmax = 1 << args.sweep_max_log_n
         kk = torch.randint(0, 256, (nmax, 32), dtype=torch.uint8, device=dev, generator=gsw)
@@ -389,57 +558,61 @@ def run_ours(args):
             torch.cuda.synchronize()
             ms_s = e0.elapsed_time(e1) / reps
             sweep.append({"log_n": ln, "ms": ms_s, "points_per_s": m / (ms_s * 1e-3), "window_bits": dv.last_msm_stats()["window_bits"]})
+            line["roofline"][f"sweep_2p{ln}_ms"] = ms_s
         dv.sync_status()
         line["secondary_g1_sweep"] = sweep
-        del sw_p, sw_s
+
     # secondary: batched scalar multiplication: g^x from the fixed-base table and P^k, rank 0 only,
     # device-resident; CPU beside it: the reference's multiply (PAIR_G1mul) on a sample over all host threads
-    if not args.no_secondary and args.sweep_max_log_n >= 10 and rank == 0:
+    def sec_scalar_mul():
+        if args.sweep_max_log_n < 10 or rank != 0:
+            return
+        nb = 1 << 18
+        xs_t = torch.from_numpy(rand_scalars(nb, 8100)).reshape(-1).to(dev)
+        ks_t = torch.from_numpy(rand_scalars(nb, 8200)).reshape(-1).to(dev)
+
+        def timed_ms(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                out = fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / reps, out
+
+        ms_fb, pts_t = timed_ms(lambda: dv.g1_fixed_base_mul_batch(xs_t))
+        ms_mul, enc_t = timed_ms(lambda: dv.g1_mul_batch(pts_t, ks_t))
+        ms_fb2, pts2_t = timed_ms(lambda: dv.g2_fixed_base_mul_batch(xs_t[:32 * (nb // 4)]))
+        ms_mul2, _ = timed_ms(lambda: dv.g2_mul_batch(pts2_t, ks_t[:32 * (nb // 4)]))
+        dv.sync_status()
+        sm = {"g1_fixed_base_per_s": nb / (ms_fb * 1e-3), "g1_mul_per_s": nb / (ms_mul * 1e-3),
+              "g2_fixed_base_per_s": (nb // 4) / (ms_fb2 * 1e-3), "g2_mul_per_s": (nb // 4) / (ms_mul2 * 1e-3),
+              "batch": {"g1": nb, "g2": nb // 4}, "unit": "scalar multiplications/s",
+              "ms": {"g1_fixed_base": ms_fb, "g1_mul": ms_mul, "g2_fixed_base": ms_fb2, "g2_mul": ms_mul2}}
         try:
-            nb = 1 << 18
-            xs_t = torch.from_numpy(rand_scalars(nb, 8100)).reshape(-1).to(dev)
-            ks_t = torch.from_numpy(rand_scalars(nb, 8200)).reshape(-1).to(dev)
+            from oracle import ref
+            if ref.available():
+                m = 64 * ref.hardware_threads()
+                pb, kb = bytes(pts_t[:96 * m].cpu().numpy()), bytes(ks_t[:32 * m].cpu().numpy())
+                tc = time.perf_counter()
+                want = ref.g1_mul_batch(pb, kb, ref.hardware_threads())
+                dtc = time.perf_counter() - tc
+                sm["cpu_baseline"] = {"value": m / dtc, "unit": "G1 scalar multiplications/s", "cores": ref.hardware_threads(), "kind": "reference",
+                                      "sample": f"{m} x multiply(point1&, big) -> PAIR_G1mul over {ref.hardware_threads()} host threads",
+                                      "bit_exact_vs_gpu_on_sample": want == bytes(enc_t[:49 * m].cpu().numpy())}
+        except Exception as e:
+            sm["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+        line["secondary_scalar_mul"] = sm
+        line["roofline"].update({"g1_mul_per_s": sm["g1_mul_per_s"], "g1_fixed_base_per_s": sm["g1_fixed_base_per_s"],
+                                 "g2_mul_per_s": sm["g2_mul_per_s"], "g2_fixed_base_per_s": sm["g2_fixed_base_per_s"]})
 
-            def timed_ms(fn, reps=3):
-                fn()
-                torch.cuda.synchronize()
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(reps):
-                    out = fn()
-                a1.record()
-                torch.cuda.synchronize()
-                return a0.elapsed_time(a1) / reps, out
-
-            ms_fb, pts_t = timed_ms(lambda: dv.g1_fixed_base_mul_batch(xs_t))
-            ms_mul, enc_t = timed_ms(lambda: dv.g1_mul_batch(pts_t, ks_t))
-            ms_fb2, pts2_t = timed_ms(lambda: dv.g2_fixed_base_mul_batch(xs_t[:32 * (nb // 4)]))
-            ms_mul2, _ = timed_ms(lambda: dv.g2_mul_batch(pts2_t, ks_t[:32 * (nb // 4)]))
-            dv.sync_status()
-            sm = {"g1_fixed_base_per_s": nb / (ms_fb * 1e-3), "g1_mul_per_s": nb / (ms_mul * 1e-3),
-                  "g2_fixed_base_per_s": (nb // 4) / (ms_fb2 * 1e-3), "g2_mul_per_s": (nb // 4) / (ms_mul2 * 1e-3),
-                  "batch": {"g1": nb, "g2": nb // 4}, "unit": "scalar multiplications/s",
-                  "ms": {"g1_fixed_base": ms_fb, "g1_mul": ms_mul, "g2_fixed_base": ms_fb2, "g2_mul": ms_mul2}}
-            try:
-                from oracle import ref
-                if ref.available():
-                    m = 64 * ref.hardware_threads()
-                    pb, kb = bytes(pts_t[:96 * m].cpu().numpy()), bytes(ks_t[:32 * m].cpu().numpy())
-                    tc = time.perf_counter()
-                    want = ref.g1_mul_batch(pb, kb, ref.hardware_threads())
-                    dtc = time.perf_counter() - tc
-                    sm["cpu_baseline"] = {"value": m / dtc, "unit": "G1 scalar multiplications/s", "cores": ref.hardware_threads(), "kind": "reference",
-                                          "sample": f"{m} x multiply(point1&, big) -> PAIR_G1mul over {ref.hardware_threads()} host threads",
-                                          "bit_exact_vs_gpu_on_sample": want == bytes(enc_t[:49 * m].cpu().numpy())}
-            except Exception as e:
-                sm["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
-            line["secondary_scalar_mul"] = sm
-        except Exception as e:      # a secondary must never cost the headline line
-            line["secondary_scalar_mul"] = {"error": str(e)}
-    # secondary 3: BBS+ batch verification (BASELINE configs[4]): 2^16 signatures x 10 message blocks over all ranks,
+    # secondary: BBS+ batch verification (BASELINE configs[4]): 2^16 signatures x 10 message blocks over all ranks,
     # instances split across ranks with no collective; the timed region is the whole device pipeline of bbs_plus.verify_batch_device
-    if not args.no_secondary and args.bbs_log_b > 0:
-        import numpy as np
+    def sec_bbs():
+        if args.bbs_log_b <= 0:
+            return
         from crypto12381_b200 import bbs_plus
         Bs, nmsg = max(1, (1 << args.bbs_log_b) // world), 10
         R_ORD = bbs_plus.R
@@ -457,78 +630,69 @@ def run_ours(args):
         one[:, :, 31] = 1
         sc_g1 = torch.from_numpy(np.concatenate((one, rs.reshape(Bs, 1, 32), ms), axis=1).reshape(-1)).to(dev)
         sc_g2 = torch.from_numpy(np.concatenate((one, xs.reshape(Bs, 1, 32)), axis=1).reshape(-1)).to(dev)
-        # sign on the GPU: A = (g1 h0^r prod h_j^m_j)^(1/(gamma + x)); the Zp inverse stays on the host as in the reference
+        # sign on the GPU: A = (g1 h0^r prod h_j^m_j)^(1/(gamma + x)); the Zp inverse stays on the host as in the reference.
+        # The first `mref` signatures are made by the REFERENCE's arithmetic instead (oracle/_ref, bbs+.cpp:38-55 at the bridge level)
         inv = b"".join(pow((gamma + int.from_bytes(x.tobytes(), "big")) % R_ORD, -1, R_ORD).to_bytes(32, "big") for x in xs)
         Bp = dv.g1_multi_fixed_base_batch(gens, sc_g1)
         sigA = dv.g1_mul_batch(Bp, torch.frombuffer(bytearray(inv), dtype=torch.uint8).to(dev))      # compressed 49 B
+        ref_made, ref_info = 0, None
+        try:
+            from oracle import ref
+            if ref.available() and rank == 0:
+                mref = min(Bs, 8 * ref.hardware_threads())
+                hb = bytes(gens.cpu().numpy())
+                tc = time.perf_counter()
+                refA = ref.bbs_sign_batch(hb[:96], hb[96:192], hb[192:], gamma.to_bytes(32, "big"), bytes(sc_g1[:32 * 12 * mref].cpu().numpy()),
+                                          nmsg, ref.hardware_threads(), xs=xs[:mref].tobytes())
+                ref_info = {"signatures": mref, "sign_s": time.perf_counter() - tc, "equal_to_gpu_made": refA == bytes(sigA[:49 * mref].cpu().numpy())}
+                sigA[:49 * mref] = torch.frombuffer(bytearray(refA), dtype=torch.uint8).to(dev)
+                ref_made = mref
+        except Exception as e:
+            ref_info = {"error": str(e)}
         v = bbs_plus.verify_batch_device(gens, bases_g2, neg_g2, sigA, sc_g1, sc_g2)
         dv.sync_status()
         all_ok = bool((v == 1).all().item())
         sigA_bad = sigA.clone()
         sigA_bad[49:98] = sigA[0:49]                            # signature 1 gets signature 0's A
         v_bad = bbs_plus.verify_batch_device(gens, bases_g2, neg_g2, sigA_bad, sc_g1, sc_g2)
-        bad_ok = bool(v_bad[1].item() == 0 and (v_bad[2:] == 1).all().item())
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        flush.fill_(1)
-        e0.record()
-        v = bbs_plus.verify_batch_device(gens, bases_g2, neg_g2, sigA, sc_g1, sc_g2)
-        e1.record()
-        barrier()
-        # the same batch through the random-linear-combination check (one verdict per rank's shard; bbs_plus.verify_batch_aggregate)
-        xi = [int.from_bytes(x.tobytes(), "big") for x in xs]
-        rho_i = [int.from_bytes(r16.tobytes(), "big") | 1 for r16 in rngb.integers(0, 256, size=(Bs, 16), dtype=np.uint8)]
-        tb = lambda vals: torch.frombuffer(bytearray(b"".join(v.to_bytes(32, "big") for v in vals)), dtype=torch.uint8).to(dev)
-        rho_t, rhox_t, nrho_t = tb(rho_i), tb([r * x % R_ORD for r, x in zip(rho_i, xi)]), tb([R_ORD - r for r in rho_i])
-        va = bbs_plus.verify_batch_aggregate_device(gens, bases_g2, sigA, sc_g1, rho_t, rhox_t, nrho_t)
-        va_bad = bbs_plus.verify_batch_aggregate_device(gens, bases_g2, sigA_bad, sc_g1, rho_t, rhox_t, nrho_t)
-        dv.sync_status()
-        agg_ok = bool(va.item() == 1 and va_bad.item() == 0)
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        bbs_plus.verify_batch_aggregate_device(gens, bases_g2, sigA, sc_g1, rho_t, rhox_t, nrho_t)
-        a1.record()
-        barrier()
-        agg_ms = a0.elapsed_time(a1)
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            ms_t = float(t.item())
-            line["secondary_bbs_plus_verify"] = {"aggregate_check": {"what": "random-linear-combination batch check (an extension: one verdict per shard): B_i products, two G1 MSMs, one 2-pair pairing check",
-                                                                     "ms_rank0": agg_ms, "signatures_per_s_rank0": Bs / (agg_ms * 1e-3), "valid_accepted_tampered_rejected": agg_ok},"metric": "bbs_plus_verifications_per_s", "value": Bs * world / (ms_t * 1e-3), "unit": "signatures/s",
-                                                 "signatures": Bs * world, "message_blocks": nmsg, "ms": ms_t, "all_valid_accepted": all_ok,
-                                                 "tampered_rejected": bad_ok,
-                                                 "pipeline": "decompress A; w + x g2; g1 + r h0 + sum m_j h_j (window tables over the 12 shared bases); 2-pair pairing check"}
-            try:   # the reference's arithmetic for the same verifications (bbs+.cpp:57-73) from its own bridge functions, all host threads
-                from concurrent.futures import ThreadPoolExecutor
-                from oracle import ref
-                if ref.available():
-                    mS, th = 4 * ref.hardware_threads(), ref.hardware_threads()
-                    hb, h2, hA = bytes(gens.cpu().numpy()), bytes(bases_g2.cpu().numpy()), bytes(dv.g1_decompress_batch(sigA[:49 * mS]).cpu().numpy())
-                    s1, s2 = bytes(sc_g1[:32 * 12 * mS].cpu().numpy()), bytes(sc_g2[:64 * mS].cpu().numpy())
-                    ng = bytes(neg_g2.cpu().numpy())
-                    tc = time.perf_counter()
-                    with ThreadPoolExecutor(th) as ex:     # per signature: the live product loop (double_multiply pairs) and w * g2^x
-                        Bc = list(ex.map(lambda i: ref.g1_msm(hb, s1[384 * i:384 * (i + 1)], 1, 1), range(mS)))
-                        Wc = list(ex.map(lambda i: ref.g2_msm(h2, s2[64 * i:64 * (i + 1)], 1), range(mS)))
-                    dt1 = time.perf_counter() - tc
-                    Ba = bytes(dv.g1_decompress_batch(torch.frombuffer(bytearray(b"".join(Bc)), dtype=torch.uint8).to(dev)).cpu().numpy())
-                    Wa = bytes(dv.g2_decompress_batch(torch.frombuffer(bytearray(b"".join(Wc)), dtype=torch.uint8).to(dev)).cpu().numpy())
-                    p1 = b"".join(hA[96 * i:96 * i + 96] + Ba[96 * i:96 * i + 96] for i in range(mS))
-                    p2 = b"".join(Wa[192 * i:192 * i + 192] + ng for i in range(mS))
-                    tc = time.perf_counter()
-                    gtc = ref.pairing_product_batch(p1, p2, 2, 1, th)
-                    dtc = dt1 + time.perf_counter() - tc
-                    unity = bytes(575) + b"\x01"
-                    line["secondary_bbs_plus_verify"]["cpu_baseline"] = {
-                        "value": mS / dtc, "unit": "signatures/s", "cores": th, "kind": "reference",
-                        "sample": f"{mS} signatures: per signature the live G1 product loop (double_multiply), w * g2^x, pair_double_ate + final exponentiation "
-                                  "through the unmodified bridge (point parsing excluded; the two affine conversions in between are not timed work of the reference)",
-                        "all_accepted": all(gtc[576 * i:576 * i + 576] == unity for i in range(mS))}
-            except Exception as e:
-                line["secondary_bbs_plus_verify"]["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+        bad_ok = bool(v_bad[1].item() == 0 and v_bad[0].item() == 1 and (v_bad[2:] == 1).all().item())
+        ms_t, _ = timed(lambda: bbs_plus.verify_batch_device(gens, bases_g2, neg_g2, sigA, sc_g1, sc_g2), 2)
+        if rank != 0:
+            return
+        bb = {"metric": "bbs_plus_verifications_per_s", "value": Bs * world / (ms_t * 1e-3), "unit": "signatures/s",
+              "signatures": Bs * world, "message_blocks": nmsg, "ms": ms_t, "all_valid_accepted": all_ok, "tampered_rejected": bad_ok,
+              "reference_made_signatures": ref_made, "reference_sign": ref_info,
+              "pipeline": "decompress A; w + x g2; g1 + r h0 + sum m_j h_j (window tables over the 12 shared bases); 2-pair pairing check"}
+        try:   # the reference's own verify (bbs+.cpp:57-73 at the bridge level) on a sample: verdicts must agree, valid and tampered
+            from oracle import ref
+            if ref.available():
+                mS, th = min(Bs, 4 * ref.hardware_threads()), ref.hardware_threads()
+                hb, h2 = bytes(gens.cpu().numpy()), bytes(bases_g2.cpu().numpy())
+                args_ref = (hb[:96], h2[192:], hb[96:192], hb[192:], h2[:192], nmsg)
+                tc = time.perf_counter()
+                vr = ref.bbs_verify_batch(*args_ref, bytes(sigA[:49 * mS].cpu().numpy()), bytes(sc_g1[:32 * 12 * mS].cpu().numpy()),
+                                          bytes(sc_g2[:64 * mS].cpu().numpy()), th)
+                dtc = time.perf_counter() - tc
+                vr_bad = ref.bbs_verify_batch(*args_ref, bytes(sigA_bad[:49 * mS].cpu().numpy()), bytes(sc_g1[:32 * 12 * mS].cpu().numpy()),
+                                              bytes(sc_g2[:64 * mS].cpu().numpy()), th)
+                bb["cpu_baseline"] = {"value": mS / dtc, "unit": "signatures/s", "cores": th, "kind": "reference",
+                                      "sample": f"{mS} signatures through the reference's verify restated on its bridge (parse A, the live double_multiply product loop, "
+                                                "w * g2^x, two pair_ate + final exponentiations, equal)",
+                                      "verdicts_equal_valid": vr == bytes(v[:mS].cpu().numpy()), "verdicts_equal_tampered": vr_bad == bytes(v_bad[:mS].cpu().numpy())}
+        except Exception as e:
+            bb["cpu_baseline"] = {"value": None, "sample": f"unavailable: {e}"}
+        line["secondary_bbs_plus_verify"] = bb
+        cb = bb.get("cpu_baseline", {})
+        line["roofline"].update({"bbs_verifications_per_s": bb["value"], "bbs_signatures": Bs * world, "bbs_ms": ms_t, "bbs_all_valid_accepted": all_ok,
+                                 "bbs_tampered_rejected": bad_ok, "bbs_reference_made_signatures": ref_made,
+                                 "bbs_cpu_verifications_per_s": cb.get("value"), "bbs_verdicts_equal_reference": (cb.get("verdicts_equal_valid") and cb.get("verdicts_equal_tampered")) if cb.get("value") else None})
+
+    if not args.no_secondary:
+        secondary("secondary", sec_pairing)
+        secondary("secondary_g2_msm", sec_g2)
+        secondary("secondary_g1_sweep", sec_sweep)
+        secondary("secondary_scalar_mul", sec_scalar_mul)
+        secondary("secondary_bbs_plus_verify", sec_bbs)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -28,6 +28,8 @@ SIGNATURES = {
     "c12381_set_msm_window": (None, [_i]),
     "c12381_set_msm_batch_affine": (None, [_i]),
     "c12381_g1_msm": (_i, [_p, _p, _sz, _p]),
+    "c12381_g1_msm_partial": (_i, [_p, _p, _sz, _p]),
+    "c12381_g2_msm_partial": (_i, [_p, _p, _sz, _p]),
     "c12381_g1_msm_dev": (_i, [_p, _p, _sz, _p, _p]),
     "c12381_g1_msm_partial_dev": (_i, [_p, _p, _sz, _p, _p]),
     "c12381_g1_sum_dev": (_i, [_p, _sz, _p, _p]),

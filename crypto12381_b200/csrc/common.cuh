@@ -31,7 +31,18 @@ struct Ctx {
     size_t arena_bytes = 0;
     size_t arena_used = 0;
     int arena_depth = 0;   // > 0 while a host entry runs its pipeline: nested arena_begin calls carve from the same reservation
+    // stream ordering of the ONE arena: the stream of the call that carved from it last.  A call arriving on another stream first
+    // waits (on the device, cudaStreamWaitEvent) for everything enqueued on that stream so far - the previous call's kernels still
+    // read the scratch the new call is about to overwrite; before the arena is freed to grow it, that event is waited for on the host.
+    cudaStream_t arena_stream = nullptr;
+    bool arena_stream_valid = false;
+    cudaEvent_t arena_ev = nullptr;
+    int host_depth = 0;    // > 0 inside a host-pointer entry: its kernels report malformed input in a flag word of their own
+    bool pc_configured = false;   // cooperative pairing kernels: dynamic shared memory opt-in done on THIS device
+    int sm_count = 0;
     // pinned staging for small results / flags
+    // d_flags[0]: the `_dev` entries' word, collected by c12381_sync_status; d_flags[HOST_FLAG_WORD]: the host entries' word,
+    // reset and collected inside each call - so a host call can neither wipe nor inherit what an earlier `_dev` call flagged
     int* h_flags = nullptr;
     int* d_flags = nullptr;
     int forced_window = 0;
@@ -43,6 +54,8 @@ struct Ctx {
 };
 
 Ctx& ctx();
+constexpr int HOST_FLAG_WORD = 16;
+inline int* flags_word() { Ctx& c = ctx(); return c.d_flags + (c.host_depth > 0 ? HOST_FLAG_WORD : 0); }
 int set_error(int code, const char* what, cudaError_t e = cudaSuccess);
 
 // Reserve `bytes` of scratch for the CURRENT call.  Call arena_begin(total) once per entry point with an upper
@@ -63,9 +76,12 @@ void* arena_take(size_t bytes);
         if (e__ != cudaSuccess) return c12::set_error(C12381_ECUDA, "kernel launch", e__);  \
     } while (0)
 
+// every entry re-asserts the context's device: the caller (or torch) may have changed the thread's current device
 #define C12_REQUIRE_CTX()                                                                   \
     do {                                                                                    \
         if (c12::ctx().device < 0) return c12::set_error(C12381_ENODEV, "c12381_init was not called or no CUDA device"); \
+        cudaError_t e__ = cudaSetDevice(c12::ctx().device);                                 \
+        if (e__ != cudaSuccess) return c12::set_error(C12381_ECUDA, "cudaSetDevice", e__);  \
     } while (0)
 
 static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }

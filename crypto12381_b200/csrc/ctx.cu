@@ -26,8 +26,20 @@ int arena_begin(size_t total, cudaStream_t s)
         if (c.arena_used + total > c.arena_bytes) return set_error(C12381_ECUDA, "nested scratch reservation too small");
         return C12381_OK;
     }
+    // the previous call carved from the same arena on another stream: order this call's stream behind everything enqueued there
+    bool ordered = !c.arena_stream_valid || c.arena_stream == s;
+    if (!ordered) {
+        if (cudaEventRecord(c.arena_ev, c.arena_stream) == cudaSuccess) {
+            C12_CUDA(cudaStreamWaitEvent(s, c.arena_ev, 0));
+            ordered = true;
+        } else {
+            cudaGetLastError();            // that stream no longer exists: whatever ran on it has been synchronised by its destruction
+            c.arena_stream_valid = false;
+        }
+    }
     if (total > c.arena_bytes) {
         // growing: earlier work may still read the old arena
+        if (c.arena_stream_valid && c.arena_stream != s && ordered) C12_CUDA(cudaEventSynchronize(c.arena_ev));
         C12_CUDA(cudaStreamSynchronize(s));
         if (s != c.stream) C12_CUDA(cudaStreamSynchronize(c.stream));
         if (c.copy_stream) C12_CUDA(cudaStreamSynchronize(c.copy_stream));
@@ -39,6 +51,8 @@ int arena_begin(size_t total, cudaStream_t s)
         c.arena_bytes = want;
     }
     c.arena_used = 0;
+    c.arena_stream = s;
+    c.arena_stream_valid = true;
     return C12381_OK;
 }
 
@@ -171,8 +185,11 @@ int c12381_init(int device)
     C12_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     C12_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c.copy_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    C12_CUDA(cudaEventCreateWithFlags(&c.arena_ev, cudaEventDisableTiming));
+    C12_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
     C12_CUDA(cudaMalloc(&c.d_flags, 64 * sizeof(int)));
+    C12_CUDA(cudaMemset(c.d_flags, 0, 64 * sizeof(int)));
     for (auto& ev : c.ev) C12_CUDA(cudaEventCreate(&ev));
     for (auto& ev : c.pev) C12_CUDA(cudaEventCreate(&ev));
     c.device = device;
@@ -185,7 +202,7 @@ void c12381_shutdown(void)
     Ctx& c = ctx();
     if (c.device < 0) return;
     cudaSetDevice(c.device);
-    cudaStreamSynchronize(c.stream);
+    cudaDeviceSynchronize();       // `_dev` calls may still run on the caller's streams
     if (c.arena) cudaFree(c.arena);
     for (auto& t : c.fb_table)
         if (t) cudaFree(t);
@@ -197,6 +214,7 @@ void c12381_shutdown(void)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : c.copy_ev)
         if (ev) cudaEventDestroy(ev);
+    if (c.arena_ev) cudaEventDestroy(c.arena_ev);
     if (c.copy_stream) {
         cudaStreamSynchronize(c.copy_stream);
         cudaStreamDestroy(c.copy_stream);

@@ -34,7 +34,7 @@ static int hash_run(const uint8_t* d_msgs, size_t len, size_t B, int mode, uint8
     if (mode < 2)
         k_sha3_512<<<cdiv(B, 128), 128, 0, s>>>(d_msgs, len, (uint32_t)B, mode, d_out);
     else
-        k_hash_to_g1<<<cdiv(B, 128), 128, 0, s>>>(d_msgs, len, (uint32_t)B, mode, d_out, ctx().d_flags);
+        k_hash_to_g1<<<cdiv(B, 128), 128, 0, s>>>(d_msgs, len, (uint32_t)B, mode, d_out, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }

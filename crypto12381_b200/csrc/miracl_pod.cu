@@ -63,25 +63,25 @@ namespace {
 
 template <class F> int pods_to_wire(const uint8_t* d_pods, uint32_t n, uint8_t* d_wire, cudaStream_t s)
 {
-    k_pod_points_to_wire<F><<<cdiv(n, 128), 128, 0, s>>>(d_pods, n, d_wire, ctx().d_flags);
+    k_pod_points_to_wire<F><<<cdiv(n, 128), 128, 0, s>>>(d_pods, n, d_wire, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
 template <class F> int wire_to_pods(const uint8_t* d_wire, uint32_t n, uint8_t* d_pods, cudaStream_t s)
 {
-    k_wire_to_pod_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_wire, n, d_pods, ctx().d_flags);
+    k_wire_to_pod_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_wire, n, d_pods, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
 int bigs_to_scalars(const uint8_t* d_bigs, uint32_t n, uint8_t* d_out, cudaStream_t s)
 {
-    k_pod_bigs_to_scalars<<<cdiv(n, 128), 128, 0, s>>>(d_bigs, n, d_out, ctx().d_flags);
+    k_pod_bigs_to_scalars<<<cdiv(n, 128), 128, 0, s>>>(d_bigs, n, d_out, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
 int fp12_to_wire(const uint8_t* d_pods, uint32_t n, uint8_t* d_wire, cudaStream_t s)
 {
-    k_pod_fp12_to_wire<<<cdiv((size_t)n * 12, 64), 64, 0, s>>>(d_pods, n, d_wire, ctx().d_flags);
+    k_pod_fp12_to_wire<<<cdiv((size_t)n * 12, 64), 64, 0, s>>>(d_pods, n, d_wire, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }

@@ -114,12 +114,53 @@ template <class F> C12_HD bool wire_to_pod_point(const uint8_t* wire, uint8_t* p
     return ok;
 }
 
-// big -> 32-byte big-endian scalar; false if the value does not fit 256 bits or is negative
+// w (< 2^416) mod r by shift-and-subtract; only values >= r pay for it (the DSL hands over scalars in [0, r))
+C12_HD void words_mod_r(uint32_t (&w)[13])
+{
+    const uint32_t r[8] = C12_R_LIMBS;
+    bool small = (w[8] | w[9] | w[10] | w[11] | w[12]) == 0;
+    if (small) {
+        bool lt = false, decided = false;
+        for (int i = 7; i >= 0; --i)
+            if (!decided && w[i] != r[i]) {
+                lt = w[i] < r[i];
+                decided = true;
+            }
+        if (lt) return;
+    }
+#pragma unroll 1
+    for (int sh = 160; sh >= 0; --sh) {            // r < 2^255: r << 160 still fits the 13 words
+        uint32_t t[13];
+        const int ws = sh >> 5, bs = sh & 31;
+        for (int i = 0; i < 13; ++i) {
+            const int j = i - ws;
+            uint32_t lo = (j >= 0 && j < 8) ? r[j] : 0u, below = (j - 1 >= 0 && j - 1 < 8) ? r[j - 1] : 0u;
+            t[i] = bs ? ((lo << bs) | (below >> (32 - bs))) : lo;
+        }
+        bool ge = true;
+        for (int i = 12; i >= 0; --i)
+            if (w[i] != t[i]) {
+                ge = w[i] > t[i];
+                break;
+            }
+        if (ge) {
+            uint64_t borrow = 0;
+            for (int i = 0; i < 13; ++i) {
+                uint64_t d = (uint64_t)w[i] - t[i] - borrow;
+                w[i] = (uint32_t)d;
+                borrow = (d >> 32) & 1u;
+            }
+        }
+    }
+}
+
+// big -> 32-byte big-endian scalar REDUCED mod r, as PAIR_G1mul / PAIR_G2mul reduce theirs (pair_BLS12381.cpp:878-881,929-932;
+// for ECP_muln / ECP_mul2, which do not, the group element is the same); false only for a negative value
 C12_HD bool pod_big_to_scalar(const uint8_t* big, uint8_t* out32)
 {
     uint32_t w[13];
     bool ok = big_to_words(reinterpret_cast<const long long*>(big), w);
-    if (w[8] | w[9] | w[10] | w[11] | w[12]) ok = false;
+    words_mod_r(w);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         uint8_t* q = out32 + 28 - 4 * j;

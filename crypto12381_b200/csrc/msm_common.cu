@@ -198,26 +198,32 @@ int sort_pairs_segmented(uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, 
     return C12381_OK;
 }
 
+// host entries: the host flag word is cleared on the way in and read on the way out (HostScope in msm_impl.cuh keeps
+// Ctx::host_depth > 0 in between, which is what routes the kernels' reports to that word)
 int flags_reset(cudaStream_t s)
 {
-    C12_CUDA(cudaMemsetAsync(ctx().d_flags, 0, sizeof(int), s));
+    C12_CUDA(cudaMemsetAsync(ctx().d_flags + HOST_FLAG_WORD, 0, sizeof(int), s));
     return C12381_OK;
 }
 
-int flags_collect(cudaStream_t s)
+static int flags_collect_word(int word, cudaStream_t s)
 {
     Ctx& c = ctx();
-    C12_CUDA(cudaMemcpyAsync(c.h_flags, c.d_flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    C12_CUDA(cudaMemcpyAsync(c.h_flags + word, c.d_flags + word, sizeof(int), cudaMemcpyDeviceToHost, s));
     C12_CUDA(cudaStreamSynchronize(s));
     C12_CUDA(cudaGetLastError());
-    int f = c.h_flags[0];
+    int f = c.h_flags[word];
     if (f) {
-        cudaMemsetAsync(c.d_flags, 0, sizeof(int), s);
-        return set_error(C12381_EINPUT, (f & FLAG_BAD_POINT) ? "malformed input: non-canonical coordinate or point off the curve"
-                                                              : "malformed input: scalar >= group order");
+        cudaMemsetAsync(c.d_flags + word, 0, sizeof(int), s);
+        const char* what = (f & FLAG_BAD_POINT) ? "malformed input: non-canonical coordinate or point off the curve"
+                           : (f & FLAG_BAD_SCALAR) ? "malformed input: scalar >= group order"
+                                                   : "malformed input: reference POD outside its documented range";
+        return set_error(C12381_EINPUT, what);
     }
     return C12381_OK;
 }
+
+int flags_collect(cudaStream_t s) { return flags_collect_word(HOST_FLAG_WORD, s); }
 
 } // namespace c12
 
@@ -226,5 +232,5 @@ using namespace c12;
 extern "C" int c12381_sync_status(void* stream)
 {
     C12_REQUIRE_CTX();
-    return flags_collect((cudaStream_t)stream);
+    return flags_collect_word(0, (cudaStream_t)stream);
 }

@@ -4,6 +4,7 @@ using namespace c12;
 
 extern "C" {
 int c12381_g1_msm(const uint8_t* points96, const uint8_t* scalars32, size_t n, uint8_t out49[49]) { return entry_msm_host<Fp>(points96, scalars32, n, out49); }
+int c12381_g1_msm_partial(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o) { return entry_msm_host<Fp>(p, s, n, o, OUT_AFFINE); }
 int c12381_g1_msm_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp>(p, s, n, o, OUT_COMPRESSED, st); }
 int c12381_g1_msm_partial_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp>(p, s, n, o, OUT_AFFINE, st); }
 int c12381_g1_sum_dev(const uint8_t* p, size_t n, uint8_t* o, void* st) { return entry_sum_dev<Fp>(p, n, o, st); }

@@ -8,6 +8,7 @@ using namespace c12;
 
 extern "C" {
 int c12381_g2_msm(const uint8_t* points192, const uint8_t* scalars32, size_t n, uint8_t out97[97]) { return entry_msm_host<Fp2>(points192, scalars32, n, out97); }
+int c12381_g2_msm_partial(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o) { return entry_msm_host<Fp2>(p, s, n, o, OUT_AFFINE); }
 int c12381_g2_msm_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp2>(p, s, n, o, OUT_COMPRESSED, st); }
 int c12381_g2_msm_partial_dev(const uint8_t* p, const uint8_t* s, size_t n, uint8_t* o, void* st) { return entry_msm_dev<Fp2>(p, s, n, o, OUT_AFFINE, st); }
 int c12381_g2_sum_dev(const uint8_t* p, size_t n, uint8_t* o, void* st) { return entry_sum_dev<Fp2>(p, n, o, st); }

@@ -683,7 +683,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
     C12_CUDA(cudaEventRecord(c.pev[0], s));
-    rc = launch_recode(pl, d_scalars, keys, vals, c.d_flags, s);
+    rc = launch_recode(pl, d_scalars, keys, vals, flags_word(), s);
     if (rc) return rc;
     C12_CUDA(cudaEventRecord(c.pev[1], s));
     rc = sort_pairs_segmented(keys, vals, keys2, vals2, pl.n, pl.windows, pl.c, hist, tiles, s);
@@ -699,7 +699,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     if (rc) return rc;
     if (points_ready) C12_CUDA(cudaStreamWaitEvent(s, points_ready, 0));
     C12_CUDA(cudaEventRecord(c.pev[3], s));
-    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.parts, pts, c.d_flags);
+    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.parts, pts, flags_word());
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
@@ -746,7 +746,7 @@ template <class F> int sum_run(const uint8_t* d_points, size_t n, uint8_t* d_out
 {
     Ctx& c = ctx();
     if (n > 0xffffffffull) return set_error(C12381_EARG, "sum: too many points");
-    k_sum_points<F><<<1, 256, 0, s>>>(d_points, (uint32_t)n, d_out, out_mode, c.d_flags);
+    k_sum_points<F><<<1, 256, 0, s>>>(d_points, (uint32_t)n, d_out, out_mode, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -757,7 +757,7 @@ int scalar_mul_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n, 
     Ctx& c = ctx();
     if (n == 0) return C12381_OK;
     if (n > 0x7fffffffull) return set_error(C12381_EARG, "mul_batch: too many terms");
-    k_scalar_mul<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, d_scalars, (uint32_t)n, d_out, out_mode, c.d_flags);
+    k_scalar_mul<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, d_scalars, (uint32_t)n, d_out, out_mode, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -773,16 +773,28 @@ template <class F> int fixed_base_run(const uint8_t* d_scalars, size_t n, uint8_
     if (n == 0) return C12381_OK;
     if (n > 0x7fffffffull) return set_error(C12381_EARG, "fixed_base: too many terms");
     Affine<F>*& table = fixed_base_table_slot<F>();
-    if (!table) {   // first use on this context: build the window table once
-        C12_CUDA(cudaMalloc(&table, sizeof(Affine<F>) * FB_WINDOWS * FB_HALF + sizeof(Proj<F>) * FB_WINDOWS));
-        Proj<F>* wbase = reinterpret_cast<Proj<F>*>(table + FB_WINDOWS * FB_HALF);
-        k_fixed_base_windows<F><<<1, 32, 0, s>>>(nullptr, 1, wbase, c.d_flags);
-        C12_LAUNCHED();
-        k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(1, wbase, table);
-        C12_LAUNCHED();
-        C12_CUDA(cudaStreamSynchronize(s));   // later calls may come on other streams
+    if (!table) {   // first use on this context: build the window table once; published only when the build has succeeded
+        Affine<F>* fresh = nullptr;
+        C12_CUDA(cudaMalloc(&fresh, sizeof(Affine<F>) * FB_WINDOWS * FB_HALF + sizeof(Proj<F>) * FB_WINDOWS));
+        Proj<F>* wbase = reinterpret_cast<Proj<F>*>(fresh + FB_WINDOWS * FB_HALF);
+        k_fixed_base_windows<F><<<1, 32, 0, s>>>(nullptr, 1, wbase, flags_word());
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) {
+            ctx().launches++;
+            k_fixed_base_table<F><<<cdiv(FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>(1, wbase, fresh);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) {
+            ctx().launches++;
+            e = cudaStreamSynchronize(s);   // later calls may come on other streams
+        }
+        if (e != cudaSuccess) {
+            cudaFree(fresh);
+            return set_error(C12381_ECUDA, "fixed-base table build", e);
+        }
+        table = fresh;
     }
-    k_fixed_base<F><<<cdiv(n, 128), 128, 0, s>>>(d_scalars, (uint32_t)n, 1, table, d_out, c.d_flags);
+    k_fixed_base<F><<<cdiv(n, 128), 128, 0, s>>>(d_scalars, (uint32_t)n, 1, table, d_out, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -802,11 +814,11 @@ template <class F> int multi_fixed_base_run(const uint8_t* d_bases, size_t m, co
     Affine<F>* table = (Affine<F>*)arena_take(sizeof(Affine<F>) * m * FB_WINDOWS * FB_HALF);
     Proj<F>* wbase = (Proj<F>*)arena_take(sizeof(Proj<F>) * m * FB_WINDOWS);
     if (!wbase) return set_error(C12381_ECUDA, "multi_fixed_base: scratch arena bound too small");
-    k_fixed_base_windows<F><<<(unsigned)m, 32, 0, s>>>(d_bases, (uint32_t)m, wbase, c.d_flags);
+    k_fixed_base_windows<F><<<(unsigned)m, 32, 0, s>>>(d_bases, (uint32_t)m, wbase, flags_word());
     C12_LAUNCHED();
     k_fixed_base_table<F><<<cdiv(m * FB_WINDOWS * FB_HALF, 128), 128, 0, s>>>((uint32_t)m, wbase, table);
     C12_LAUNCHED();
-    k_fixed_base<F><<<cdiv(B, 128), 128, 0, s>>>(d_scalars, (uint32_t)B, (uint32_t)m, table, d_out, c.d_flags);
+    k_fixed_base<F><<<cdiv(B, 128), 128, 0, s>>>(d_scalars, (uint32_t)B, (uint32_t)m, table, d_out, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -827,7 +839,7 @@ template <class F> int subgroup_run(const uint8_t* d_in, size_t n, uint8_t* d_ou
     Ctx& c = ctx();
     if (n == 0) return C12381_OK;
     if (n > 0x7fffffffull) return set_error(C12381_EARG, "subgroup_check: too many points");
-    k_subgroup_check<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, c.d_flags);
+    k_subgroup_check<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -838,9 +850,9 @@ template <class F> int convert_run(const uint8_t* d_in, size_t n, uint8_t* d_out
     if (n == 0) return C12381_OK;
     if (n > 0x7fffffffull) return set_error(C12381_EARG, "convert: too many points");
     if (decompress)
-        k_decompress<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, c.d_flags);
+        k_decompress<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, flags_word());
     else
-        k_compress<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, c.d_flags);
+        k_compress<F><<<cdiv(n, 128), 128, 0, s>>>(d_in, (uint32_t)n, d_out, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -851,10 +863,16 @@ int flags_collect(cudaStream_t s);  // synchronises `s`; returns C12381_EINPUT i
 
 // Host-pointer entry: one arena reservation covers staging + pipeline scratch; copies ride the context stream.
 // run(d_in[], d_out, stream) enqueues the device pipeline.
+struct HostScope {      // a host-pointer entry is running: its kernels flag malformed input in the host word (common.cuh)
+    HostScope() { ctx().host_depth++; }
+    ~HostScope() { ctx().host_depth--; }
+};
+
 template <class Fn>
 int with_staged(const void* const* host_in, const size_t* in_bytes, int n_in, void* host_out, size_t out_bytes, size_t scratch, Fn&& run)
 {
     Ctx& c = ctx();
+    HostScope scope;
     cudaStream_t s = c.stream;
     size_t total = scratch + align_up(out_bytes) + 4096;
     for (int i = 0; i < n_in; ++i) total += align_up(in_bytes[i]);
@@ -898,10 +916,12 @@ template <class F> int entry_msm_dev(const uint8_t* d_points, const uint8_t* d_s
     return msm_run<F>(d_points, d_scalars, n, d_out, out_mode, s);
 }
 
-template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out)
+template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scalars, size_t n, uint8_t* out, int out_mode = OUT_COMPRESSED)
 {
     C12_REQUIRE_CTX();
     if (!out || (n && (!points || !scalars))) return set_error(C12381_EARG, "msm: null pointer");
+    HostScope scope;
+    const size_t out_bytes = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
     // scalars go up on the context stream (the first stages need only them); the points - three quarters of the bytes -
     // follow on the copy stream and are awaited right before k_parse_points
     Ctx& c = ctx();
@@ -911,7 +931,7 @@ template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scal
     if (rc) return rc;
     uint8_t* d_pts = (uint8_t*)arena_take(pb ? pb : 4);
     uint8_t* d_sc = (uint8_t*)arena_take(sb ? sb : 4);
-    uint8_t* d_out = (uint8_t*)arena_take(Wire<F>::COMPRESSED);
+    uint8_t* d_out = (uint8_t*)arena_take(out_bytes);
     rc = flags_reset(s);
     if (rc) return rc;
     cudaEvent_t ready = nullptr;
@@ -923,13 +943,13 @@ template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scal
         C12_CUDA(cudaEventRecord(c.copy_ev[1], c.copy_stream));
         ready = c.copy_ev[1];
     }
-    rc = msm_run<F>(d_pts, d_sc, n, d_out, OUT_COMPRESSED, s, ready);
+    rc = msm_run<F>(d_pts, d_sc, n, d_out, out_mode, s, ready);
     if (rc) {
         cudaStreamSynchronize(c.copy_stream);
         cudaStreamSynchronize(s);
         return rc;
     }
-    C12_CUDA(cudaMemcpyAsync(out, d_out, Wire<F>::COMPRESSED, cudaMemcpyDeviceToHost, s));
+    C12_CUDA(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
     return flags_collect(s);
 }
 

@@ -260,8 +260,7 @@ __global__ void __launch_bounds__(PC_THREADS, C12_PAIR_BLOCKS) k_gt_pow_coop(con
 // >= 76 %, the cooperative kernels otherwise.  C12381_PAIRING=scalar|coop or c12381_set_pairing_kernel force one of them.
 static bool scalar_fills_its_waves(size_t B)
 {
-    static int sms = 0;
-    if (!sms && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx().device) != cudaSuccess) sms = 148;
+    const int sms = ctx().sm_count > 0 ? ctx().sm_count : 148;
     const size_t wave = (size_t)sms * 256;
     const size_t waves = (B + wave - 1) / wave;
     return B >= 16384 && (double)B >= 0.76 * (double)(waves * wave);
@@ -282,7 +281,7 @@ static bool use_scalar_kernels(size_t B)
 
 static int pc_configure()
 {
-    static bool done = false;
+    bool& done = ctx().pc_configured;      // per context: the opt-in is per device and c12381_init may rebind
     if (done) return C12381_OK;
     C12_CUDA(cudaFuncSetAttribute(k_pairing_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
     C12_CUDA(cudaFuncSetAttribute(k_final_exp_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PC_SMEM));
@@ -302,7 +301,7 @@ static int pairing_run(const uint8_t* d_g1, const uint8_t* d_g2, size_t B, int k
     if (B == 0) return C12381_OK;
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "pairing: too many instances");
     if (use_scalar_kernels(B)) {
-        k_pairing<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(d_g1, d_g2, (uint32_t)B, (uint32_t)k, mode, d_out, ctx().d_flags);
+        k_pairing<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(d_g1, d_g2, (uint32_t)B, (uint32_t)k, mode, d_out, flags_word());
         C12_LAUNCHED();
         return C12381_OK;
     }
@@ -311,7 +310,7 @@ static int pairing_run(const uint8_t* d_g1, const uint8_t* d_g2, size_t B, int k
     pc::PairIn* pin = (pc::PairIn*)arena_take(B * (size_t)k * sizeof(pc::PairIn));
     Fp2* g = (Fp2*)arena_take(B * 6 * sizeof(Fp2));
     if (!g) return set_error(C12381_ECUDA, "pairing: scratch arena bound too small");
-    k_pairing_coop<<<cdiv(B, PC_INST), PC_THREADS, PC_SMEM, s>>>(d_g1, d_g2, (uint32_t)B, (uint32_t)k, mode, d_out, pin, g, ctx().d_flags);
+    k_pairing_coop<<<cdiv(B, PC_INST), PC_THREADS, PC_SMEM, s>>>(d_g1, d_g2, (uint32_t)B, (uint32_t)k, mode, d_out, pin, g, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -376,18 +375,18 @@ static int gt_pow_run(const uint8_t* a, const uint8_t* sc, size_t B, uint8_t* d_
     if (B == 0) return C12381_OK;
     if (B > 0x7fffffffull) return set_error(C12381_EARG, "gt_pow: too many instances");
     if (gs) {
-        k_gt_pow_gs<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, sc, (uint32_t)B, d_out, ctx().d_flags);
+        k_gt_pow_gs<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, sc, (uint32_t)B, d_out, flags_word());
         C12_LAUNCHED();
         return C12381_OK;
     }
     if (use_scalar_kernels(B)) {
-        k_gt_pow<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, sc, (uint32_t)B, d_out, ctx().d_flags);
+        k_gt_pow<<<cdiv(B, PAIR_THREADS), PAIR_THREADS, 0, s>>>(a, sc, (uint32_t)B, d_out, flags_word());
         C12_LAUNCHED();
         return C12381_OK;
     }
     int rc = pc_configure();
     if (rc) return rc;
-    k_gt_pow_coop<<<cdiv(B, PC_INST), PC_THREADS, PC_SMEM, s>>>(a, sc, (uint32_t)B, d_out, ctx().d_flags);
+    k_gt_pow_coop<<<cdiv(B, PC_INST), PC_THREADS, PC_SMEM, s>>>(a, sc, (uint32_t)B, d_out, flags_word());
     C12_LAUNCHED();
     return C12381_OK;
 }

@@ -28,6 +28,29 @@ def _new(n: int, like: torch.Tensor) -> torch.Tensor:
     return torch.empty(max(n, 1), dtype=torch.uint8, device=like.device)[:n]
 
 
+def _records(t: torch.Tensor, record: int, what: str, n: int | None = None) -> int:
+    """`t` is a contiguous CUDA uint8 tensor holding a whole number of `record`-byte items (exactly n of them when n is given);
+    returns the count.  Every wrapper sizes its raw pointers through this: a mismatch is a ValueError here, never an
+    out-of-bounds access on the device."""
+    _chk(t, what)
+    if record <= 0 or t.numel() % record != 0:
+        raise ValueError(f"{what}: {t.numel()} bytes is not a whole number of {record}-byte records")
+    got = t.numel() // record
+    if n is not None and got != n:
+        raise ValueError(f"{what}: {got} records of {record} bytes, expected {n}")
+    return got
+
+
+def _out(out, nbytes: int, like: torch.Tensor) -> torch.Tensor:
+    """the caller's output buffer checked for dtype / device / contiguity / size, or a fresh one"""
+    if out is None:
+        return _new(nbytes, like)
+    _chk(out, "out")
+    if out.device != like.device or out.numel() != nbytes:
+        raise ValueError(f"out: need {nbytes} bytes on {like.device}, got {out.numel()} on {out.device}")
+    return out
+
+
 def sync_status() -> None:
     ensure_init()
     check(lib().c12381_sync_status(_stream()))
@@ -35,12 +58,9 @@ def sync_status() -> None:
 
 def _msm(fn_name: str, point_bytes: int, out_bytes: int, points: torch.Tensor, scalars: torch.Tensor, out=None):
     ensure_init()
-    _chk(points, "points"), _chk(scalars, "scalars")
-    n = scalars.numel() // SCALAR
-    if scalars.numel() != n * SCALAR or points.numel() != n * point_bytes:
-        raise ValueError("points / scalars size mismatch")
-    if out is None:
-        out = _new(out_bytes, points)
+    n = _records(scalars, SCALAR, "scalars")
+    _records(points, point_bytes, "points", n)
+    out = _out(out, out_bytes, points)
     check(getattr(lib(), fn_name)(points.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
@@ -66,72 +86,61 @@ def g2_msm_partial(points, scalars, out=None):
 def g1_sum(points, out=None):
     """Σ points[i] (merging all-gathered partials) -> 49-byte compressed point."""
     ensure_init()
-    _chk(points, "points")
-    n = points.numel() // G1_AFFINE
-    if out is None:
-        out = _new(G1_COMPRESSED, points)
+    n = _records(points, G1_AFFINE, "points")
+    out = _out(out, G1_COMPRESSED, points)
     check(lib().c12381_g1_sum_dev(points.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def g2_sum(points, out=None):
     ensure_init()
-    _chk(points, "points")
-    n = points.numel() // G2_AFFINE
-    if out is None:
-        out = _new(G2_COMPRESSED, points)
+    n = _records(points, G2_AFFINE, "points")
+    out = _out(out, G2_COMPRESSED, points)
     check(lib().c12381_g2_sum_dev(points.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def g1_mul_batch(points, scalars, out=None):
     ensure_init()
-    n = _chk(scalars, "scalars").numel() // SCALAR
-    _chk(points, "points")
-    if out is None:
-        out = _new(n * G1_COMPRESSED, points)
+    n = _records(scalars, SCALAR, "scalars")
+    _records(points, G1_AFFINE, "points", n)
+    out = _out(out, n * G1_COMPRESSED, points)
     check(lib().c12381_g1_mul_batch_dev(points.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def g2_mul_batch(points, scalars, out=None):
     ensure_init()
-    n = _chk(scalars, "scalars").numel() // SCALAR
-    _chk(points, "points")
-    if out is None:
-        out = _new(n * G2_COMPRESSED, points)
+    n = _records(scalars, SCALAR, "scalars")
+    _records(points, G2_AFFINE, "points", n)
+    out = _out(out, n * G2_COMPRESSED, points)
     check(lib().c12381_g2_mul_batch_dev(points.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def g1_fixed_base_mul_batch(scalars, out=None):
     ensure_init()
-    n = _chk(scalars, "scalars").numel() // SCALAR
-    if out is None:
-        out = _new(n * G1_AFFINE, scalars)
+    n = _records(scalars, SCALAR, "scalars")
+    out = _out(out, n * G1_AFFINE, scalars)
     check(lib().c12381_g1_fixed_base_mul_batch_dev(scalars.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def g2_fixed_base_mul_batch(scalars, out=None):
     ensure_init()
-    n = _chk(scalars, "scalars").numel() // SCALAR
-    if out is None:
-        out = _new(n * G2_AFFINE, scalars)
+    n = _records(scalars, SCALAR, "scalars")
+    out = _out(out, n * G2_AFFINE, scalars)
     check(lib().c12381_g2_fixed_base_mul_batch_dev(scalars.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def _pairing(fn_name: str, g1s, g2s, k: int, out_per_instance: int, out=None):
     ensure_init()
-    _chk(g1s, "g1s"), _chk(g2s, "g2s")
     if not 1 <= k <= _lib.MAX_PAIRS:
         raise ValueError("k out of range")
-    b = g1s.numel() // (G1_AFFINE * k)
-    if g1s.numel() != b * G1_AFFINE * k or g2s.numel() != b * G2_AFFINE * k:
-        raise ValueError("g1s / g2s size mismatch")
-    if out is None:
-        out = _new(b * out_per_instance, g1s)
+    b = _records(g1s, G1_AFFINE * k, "g1s")
+    _records(g2s, G2_AFFINE * k, "g2s", b)
+    out = _out(out, b * out_per_instance, g1s)
     check(getattr(lib(), fn_name)(g1s.data_ptr(), g2s.data_ptr(), b, k, out.data_ptr(), _stream()))
     return out
 
@@ -150,29 +159,26 @@ def pairing_check_batch(g1s, g2s, k, out=None):
 
 def final_exp_batch(values, out=None):
     ensure_init()
-    b = _chk(values, "values").numel() // GT_BYTES
-    if out is None:
-        out = _new(b * GT_BYTES, values)
+    b = _records(values, GT_BYTES, "values")
+    out = _out(out, b * GT_BYTES, values)
     check(lib().c12381_final_exp_batch_dev(values.data_ptr(), b, out.data_ptr(), _stream()))
     return out
 
 
 def gt_mul_batch(a, b, out=None):
     ensure_init()
-    n = _chk(a, "a").numel() // GT_BYTES
-    _chk(b, "b")
-    if out is None:
-        out = _new(n * GT_BYTES, a)
+    n = _records(a, GT_BYTES, "a")
+    _records(b, GT_BYTES, "b", n)
+    out = _out(out, n * GT_BYTES, a)
     check(lib().c12381_gt_mul_batch_dev(a.data_ptr(), b.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def gt_pow_batch(a, scalars, out=None):
     ensure_init()
-    n = _chk(a, "a").numel() // GT_BYTES
-    _chk(scalars, "scalars")
-    if out is None:
-        out = _new(n * GT_BYTES, a)
+    n = _records(a, GT_BYTES, "a")
+    _records(scalars, SCALAR, "scalars", n)
+    out = _out(out, n * GT_BYTES, a)
     check(lib().c12381_gt_pow_batch_dev(a.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
@@ -180,23 +186,20 @@ def gt_pow_batch(a, scalars, out=None):
 def gt_pow_gs_batch(a, scalars, out=None):
     """a[b]^scalars[b] for a in GT through the Galbraith-Scott split (c12381_gt_pow_gs_batch_dev)."""
     ensure_init()
-    n = _chk(a, "a").numel() // GT_BYTES
-    _chk(scalars, "scalars")
-    if out is None:
-        out = _new(n * GT_BYTES, a)
+    n = _records(a, GT_BYTES, "a")
+    _records(scalars, SCALAR, "scalars", n)
+    out = _out(out, n * GT_BYTES, a)
     check(lib().c12381_gt_pow_gs_batch_dev(a.data_ptr(), scalars.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
 
 def _multi_fixed(fn_name, point_bytes, bases, scalars, out=None):
     ensure_init()
-    _chk(bases, "bases"), _chk(scalars, "scalars")
-    m = bases.numel() // point_bytes
-    B = scalars.numel() // (SCALAR * m) if m else 0
-    if bases.numel() != m * point_bytes or scalars.numel() != B * m * SCALAR:
-        raise ValueError("bases / scalars size mismatch")
-    if out is None:
-        out = _new(B * point_bytes, scalars)
+    m = _records(bases, point_bytes, "bases")
+    if m == 0:
+        raise ValueError("bases: at least one base")
+    B = _records(scalars, SCALAR * m, "scalars")
+    out = _out(out, B * point_bytes, scalars)
     check(getattr(lib(), fn_name)(bases.data_ptr(), m, scalars.data_ptr(), B, out.data_ptr(), _stream()))
     return out
 
@@ -212,11 +215,8 @@ def g2_multi_fixed_base_batch(bases, scalars, out=None):
 
 def _convert(fn_name, in_bytes, out_bytes, data, out=None):
     ensure_init()
-    n = _chk(data, "data").numel() // in_bytes
-    if data.numel() != n * in_bytes:
-        raise ValueError("size mismatch")
-    if out is None:
-        out = _new(n * out_bytes, data)
+    n = _records(data, in_bytes, "data")
+    out = _out(out, n * out_bytes, data)
     check(getattr(lib(), fn_name)(data.data_ptr(), n, out.data_ptr(), _stream()))
     return out
 
@@ -239,9 +239,10 @@ def g2_compress_batch(data, out=None):
 
 def _hash(fn_name, out_bytes, msgs, msg_len, out=None):
     ensure_init()
-    n = _chk(msgs, "msgs").numel() // msg_len if msg_len else 0
-    if out is None:
-        out = _new(n * out_bytes, msgs)
+    if msg_len <= 0:
+        raise ValueError("msg_len must be positive")
+    n = _records(msgs, msg_len, "msgs")
+    out = _out(out, n * out_bytes, msgs)
     check(getattr(lib(), fn_name)(msgs.data_ptr(), msg_len, n, out.data_ptr(), _stream()))
     return out
 

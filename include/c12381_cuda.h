@@ -20,9 +20,11 @@
  *     Montgomery residue with R = 2^406; point1 192 B, point2 384 B, fp12 776 B) so the forwarding
  *     translation unit can pass its arguments through unchanged.
  *   - inputs are expected in the r-torsion subgroups (as produced by the reference), scalars reduced mod r.
- *   - one context per process (one process per GPU), not re-entrant: every entry carves its scratch from the context's
- *     single arena, so the "_dev" calls of a process must all be enqueued on ONE stream (or be separated by a
- *     synchronisation of the previous call's stream); the host entries use the context's own stream and block.
+ *   - one context per process (one process per GPU), one host thread at a time.  Every entry carves its scratch from the
+ *     context's single arena; a call that arrives on a different stream than the previous one is ordered behind it on the
+ *     device (cudaStreamWaitEvent on everything enqueued on the previous call's stream), so "_dev" calls on several
+ *     streams and the host entries (the context's own stream, blocking) may be mixed freely - they serialise, they do not
+ *     corrupt each other.  Malformed-input reports of the "_dev" entries and of the host entries use separate flag words.
  */
 #ifndef C12381_CUDA_H
 #define C12381_CUDA_H
@@ -68,11 +70,12 @@ C12381_API void c12381_set_msm_batch_affine(int rounds);
 /* ---- multi-scalar multiplication ------------------------------------------------------------------------- */
 /* out = sum_i scalars[i] * points[i] over G1.
  * Replaces sum_of_products(point1&, int, point1*, const big*) -> ECP_muln
- * (miracl_core_interface.hpp:143; src/miracl_core_interface.cpp:134-137) and the live DSL MSM loop
+ * (miracl_core_interface.hpp:102; src/miracl_core_interface.cpp:134-137) and the live DSL MSM loop
  * product(type_identity<G1Pow>, range) of double_multiply calls (g1_point.hpp:371-404). */
 C12381_API int c12381_g1_msm(const uint8_t* points96, const uint8_t* scalars32, size_t n, uint8_t out49[49]);
 C12381_API int c12381_g1_msm_dev(const uint8_t* d_points96, const uint8_t* d_scalars32, size_t n, uint8_t* d_out49, void* stream);
-/* same sum, result as AFFINE 96 B (the per-rank partial of a sharded MSM) */
+/* same sum, result as AFFINE 96 B (the per-rank partial of a sharded MSM); host-pointer and device-pointer forms */
+C12381_API int c12381_g1_msm_partial(const uint8_t* points96, const uint8_t* scalars32, size_t n, uint8_t out96[96]);
 C12381_API int c12381_g1_msm_partial_dev(const uint8_t* d_points96, const uint8_t* d_scalars32, size_t n, uint8_t* d_out96, void* stream);
 /* out = sum_i points[i] (combining the all-gathered per-rank partials in rank order); compressed result.
  * Replaces the add(point1&, point1&) loop (src/miracl_core_interface.cpp:129-132) used to merge partials. */
@@ -83,6 +86,7 @@ C12381_API int c12381_g1_sum_dev(const uint8_t* d_points96, size_t n, uint8_t* d
  * src/miracl_core_interface.cpp:202-205,212-215). */
 C12381_API int c12381_g2_msm(const uint8_t* points192, const uint8_t* scalars32, size_t n, uint8_t out97[97]);
 C12381_API int c12381_g2_msm_dev(const uint8_t* d_points192, const uint8_t* d_scalars32, size_t n, uint8_t* d_out97, void* stream);
+C12381_API int c12381_g2_msm_partial(const uint8_t* points192, const uint8_t* scalars32, size_t n, uint8_t out192[192]);
 C12381_API int c12381_g2_msm_partial_dev(const uint8_t* d_points192, const uint8_t* d_scalars32, size_t n, uint8_t* d_out192, void* stream);
 C12381_API int c12381_g2_sum_dev(const uint8_t* d_points192, size_t n, uint8_t* d_out97, void* stream);
 
@@ -189,29 +193,29 @@ C12381_API int c12381_gt_pow_gs_batch(const uint8_t* a576, const uint8_t* scalar
 C12381_API int c12381_gt_pow_gs_batch_dev(const uint8_t* d_a576, const uint8_t* d_scalars32, size_t B, uint8_t* d_out576, void* stream);
 
 /* ---- drop-in entries on the reference's PODs (batch of 1 per call; host pointers) --------------------------- */
-/* void sum_of_products(point1& result, int n, point1* points, const big* numbers)  (miracl_core_interface.hpp:143) */
+/* void sum_of_products(point1& result, int n, point1* points, const big* numbers)  (miracl_core_interface.hpp:102) */
 C12381_API int c12381_sum_of_products_miracl(void* result_point1, int n, const void* points_point1, const void* numbers_big);
-/* void multiply(point1& object, const big& value)  (:165) */
+/* void multiply(point1& object, const big& value)  (:122) */
 C12381_API int c12381_multiply_point1_miracl(void* object_point1, const void* value_big);
-/* void double_multiply(point1& p1, point1& p2, big& v1, big& v2): p1 = v1*p1 + v2*p2  (:167) */
+/* void double_multiply(point1& p1, point1& p2, big& v1, big& v2): p1 = v1*p1 + v2*p2  (:125) */
 C12381_API int c12381_double_multiply_miracl(void* p1_point1, const void* p2_point1, const void* v1_big, const void* v2_big);
-/* void multiply(point2& object, const big& value)  (:139-141 region; src :202) */
+/* void multiply(point2& object, const big& value)  (:151; src/miracl_core_interface.cpp:202) */
 C12381_API int c12381_multiply_point2_miracl(void* object_point2, const void* value_big);
 /* batched G2 sum of products on PODs (new entry the lazy G2Pow of SURVEY "next" N2 would call) */
 C12381_API int c12381_sum_of_products2_miracl(void* result_point2, int n, const void* points_point2, const void* numbers_big);
-/* void pair_ate(fp12& result, point2& p2, point1& p1)  (:199) */
+/* void pair_ate(fp12& result, point2& p2, point1& p1)  (:200) */
 C12381_API int c12381_pair_ate_miracl(void* result_fp12, const void* p2_point2, const void* p1_point1);
-/* void pair_double_ate(fp12& result, point2& p2, point1& p1, point2& q2, point1& q1)  (:203) */
+/* void pair_double_ate(fp12& result, point2& p2, point1& p1, point2& q2, point1& q1)  (:204) */
 C12381_API int c12381_pair_double_ate_miracl(void* result_fp12, const void* p2, const void* p1, const void* q2, const void* q1);
 /* ABI-additive: the product of n <= C12381_MAX_PAIRS Miller loops with shared squarings, p2s = point2[n], p1s = point1[n];
  * what a `pair * pair * ...` chain (liner_pair.hpp:219-230,291-303: pair_double_ate two at a time + multiply(fp12&, fp12&)) folds to,
  * and the value of MIRACL's unbridged PAIR_initmp / PAIR_another / PAIR_miller (pair_BLS12381.cpp:181-207,352-422). */
 C12381_API int c12381_pair_multi_ate_miracl(void* result_fp12, int n, const void* p2s_point2, const void* p1s_point1);
-/* void pair_final_exponentiation(fp12& object)  (:201) */
+/* void pair_final_exponentiation(fp12& object)  (:202) */
 C12381_API int c12381_pair_final_exponentiation_miracl(void* object_fp12);
-/* void multiply(fp12& result, fp12& value): result *= value  (:189) */
+/* void multiply(fp12& result, fp12& value): result *= value  (:192) */
 C12381_API int c12381_fp12_multiply_miracl(void* result_fp12, const void* value_fp12);
-/* void pow(fp12& result, fp12& base, const big& exponent)  (:191) */
+/* void pow(fp12& result, fp12& base, const big& exponent)  (:194) */
 C12381_API int c12381_fp12_pow_miracl(void* result_fp12, const void* base_fp12, const void* exponent_big);
 
 /* ---- measurement helpers ---------------------------------------------------------------------------------- */

@@ -232,3 +232,24 @@ def map_to_g1(u48: bytes, n: int) -> bytes:
     out = ctypes.create_string_buffer(49 * n)
     lib().ref_map_to_g1(u48, _sz(n), out)
     return out.raw
+
+
+# --- BBS+ (examples/bbs-plus/src/bbs+.cpp:38-73) on the reference's own bridge arithmetic ------------------------------
+def bbs_sign_batch(g1: bytes, h0: bytes, h: bytes, gamma32: bytes, rows: bytes, n: int, threads: int = 1, xs: bytes | None = None) -> bytes:
+    """A_i = (g1 * h0^r_i * prod h_j^m_ij)^(1 / (gamma + x_i)), compressed 49 B each.  g1, h0: affine 96 B; h: n x 96 B;
+    rows: B x (2 + n) x 32 B scalars (1, r_i, m_i0 ..); xs: B x 32 B (required)."""
+    assert xs is not None and len(h) == 96 * n
+    B = len(rows) // (32 * (2 + n))
+    assert len(xs) == 32 * B
+    out = ctypes.create_string_buffer(49 * B)
+    assert lib().ref_bbs_sign_batch(g1, h0, h, _int(n), gamma32, rows, xs, _sz(B), out, _int(threads)) == 1
+    return out.raw
+
+
+def bbs_verify_batch(g1: bytes, g2: bytes, h0: bytes, h: bytes, w: bytes, n: int, A49: bytes, rows: bytes, xrows: bytes, threads: int = 1) -> bytes:
+    """verdict bytes of pair(A, w * g2^x) == pair(g1 * h0^r * prod h_j^m_j, g2); xrows: B x 2 x 32 B rows (1, x_i)."""
+    B = len(A49) // 49
+    assert len(rows) == 32 * (2 + n) * B and len(xrows) == 64 * B and len(h) == 96 * n
+    out = ctypes.create_string_buffer(max(B, 1))
+    assert lib().ref_bbs_verify_batch(g1, g2, h0, h, w, _int(n), A49, rows, xrows, _sz(B), out, _int(threads)) == 1
+    return out.raw[:B]

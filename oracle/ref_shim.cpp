@@ -550,4 +550,113 @@ extern "C"
             g1_to_c49(out49 + 49 * i, P);
         }
     }
+
+    // ---- BBS+ at the bridge level: the arithmetic of examples/bbs-plus/src/bbs+.cpp:38-73 as the DSL evaluates it ----------
+    // Shared layout (one pp, one key, B instances): g1, h0, h_j affine 96 B each (parsed public parameters), g2 / w affine
+    // 192 B; per instance a row of 2 + n scalars (1, r, m_0 .. m_(n-1)), 32 B big-endian each (m_j = encode_to<Zp> blocks).
+    //
+    // product(): g1 * h0^r * PI[n](h[i]^m[i]) - the PI term through the live path of g1_point.hpp:389-401 (pairs through
+    // double_multiply, an odd tail through multiply, partials combined with add), h0^r through multiply, the three
+    // factors combined with add (operator* on G1 elements).
+    static void bbs_product(mc::point1& out, const uint8_t* g1_96, const uint8_t* h0_96, const uint8_t* h_96, int n, const uint8_t* row)
+    {
+        mc::point1 acc; mc::get_infinity(acc);
+        int i = 0;
+        for (; i + 1 < n; i += 2)
+        {
+            mc::point1 a, b; mc::big ka, kb;
+            g1_from_affine(a, h_96 + 96 * i); g1_from_affine(b, h_96 + 96 * (i + 1));
+            scalar_to_big(ka, row + 32 * (2 + i)); scalar_to_big(kb, row + 32 * (3 + i));
+            mc::double_multiply(a, b, ka, kb);
+            mc::add(acc, a);
+        }
+        if (i < n)
+        {
+            mc::point1 a; mc::big ka;
+            g1_from_affine(a, h_96 + 96 * i);
+            scalar_to_big(ka, row + 32 * (2 + i));
+            mc::multiply(a, ka);
+            mc::add(acc, a);
+        }
+        mc::point1 h0; mc::big r;
+        g1_from_affine(h0, h0_96);
+        scalar_to_big(r, row + 32);
+        mc::multiply(h0, r);
+        g1_from_affine(out, g1_96);
+        mc::add(out, h0);
+        mc::add(out, acc);
+    }
+
+    // sign (bbs+.cpp:38-55) with the caller's (x, r): A = product^(1 / (gamma + x)); x = xs[i], r = rows[i][1].
+    // outA49: B compressed points (the A of serialize(A, x, r)).
+    int ref_bbs_sign_batch(const uint8_t* g1_96, const uint8_t* h0_96, const uint8_t* h_96, int n, const uint8_t* gamma32,
+                           const uint8_t* rows, const uint8_t* xs32, size_t B, uint8_t* outA49, int threads)
+    {
+        parallel_for(B, threads, [&](size_t lo, size_t hi, int) {
+            mc::big r_mod, gamma;
+            mc::from_bytes(r_mod, (const char*)R_BYTES);
+            scalar_to_big(gamma, gamma32);
+            for (size_t b = lo; b < hi; ++b)
+            {
+                mc::point1 P;
+                bbs_product(P, g1_96, h0_96, h_96, n, rows + 32 * (size_t)(2 + n) * b);
+                // inverse(gamma + x) in Zp: (gamma + x) mod r through the bridge's double-width mod, then mod_inverse
+                mc::big x, one, e;
+                scalar_to_big(x, xs32 + 32 * b);
+                // gamma + x < 2 r < 2^256: add byte-wise, reduce by one conditional subtraction via mod on a big2
+                unsigned char sum[48] = {0};
+                unsigned carry = 0;
+                for (int i = 31; i >= 0; --i)
+                {
+                    unsigned t = (unsigned)gamma32[i] + xs32[32 * b + i] + carry;
+                    sum[16 + i] = (unsigned char)t; carry = t >> 8;
+                }
+                sum[15] = (unsigned char)carry;
+                mc::big2 wide; mc::big s;
+                mc::from_bytes(wide, (const char*)sum, 48);
+                mc::mod(s, wide, r_mod);
+                mc::mod_inverse(e, s, r_mod);
+                mc::multiply(P, e);
+                g1_to_c49(outA49 + 49 * b, P);
+            }
+        });
+        return 1;
+    }
+
+    // verify (bbs+.cpp:57-73): parse A (compressed 49 B; a parse failure is verdict 0, where the DSL throws),
+    // pair(A, w * g2^x) == pair(product, g2), each side pair_ate + pair_final_exponentiation, compared with equal.
+    // x = xrows[i][1] (rows of (1, x) as the CUDA pipeline takes them).
+    int ref_bbs_verify_batch(const uint8_t* g1_96, const uint8_t* g2_192, const uint8_t* h0_96, const uint8_t* h_96, const uint8_t* w_192, int n,
+                             const uint8_t* A49, const uint8_t* rows, const uint8_t* xrows, size_t B, uint8_t* verdict, int threads)
+    {
+        parallel_for(B, threads, [&](size_t lo, size_t hi, int) {
+            for (size_t b = lo; b < hi; ++b)
+            {
+                verdict[b] = 0;
+                mc::point1 A;
+                if (all_zero(A49 + 49 * b, 49)) mc::get_infinity(A);
+                else
+                {
+                    char buf[49];
+                    std::memcpy(buf, A49 + 49 * b, 49);
+                    mc::bytes_view v{49, 49, buf};
+                    if (!mc::from_bytes(A, v)) continue;
+                }
+                mc::point1 P;
+                bbs_product(P, g1_96, h0_96, h_96, n, rows + 32 * (size_t)(2 + n) * b);
+                mc::point2 W, G2, G2x; mc::big x;
+                g2_from_affine(W, w_192); g2_from_affine(G2, g2_192); g2_from_affine(G2x, g2_192);
+                scalar_to_big(x, xrows + 64 * b + 32);
+                mc::multiply(G2x, x);
+                mc::add(W, G2x);
+                mc::fp12 l, r;
+                mc::pair_ate(l, W, A);
+                mc::pair_final_exponentiation(l);
+                mc::pair_ate(r, G2, P);
+                mc::pair_final_exponentiation(r);
+                verdict[b] = mc::equal(l, r) ? 1 : 0;
+            }
+        });
+        return 1;
+    }
 }

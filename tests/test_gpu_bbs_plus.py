@@ -84,6 +84,56 @@ def test_products_over_shared_bases(gpu):
         assert bridge.to_bytes2(got2[192 * b:192 * b + 192]) == bridge.sum_of_products2(bases2, flat2[64 * b:64 * b + 64])
 
 
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libref12381.so not present")
+def test_bbs_plus_verify_reference_made_signatures(gpu):
+    """Signatures made by the REFERENCE's arithmetic (oracle/ref_shim.cpp: bbs+.cpp:38-55 on the unmodified bridge - parse, the live
+    double_multiply product loop, multiply by 1 / (gamma + x)) go to the CUDA `verify_batch`; and the reference's own verify
+    (bbs+.cpp:57-73) confirms every verdict, valid and tampered - nothing in this test was signed by the GPU."""
+    bridge, bbs = gpu
+    rnd = random.Random(88)
+    n, B, t = 10, 96, ref.hardware_threads()
+    gen_k = b"".join(be32(rnd.randrange(1, R)) for _ in range(n + 2))
+    gens_a = ref.g1_fixed_base_mul(gen_k, t)                     # g1, h0, h_0 .. h_9: affine, made by the reference
+    g2_a = ref.g2_fixed_base_mul(be32(rnd.randrange(1, R)))
+    gamma = rnd.randrange(1, R)
+    pk = ref.g2_mul_batch(g2_a, be32(gamma))                     # w = g2^gamma, 97 B
+    w_a, ok = ref.g2_decompress(pk)
+    assert ok
+    gens_c, g2_c = ref.g1_compress(gens_a), ref.g2_compress(g2_a)
+    pp = bbs.PublicParameters(gens_c[:49] + g2_c + gens_c[49:98], [gens_c[49 * i:49 * i + 49] for i in range(2, n + 2)])
+    assert pp.g1 + pp.h0 + pp.h == gens_a and pp.g2 == g2_a
+    msgs = [bytes(rnd.randrange(256) for _ in range(31 * n)) for _ in range(B)]      # n full blocks each
+    msgs[1] = b"short"                                                              # ... and ragged ones
+    msgs[2] = bytes(rnd.randrange(256) for _ in range(31 * 3 + 7))
+    xs, rs = [rnd.randrange(R) for _ in range(B)], [rnd.randrange(R) for _ in range(B)]
+    blocks = [bbs.encode_to_zp(m) for m in msgs]
+    rows = b"".join(be32(1) + be32(r) + b"".join(be32(m) for m in ms) + bytes(32 * (n - len(ms))) for r, ms in zip(rs, blocks))
+    xrows = b"".join(be32(1) + be32(x) for x in xs)
+    A = ref.bbs_sign_batch(gens_a[:96], gens_a[96:192], gens_a[192:], be32(gamma), rows, n, t, xs=b"".join(be32(x) for x in xs))
+    sigs = [A[49 * i:49 * i + 49] + xs[i].to_bytes(48, "big") + rs[i].to_bytes(48, "big") for i in range(B)]
+    ref_verify = lambda enc, rows_, xrows_: list(ref.bbs_verify_batch(gens_a[:96], g2_a, gens_a[96:192], gens_a[192:], w_a, n, enc, rows_, xrows_, t))
+    assert ref_verify(A, rows, xrows) == [1] * B                 # the reference accepts its own signatures
+    assert bbs.verify_batch(pp, pk, msgs, sigs) == [True] * B    # ... and so does the CUDA path
+    # the GPU's sign_batch makes the same bytes
+    assert bbs.sign_batch(pp, gamma.to_bytes(48, "big"), msgs, xs, rs) == sigs
+    # tampered: message changed, x changed, r changed, A swapped, A negated, A = identity
+    bad_msgs, bad = list(msgs), [bytearray(s_) for s_ in sigs]
+    bad_msgs[4] = bytes([msgs[4][0] ^ 1]) + msgs[4][1:]
+    bad[6][49:97] = ((xs[6] + 1) % R).to_bytes(48, "big")
+    bad[8][97:145] = ((rs[8] + 1) % R).to_bytes(48, "big")
+    bad[10][:49] = sigs[11][:49]
+    bad[12][0] ^= 1                                                # the other square root: -A
+    bad[14][:49] = bytes(49)
+    bad = [bytes(b_) for b_ in bad]
+    got = bbs.verify_batch(pp, pk, bad_msgs, bad)
+    assert got == [i not in (4, 6, 8, 10, 12, 14) for i in range(B)]
+    bad_blocks = [bbs.encode_to_zp(m) for m in bad_msgs]
+    bad_rows = b"".join(be32(1) + be32(int.from_bytes(s_[97:145], "big")) + b"".join(be32(m) for m in ms) + bytes(32 * (n - len(ms)))
+                        for s_, ms in zip(bad, bad_blocks))
+    bad_xrows = b"".join(be32(1) + be32(int.from_bytes(s_[49:97], "big")) for s_ in bad)
+    assert ref_verify(b"".join(s_[:49] for s_ in bad), bad_rows, bad_xrows) == [int(v) for v in got]
+
+
 def test_bbs_plus_sign_verify_batch(gpu):
     bridge, bbs = gpu
     rnd = random.Random(8)

@@ -138,6 +138,34 @@ def test_g2_msm_vs_reference(cuda, n, ba_rounds):
     assert cuda.msm2(pts, ss) == ref.g2_msm(pts, ss, t)
 
 
+# ---- the compiled reference at the sizes the benchmark quotes (differentials had stopped at 20 000 / 3 000 / 16) ----------
+@needs_ref
+def test_g1_msm_vs_reference_2p18(cuda):
+    """G1, n = 2^18: ECP_muln over all host threads (about a second on 16) against the whole CUDA pipeline at its c = 16 plan."""
+    n, t = 1 << 18, ref.hardware_threads()
+    ks, ss = rand_scalars(n, 1801), rand_scalars(n, 1802)
+    pts = cuda.fixed_base1(ks)
+    assert cuda.msm1(pts, ss) == ref.g1_msm(pts, ss, 0, t)
+
+
+@needs_ref
+def test_g2_msm_vs_reference_2p16(cuda):
+    """G2, n = 2^16: the reference's per-term PAIR_G2mul + ECP2_add loop over all host threads."""
+    n, t = 1 << 16, ref.hardware_threads()
+    ks, ss = rand_scalars(n, 1601), rand_scalars(n, 1602)
+    pts = cuda.fixed_base2(ks)
+    assert cuda.msm2(pts, ss) == ref.g2_msm(pts, ss, t)
+
+
+@needs_ref
+def test_pairing_products_vs_reference_1024x4(cuda, pairing_kernel):
+    """1024 instances x 4 pairs (BASELINE configs[3]'s shape): raw Miller products and GT values, every instance."""
+    B, k, t = 1024, 4, ref.hardware_threads()
+    g1, g2 = cuda.fixed_base1(rand_scalars(B * k, 1024)), cuda.fixed_base2(rand_scalars(B * k, 1025))
+    assert cuda.product(g1, g2, k) == ref.pairing_product_batch(g1, g2, k, 1, t)
+    assert cuda.miller(g1, g2, k) == ref.pairing_product_batch(g1, g2, k, 0, t)
+
+
 @needs_ref
 def test_mul_batch_vs_reference(cuda):
     t = ref.hardware_threads()
@@ -310,6 +338,65 @@ def test_pairing_check_full_batch(cuda, pairing_kernel):
     assert [i for i in range(B) if verdict[i] == 0] == sorted(bad)
     gt = dv.pairing_product_batch(d1, d2, k).cpu().numpy().tobytes()
     assert all((gt[576 * i:576 * (i + 1)] == ps.ONE_GT) == (i not in bad) for i in range(B))
+
+
+# ---- one arena, several streams ----------------------------------------------------------------------------
+def test_interleaved_streams_share_the_arena(cuda):
+    """`_dev` MSMs on two torch streams and host entries on the context's own stream, issued back to back without any
+    synchronisation: every call carves from the same scratch arena, so each must be ordered behind the previous one."""
+    dv, br = cuda.device, cuda.bridge
+    n = 1 << 16
+    ks, ss = rand_scalars(n, 901), rand_scalars(n, 902)
+    d_k = torch.frombuffer(bytearray(ks), dtype=torch.uint8).cuda()
+    d_s = torch.frombuffer(bytearray(ss), dtype=torch.uint8).cuda()
+    pts = dv.g1_fixed_base_mul_batch(d_k)
+    want = bytes(dv.g1_msm(pts, d_s).cpu().numpy())
+    want_half = bytes(dv.g1_msm(pts[:96 * (n // 2)], d_s[:32 * (n // 2)]).cpu().numpy())
+    comp = br.to_bytes(bytes(pts[:96 * 64].cpu().numpy()))
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for rep in range(4):
+        with torch.cuda.stream(s1):
+            a = dv.g1_msm(pts, d_s)
+        with torch.cuda.stream(s2):
+            b = dv.g1_msm(pts[:96 * (n // 2)], d_s[:32 * (n // 2)])
+        aff = br.from_bytes(comp)                       # host entry: context stream, its own copies
+        with torch.cuda.stream(s1):
+            c = dv.g1_msm(pts, d_s)
+        small = br.sum_of_products(bytes(pts[:96 * 33].cpu().numpy()), ss[:32 * 33])
+        torch.cuda.synchronize()
+        assert bytes(a.cpu().numpy()) == want and bytes(c.cpu().numpy()) == want and bytes(b.cpu().numpy()) == want_half
+        assert aff == bytes(pts[:96 * 64].cpu().numpy())
+        assert small == bytes(dv.g1_msm(pts[:96 * 33], d_s[:32 * 33]).cpu().numpy())
+    dv.sync_status()
+
+
+def test_device_wrappers_validate_sizes(cuda):
+    """A mismatched tensor is a ValueError in Python, never an out-of-bounds access on the device."""
+    dv = cuda.device
+    z = lambda n: torch.zeros(n, dtype=torch.uint8, device="cuda")
+    for fn, args in ((dv.g1_mul_batch, (z(96), z(64))), (dv.g2_mul_batch, (z(192 * 2), z(32))), (dv.gt_mul_batch, (z(576 * 2), z(576))),
+                     (dv.gt_pow_batch, (z(576), z(64))), (dv.gt_pow_gs_batch, (z(576 * 2), z(32))), (dv.g1_sum, (z(97),)), (dv.g2_sum, (z(191),)),
+                     (dv.final_exp_batch, (z(577),)), (dv.sha3_512_batch, (z(10), 3)), (dv.g1_msm, (z(96), z(32), z(48))),
+                     (dv.g1_fixed_base_mul_batch, (z(32), torch.zeros(96, dtype=torch.uint8))), (dv.g1_compress_batch, (z(96), z(50))),
+                     (dv.pairing_check_batch, (z(96), z(192), 1, z(2))), (dv.g1_multi_fixed_base_batch, (z(96 * 2), z(32 * 3)))):
+        with pytest.raises(ValueError):
+            fn(*args)
+    with pytest.raises(ValueError):
+        dv.g1_msm(torch.zeros(96, dtype=torch.uint8), torch.zeros(32, dtype=torch.uint8))     # CPU tensors
+
+
+@needs_ref
+def test_pod_scalar_at_or_above_r_is_reduced(cuda):
+    """multiply(point1&, big) with value >= r: the reference (PAIR_G1mul) reduces mod r, so does the drop-in entry - no error."""
+    br = cuda.bridge
+    k = ref.random_scalars("pod-big-reduce", 1)
+    a1 = ref.g1_fixed_base_mul(k)
+    for v in (R, R + 5, 2 * R - 1):
+        big = ref.make_big(be32(v))
+        o1 = ref.make_point1(a1)
+        br.multiply_pod(o1, big)
+        assert ref.point1_to_c49(o1, 1) == ref.g1_mul_batch(a1, be32(v % R))
 
 
 # ---- error behaviour -------------------------------------------------------------------------------------------------
