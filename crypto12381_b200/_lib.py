@@ -27,6 +27,8 @@ SIGNATURES = {
     "c12381_sync_status": (_i, [_p]),
     "c12381_set_msm_window": (None, [_i]),
     "c12381_set_msm_batch_affine": (None, [_i]),
+    "c12381_set_msm_pipelines": (None, [_i]),
+    "c12381_set_knob": (None, [_i, _i]),
     "c12381_g1_msm": (_i, [_p, _p, _sz, _p]),
     "c12381_g1_msm_partial": (_i, [_p, _p, _sz, _p]),
     "c12381_g2_msm_partial": (_i, [_p, _p, _sz, _p]),

@@ -46,7 +46,11 @@ struct Ctx {
     int* h_flags = nullptr;
     int* d_flags = nullptr;
     int forced_window = 0;
-    int ba_rounds = 0;      // batch-affine pre-reduction rounds before the XYZZ accumulation (0, 1, 2): measured slower, opt-in
+    int ba_rounds = -1;     // batch-affine halving rounds in front of the XYZZ accumulation: -1 = chosen from the bucket load, 0 = none, k = k rounds
+    int ba_pipes = 2;       // independent round pipelines (groups of windows on their own streams: one's inversion kernel hides behind the other's additions)
+    int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // streams of pipelines 1 .. 3 (pipeline 0 runs on the caller's stream)
+    cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork + one join per side stream
     void* fb_table[2] = {nullptr, nullptr};   // fixed-base window tables (G1, G2), built on first use
     MsmStats stats;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

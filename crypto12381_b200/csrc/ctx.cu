@@ -186,6 +186,8 @@ int c12381_init(int device)
     C12_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c.copy_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaEventCreateWithFlags(&c.arena_ev, cudaEventDisableTiming));
+    for (auto& st : c.side) C12_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& ev : c.side_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
     C12_CUDA(cudaMalloc(&c.d_flags, 64 * sizeof(int)));
@@ -215,6 +217,10 @@ void c12381_shutdown(void)
     for (auto& ev : c.copy_ev)
         if (ev) cudaEventDestroy(ev);
     if (c.arena_ev) cudaEventDestroy(c.arena_ev);
+    for (auto& ev : c.side_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& st : c.side)
+        if (st) cudaStreamDestroy(st);
     if (c.copy_stream) {
         cudaStreamSynchronize(c.copy_stream);
         cudaStreamDestroy(c.copy_stream);
@@ -226,7 +232,12 @@ void c12381_shutdown(void)
 const char* c12381_last_error(void) { return ctx().err.c_str(); }
 int c12381_device(void) { return ctx().device; }
 void c12381_set_msm_window(int c) { ctx().forced_window = c; }
-void c12381_set_msm_batch_affine(int rounds) { ctx().ba_rounds = rounds < 0 ? 0 : (rounds > 2 ? 2 : rounds); }
+void c12381_set_msm_batch_affine(int rounds) { ctx().ba_rounds = rounds < 0 ? -1 : (rounds > 16 ? 16 : rounds); }
+void c12381_set_knob(int id, int value)
+{
+    if (id >= 0 && id < 4) ctx().knob[id] = value;
+}
+void c12381_set_msm_pipelines(int pipes) { ctx().ba_pipes = pipes < 1 ? 1 : (pipes > 4 ? 4 : pipes); }
 unsigned long long c12381_launch_count(void) { return ctx().launches; }
 
 int c12381_last_msm_stats(double* accumulate_ms, double* total_ms, unsigned long long* bucket_adds, int* window_bits)

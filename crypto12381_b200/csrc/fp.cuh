@@ -304,95 +304,169 @@ C12_HD Fp fp_to_mont(const Fp& a) { return fp_mul(fp_r2(), a); }  // a may be an
 C12_HD Fp fp_from_mont(const Fp& a) { return fp_redc(a); }
 
 // ---- inversion ---------------------------------------------------------------------------------------------
-// Binary extended Euclid on the plain 384-bit integers (Replaces FP_inv, 3rd-party/miracl-core/fp_BLS12381.cpp:817,
-// which is Fermat a^(p-2) through FP_progen).  About 2*381 shift/subtract steps of 12-limb add/sub instead of
-// ~480 Montgomery products: an order of magnitude fewer instructions, which matters most where ONE thread
-// normalises a final result (the serial tail of an MSM).  Not constant time — all inputs here are public.
-// inv(0) = 0.  Inversions are still amortised by Montgomery's trick wherever a batch exists.
+// Bernstein-Yang "safegcd" division steps (eprint 2019/266) on 13 signed 30-bit limbs, in batches of 30 steps: a batch walks
+// the LOW WORDS of f and g only (30 x ~14 single-word instructions) and yields a 2 x 2 transition matrix that is then
+// applied to the full f, g (exactly divisible by 2^30) and, modulo p, to the cofactors d, e - 8 x 13 signed multiply-adds.
+// Replaces FP_inv (3rd-party/miracl-core/fp_BLS12381.cpp:817, Fermat a^(p-2) through FP_progen: ~480 Montgomery products).
+// About 27 batches = ~20 k instructions, and - unlike a binary Euclid with its data-dependent inner loops - every lane of a
+// warp runs the same instruction stream (the batch body is branch-free; lanes only differ in the batch at which g reaches 0,
+// by one or two), which is what matters where 32 lanes invert 32 different elements (k_ba_inv) and where ONE thread
+// normalises a final result (the serial tail of an MSM).  The loop runs until g = 0, so it relies on no iteration bound; the
+// proven one is 1,101 steps = 37 batches for inputs below 2^381 (Thm. 11.2).  Not constant time.  inv(0) = 0.
+// Inversions are still amortised by Montgomery's trick wherever a batch exists.
 namespace detail {
-C12_HD bool limbs_is_one(const uint32_t (&a)[12])
+struct S30 {
+    int32_t v[13];      // value = sum v[i] 2^(30 i)
+};
+struct Trans30 {
+    int32_t u, v, q, r;
+};
+#define C12_P30_SIGNED {0x3fffaaab, 0x27fbffff, 0x153ffffb, 0x2affffac, 0x30f6241e, 0x034a83da, 0x112bf673, 0x12e13ce1, 0x2cd76477, 0x1ed90d2e, 0x29a4b1ba, 0x3a8e5ff9, 0x001a0111}
+constexpr uint32_t P_INV30 = 0x00030003u;   // p^-1 mod 2^30
+constexpr int32_t M30 = 0x3fffffff;
+
+// 30 division steps on the low words.  zeta = -(delta + 1/2); returns the new zeta, t maps (f, g) to (f', g') 2^30.
+C12_HD int32_t safegcd_divsteps_30(int32_t zeta, uint32_t f0, uint32_t g0, Trans30& t)
 {
-    uint32_t z = a[0] ^ 1u;
-#pragma unroll
-    for (int i = 1; i < 12; ++i) z |= a[i];
-    return z == 0;
-}
-C12_HD bool limbs_ge(const uint32_t (&a)[12], const uint32_t (&b)[12])
-{
-    uint64_t borrow = 0;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        uint64_t d = (uint64_t)a[i] - b[i] - borrow;
-        borrow = (d >> 32) & 1u;
+    uint32_t u = 1, v = 0, q = 0, r = 1, f = f0, g = g0;
+#pragma unroll 5
+    for (int i = 0; i < 30; ++i) {
+        uint32_t c1 = (uint32_t)(zeta >> 31);         // all ones when delta > 0 ...
+        const uint32_t c2 = 0u - (g & 1u);            // ... and g is odd: swap-and-subtract, else add f to g when g is odd
+        const uint32_t x = (f ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+        g += x & c2;
+        q += y & c2;
+        r += z & c2;
+        c1 &= c2;
+        zeta = (int32_t)(((uint32_t)zeta ^ c1) - 1u);
+        f += g & c1;
+        u += q & c1;
+        v += r & c1;
+        g >>= 1;
+        u <<= 1;
+        v <<= 1;
     }
-    return borrow == 0;
+    t.u = (int32_t)u;
+    t.v = (int32_t)v;
+    t.q = (int32_t)q;
+    t.r = (int32_t)r;
+    return zeta;
 }
-C12_HD void limbs_sub(uint32_t (&a)[12], const uint32_t (&b)[12])  // a -= b, a >= b
+
+// (d, e) <- t (d, e) / 2^30 mod p, both kept in (-2p, p)
+C12_HD void safegcd_update_de(S30& d, S30& e, const Trans30& t)
 {
-    uint64_t borrow = 0;
+    const int32_t pl[13] = C12_P30_SIGNED;
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    const int32_t sd = d.v[12] >> 31, se = e.v[12] >> 31;
+    int32_t md = (t.u & sd) + (t.v & se), me = (t.q & sd) + (t.r & se);
+    int64_t cd = u * d.v[0] + v * e.v[0], ce = q * d.v[0] + r * e.v[0];
+    md -= (int32_t)((P_INV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+    me -= (int32_t)((P_INV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+    cd += (int64_t)pl[0] * md;
+    ce += (int64_t)pl[0] * me;
+    cd >>= 30;      // the low 30 bits are zero by the choice of md, me
+    ce >>= 30;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        uint64_t d = (uint64_t)a[i] - b[i] - borrow;
-        a[i] = (uint32_t)d;
-        borrow = (d >> 32) & 1u;
+    for (int i = 1; i < 13; ++i) {
+        cd += u * d.v[i] + v * e.v[i] + (int64_t)pl[i] * md;
+        ce += q * d.v[i] + r * e.v[i] + (int64_t)pl[i] * me;
+        d.v[i - 1] = (int32_t)cd & M30;
+        e.v[i - 1] = (int32_t)ce & M30;
+        cd >>= 30;
+        ce >>= 30;
     }
+    d.v[12] = (int32_t)cd;
+    e.v[12] = (int32_t)ce;
 }
-// x = x / 2 mod p for x < p: (x even ? x : x + p) >> 1
-C12_HD void limbs_half_mod_p(uint32_t (&x)[12])
+
+// (f, g) <- t (f, g) / 2^30 (exact)
+C12_HD void safegcd_update_fg(S30& f, S30& g, const Trans30& t)
 {
-    const uint32_t pl[12] = C12_P_LIMBS;
-    const uint32_t mask = 0u - (x[0] & 1u);
-    uint64_t c = 0;
+    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
+    int64_t cf = u * f.v[0] + v * g.v[0], cg = q * f.v[0] + r * g.v[0];
+    cf >>= 30;
+    cg >>= 30;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) {
-        uint64_t t = (uint64_t)x[i] + (pl[i] & mask) + c;
-        x[i] = (uint32_t)t;
-        c = t >> 32;
+    for (int i = 1; i < 13; ++i) {
+        cf += u * f.v[i] + v * g.v[i];
+        cg += q * f.v[i] + r * g.v[i];
+        f.v[i - 1] = (int32_t)cf & M30;
+        g.v[i - 1] = (int32_t)cg & M30;
+        cf >>= 30;
+        cg >>= 30;
     }
-#pragma unroll
-    for (int i = 0; i < 11; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
-    x[11] = (x[11] >> 1) | ((uint32_t)c << 31);
+    f.v[12] = (int32_t)cf;
+    g.v[12] = (int32_t)cg;
 }
-C12_HD void limbs_shr1(uint32_t (&x)[12])
+
+// d in (-2p, p), negated when `sign` is negative -> [0, p), limbs in [0, 2^30)
+C12_HD void safegcd_normalize(S30& d, int32_t sign)
 {
+    const int32_t pl[13] = C12_P30_SIGNED;
+    const int32_t neg = sign >> 31;
+    int32_t add = d.v[12] >> 31, carry = 0;
 #pragma unroll
-    for (int i = 0; i < 11; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
-    x[11] >>= 1;
+    for (int i = 0; i < 13; ++i) {
+        int32_t x = d.v[i] + (pl[i] & add);
+        x = (x ^ neg) - neg + carry;
+        carry = i < 12 ? x >> 30 : 0;
+        d.v[i] = i < 12 ? x & M30 : x;
+    }
+    add = d.v[12] >> 31;        // now in (-p, p)
+    carry = 0;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+        int32_t x = d.v[i] + (pl[i] & add) + carry;
+        carry = i < 12 ? x >> 30 : 0;
+        d.v[i] = i < 12 ? x & M30 : x;
+    }
 }
 } // namespace detail
 
 C12_HD_NOINLINE Fp fp_inv(const Fp& a)
 {
-    if (fp_is_zero(a)) return fp_zero();
-    const uint32_t pl[12] = C12_P_LIMBS;
-    Fp u = a, v, x1 = fp_zero(), x2 = fp_zero();   // u = a R (as a plain integer), v = p
+    using namespace detail;
+    const int32_t pl[13] = C12_P30_SIGNED;
+    S30 d, e, f, g;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) v.v[i] = pl[i];
-    x1.v[0] = 1;
+    for (int i = 0; i < 13; ++i) {
+        d.v[i] = 0;
+        e.v[i] = i == 0 ? 1 : 0;
+        f.v[i] = pl[i];
+        // 12 x 32 -> 13 x 30: a R as a plain integer
+        const int bit = 30 * i, w = bit >> 5, sh = bit & 31;
+        uint32_t x = a.v[w] >> sh;
+        if (sh > 2 && w + 1 < 12) x |= a.v[w + 1] << (32 - sh);
+        g.v[i] = (int32_t)(x & (uint32_t)M30);
+    }
+    int32_t zeta = -1;
 #pragma unroll 1
-    while (!detail::limbs_is_one(u.v) && !detail::limbs_is_one(v.v)) {
-#pragma unroll 1
-        while (!(u.v[0] & 1u)) {
-            detail::limbs_shr1(u.v);
-            detail::limbs_half_mod_p(x1.v);
-        }
-#pragma unroll 1
-        while (!(v.v[0] & 1u)) {
-            detail::limbs_shr1(v.v);
-            detail::limbs_half_mod_p(x2.v);
-        }
-        if (detail::limbs_ge(u.v, v.v)) {
-            detail::limbs_sub(u.v, v.v);
-            x1 = fp_sub(x1, x2);
-        } else {
-            detail::limbs_sub(v.v, u.v);
-            x2 = fp_sub(x2, x1);
-        }
+    for (int batch = 0; batch < 48; ++batch) {
+        int32_t nz = 0;
+#pragma unroll
+        for (int i = 0; i < 13; ++i) nz |= g.v[i];
+        if (nz == 0) break;
+        Trans30 t;
+        zeta = safegcd_divsteps_30(zeta, (uint32_t)f.v[0], (uint32_t)g.v[0], t);
+        safegcd_update_de(d, e, t);
+        safegcd_update_fg(f, g, t);
+    }
+    // f = +-gcd = +-1 (or +-p when a = 0, where d = 0 anyway): d = +-(a R)^-1
+    safegcd_normalize(d, f.v[12]);
+    Fp x;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {          // 13 x 30 -> 12 x 32
+        const int bit = 32 * j, i0 = bit / 30, o = bit - 30 * i0;
+        uint32_t w = (uint32_t)d.v[i0] >> o;
+        if (i0 + 1 < 13) w |= (uint32_t)d.v[i0 + 1] << (30 - o);
+        if (60 - o < 32 && i0 + 2 < 13) w |= (uint32_t)d.v[i0 + 2] << (60 - o);
+        x.v[j] = w;
     }
     // (a R)^-1; times R^3 / R  ->  a^-1 R
     const Fp r3 = {{0xd94ca1e0u, 0xed48ac6bu, 0x03a7adf8u, 0x315f831eu, 0x615e29ddu, 0x9a53352au, 0x921e1761u, 0x34c04e5eu, 0x65724728u,
                     0x2512d435u, 0x91755d4du, 0x0aa63460u}};
-    return fp_mul(detail::limbs_is_one(u.v) ? x1 : x2, r3);
+    return fp_mul(x, r3);
 }
 
 // a^((p+1)/4): the square root when a is a residue (p = 3 mod 4).  Replaces FP_sqrt

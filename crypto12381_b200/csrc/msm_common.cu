@@ -31,61 +31,125 @@ int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* star
     return C12381_OK;
 }
 
-__global__ void k_bucket_size_keys(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ ids)
+// ---- offsets of the bucket lists after each batch-affine halving round ------------------------------------------------
+// off_r[b] = sum over b' < b of ceil(m_b' / 2^r), r = 1 .. rounds (blockIdx.y = r - 1), total + 1 entries per round: three
+// launches for all rounds together (tile sums, scan of the tile sums, apply).
+constexpr int BA_PLAN_ITEMS = 8, BA_PLAN_TILE = 256 * BA_PLAN_ITEMS;
+
+__device__ __forceinline__ uint32_t ba_plan_len(const uint32_t* start, const uint32_t* end, uint32_t total, uint32_t b, uint32_t r)
 {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total) return;
-    uint32_t sz = end[b] - start[b];
-    keys[b] = 255u - (sz > 255u ? 255u : sz);   // ascending key = descending size
-    ids[b] = b;
+    return b < total ? ba_len(end[b] - start[b], r) : 0u;
 }
 
-__global__ void k_ba_counts(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end, uint32_t* __restrict__ out)
+__global__ void __launch_bounds__(256) k_ba_plan_tiles(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                                       uint32_t* __restrict__ tile_sums, uint32_t ntiles)
 {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < total) out[b] = ba_pairs0(end[b] - start[b]);
+    const uint32_t r = blockIdx.y + 1, base = blockIdx.x * BA_PLAN_TILE + threadIdx.x * BA_PLAN_ITEMS;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < BA_PLAN_ITEMS; ++i) s += ba_plan_len(start, end, total, base + i, r);
+    uint32_t tot;
+    block_exclusive_scan_256(s, &tot);
+    if (threadIdx.x == 0) tile_sums[(size_t)blockIdx.y * ntiles + blockIdx.x] = tot;
 }
 
-size_t ba_offsets_tile_words(const MsmPlan& pl) { return cdiv(pl.total, SCAN_TILE) + 2; }
-
-// o0[b] = sum of the round-0 pair counts of the buckets before b
-int launch_ba_offsets(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* o0, uint32_t* tile_sums, cudaStream_t s)
+__global__ void __launch_bounds__(256) k_ba_plan_top(uint32_t* __restrict__ tile_sums, uint32_t ntiles)
 {
-    k_ba_counts<<<cdiv(pl.total, 256), 256, 0, s>>>(pl.total, start, end, o0);
+    uint32_t* t = tile_sums + (size_t)blockIdx.x * ntiles;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < ntiles; base += 256) {
+        const uint32_t idx = base + threadIdx.x;
+        const uint32_t v = idx < ntiles ? t[idx] : 0;
+        uint32_t tot;
+        const uint32_t e = block_exclusive_scan_256(v, &tot);
+        if (idx < ntiles) t[idx] = e + carry;
+        carry += tot;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ba_plan_apply(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                                       const uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ off)
+{
+    const uint32_t r = blockIdx.y + 1, base = blockIdx.x * BA_PLAN_TILE + threadIdx.x * BA_PLAN_ITEMS;
+    uint32_t v[BA_PLAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < BA_PLAN_ITEMS; ++i) {
+        v[i] = ba_plan_len(start, end, total, base + i, r);
+        s += v[i];
+    }
+    uint32_t tot;
+    uint32_t e = block_exclusive_scan_256(s, &tot) + tile_sums[(size_t)blockIdx.y * ntiles + blockIdx.x];
+    uint32_t* o = off + (size_t)blockIdx.y * (total + 1);
+#pragma unroll
+    for (int i = 0; i < BA_PLAN_ITEMS; ++i) {
+        if (base + i <= total) o[base + i] = e;       // entry `total` is the round's slot count
+        e += v[i];
+    }
+}
+
+size_t ba_plan_scratch_words(const MsmPlan& pl, uint32_t rounds) { return (size_t)rounds * (cdiv((size_t)pl.total + 1, BA_PLAN_TILE) + 1) + 64; }
+
+int launch_ba_plan(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s)
+{
+    const uint32_t ntiles = cdiv((size_t)pl.total + 1, BA_PLAN_TILE);
+    k_ba_plan_tiles<<<dim3(ntiles, rounds), 256, 0, s>>>(pl.total, start, end, tile_sums, ntiles);
     C12_LAUNCHED();
-    const uint32_t ntiles = cdiv(pl.total, SCAN_TILE);
-    k_scan_tile_sums<<<ntiles, SCAN_THREADS, 0, s>>>(o0, pl.total, tile_sums);
+    k_ba_plan_top<<<rounds, 256, 0, s>>>(tile_sums, ntiles);
     C12_LAUNCHED();
-    k_scan_top<<<1, SCAN_THREADS, 0, s>>>(tile_sums, ntiles);
-    C12_LAUNCHED();
-    k_scan_apply<<<ntiles, SCAN_THREADS, 0, s>>>(o0, pl.total, tile_sums);
+    k_ba_plan_apply<<<dim3(ntiles, rounds), 256, 0, s>>>(pl.total, start, end, tile_sums, ntiles, off);
     C12_LAUNCHED();
     return C12381_OK;
 }
 
-size_t bucket_order_scratch_words(const MsmPlan& pl)
+// every output slot of every round -> the two inputs it adds (blockIdx.y = round; see msm_impl.cuh).  A thread resolves
+// BA_MAP_RUN consecutive slots: one binary search for the first, then the bucket only moves forward by a step or two.
+constexpr uint32_t BA_MAP_RUN = 8;
+__global__ void __launch_bounds__(256) k_ba_map(BaMapGeom g)
 {
-    size_t tile_words = 0;
-    size_t hist = sort_scratch_words(pl.total, 1, &tile_words);
-    return 4 * (size_t)pl.total + hist + tile_words + 64;
+    const uint32_t r = blockIdx.y;
+    const uint32_t* off_out = g.off + (size_t)r * (g.total + 1);
+    const uint32_t* off_in = r ? g.off + (size_t)(r - 1) * (g.total + 1) : g.start;
+    const uint32_t n_slots = off_out[g.total];
+    uint32_t t = (blockIdx.x * 256 + threadIdx.x) * BA_MAP_RUN;
+    if (t >= n_slots) return;
+    const uint32_t t_end = t + BA_MAP_RUN < n_slots ? t + BA_MAP_RUN : n_slots;
+    uint32_t b = ba_bucket_of(off_out, 0u, g.total, t), p = 0;
+    uint32_t lo = off_out[b], hi = off_out[b + 1], len = ba_len(g.end[b] - g.start[b], r), in0 = off_in[b];
+    while (p + 1 < g.pipes && b >= g.b_lo[p + 1]) ++p;
+    uint32_t p_slot0 = off_out[g.b_lo[p]], p_in0 = r ? off_in[g.b_lo[p]] : 0u;
+    for (; t < t_end; ++t) {
+        if (t >= hi) {
+            b = ba_bucket_of(off_out, b + 1, g.total, t);
+            lo = off_out[b];
+            hi = off_out[b + 1];
+            len = ba_len(g.end[b] - g.start[b], r);
+            in0 = off_in[b];
+            if (p + 1 < g.pipes && b >= g.b_lo[p + 1]) {
+                while (p + 1 < g.pipes && b >= g.b_lo[p + 1]) ++p;
+                p_slot0 = off_out[g.b_lo[p]];
+                p_in0 = r ? off_in[g.b_lo[p]] : 0u;
+            }
+        }
+        const uint32_t ii = t - lo;
+        const bool has2 = 2 * ii + 1 < len;
+        uint2 ref;
+        if (r == 0) {
+            const uint32_t pos = in0 + 2 * ii;
+            ref.x = g.vals[pos];
+            ref.y = has2 ? g.vals[pos + 1] : BA_NONE;
+        } else {
+            const uint32_t pos = g.list_region[(r - 1) & 1][p] + (in0 + 2 * ii - p_in0);
+            ref.x = pos;
+            ref.y = has2 ? pos + 1 : BA_NONE;
+        }
+        g.refs[(size_t)g.ref_region[r][p] + (t - p_slot0)] = ref;
+    }
 }
 
-int launch_bucket_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** order, cudaStream_t s)
+int launch_ba_map(const BaMapGeom& g, uint32_t max_slots, cudaStream_t s)
 {
-    size_t tile_words = 0;
-    size_t hist_words = sort_scratch_words(pl.total, 1, &tile_words);
-    uint32_t* keys = scratch;
-    uint32_t* ids = keys + pl.total;
-    uint32_t* keys2 = ids + pl.total;
-    uint32_t* ids2 = keys2 + pl.total;
-    uint32_t* hist = ids2 + pl.total;
-    uint32_t* tiles = hist + hist_words;
-    k_bucket_size_keys<<<cdiv(pl.total, 256), 256, 0, s>>>(pl.total, start, end, keys, ids);
+    k_ba_map<<<dim3(cdiv(max_slots, 256 * BA_MAP_RUN), g.rounds), 256, 0, s>>>(g);
     C12_LAUNCHED();
-    int rc = sort_pairs_segmented(keys, ids, keys2, ids2, pl.total, 1, 8, hist, tiles, s);
-    if (rc) return rc;
-    *order = ids;
     return C12381_OK;
 }
 

@@ -474,18 +474,39 @@ template <class F> C12_HD Proj<F> msm_fold_body(const Proj<F>* partials, uint32_
     return acc;
 }
 
-// ---- batch-affine pre-reduction of the bucket lists -----------------------------------------------------------------
-// Before the XYZZ accumulation, up to two rounds halve each bucket's list with AFFINE additions whose inversions are
-// shared by Montgomery's trick: round 0 adds the entries of a bucket pairwise (2i, 2i+1), round 1 adds round 0's results
-// pairwise.  An affine addition is 1 product for the running denominator product, 2 to unwind it, and lambda, lambda^2,
-// y3: 6 Fp products against 10 for the XYZZ mixed addition; one field inversion serves a whole thread block
-// (BA_CAP pairs x 128 buckets), staged through a product tree in shared memory.
-//   round 0: p0 = min(m / 2, BA_CAP) pairs of bucket b (m entries) -> A0[o0 .. o0 + p0), o0 = exclusive scan of p0
-//   round 1: p1 = p0 / 2 pairs of those                            -> A1[ceil(o0 / 2) .. + p1)
-//   the accumulation then sums  A1 (or A0 after one round) + the odd A0 element + the untouched entries 2 p0 .. m
-constexpr uint32_t BA_CAP = 64;
+// ---- batch-affine halving rounds of the bucket lists -----------------------------------------------------------------
+// The bucket sums are formed by AFFINE additions whose inversions are shared by Montgomery's trick.  Round r halves every
+// bucket's list: entries (2i, 2i+1) are added, an odd last entry is carried over, so after r rounds a list of m entries holds
+// ceil(m / 2^r) partial sums - the same group sum whatever the pairing order, and the outputs are compared on normalised
+// encodings.  An affine addition is 1 product for the running denominator product, 2 to unwind it, and lambda, lambda^2, y3:
+// 6 Fp products against 10 for the XYZZ mixed addition.
+//   lists of round r     : bucket b owns [off_r[b], off_r[b] + len_r(b)) of the round's point array, len_r(b) = ceil(m_b / 2^r);
+//                          round 0 is the sorted (key, term) array itself (off_0 = start[], entries fetched through vals -> points)
+//   output slot t of a round: bucket b = the one with off_(r+1)[b] <= t < off_(r+1)[b + 1], i = t - off_(r+1)[b],
+//                          inputs off_r[b] + 2i and (if 2i + 1 < len_r(b)) + 2i + 1
+// Slots are a FLAT index space: every thread of the round's kernels does the same amount of work whatever the bucket sizes are
+// (msm_impl.cuh: k_ba_fwd / k_ba_inv / k_ba_bwd).
+C12_HD uint32_t ba_len(uint32_t m0, uint32_t r) { return (uint32_t)(((uint64_t)m0 + ((1ull << r) - 1ull)) >> r); }
 
-C12_HD uint32_t ba_pairs0(uint32_t m) { return m / 2 < BA_CAP ? m / 2 : BA_CAP; }
+// the bucket owning output slot `slot`: largest b in [lo, hi) with off[b] <= slot, given off[lo] <= slot < off[hi]
+// (empty buckets share their successor's offset and are never returned).  `hint` is a bucket at or before the answer.
+C12_HD uint32_t ba_bucket_of(const uint32_t* off, uint32_t hint, uint32_t hi, uint32_t slot)
+{
+    uint32_t b = hint;
+    for (int step = 0; step < 3; ++step) {          // neighbouring slots of a thread are a bucket or two apart
+        if (off[b + 1] > slot) return b;
+        ++b;
+    }
+    uint32_t lo = b;                                 // off[lo] <= slot < off[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (off[mid] <= slot)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
 
 // entry j of a bucket's sorted list as a signed affine point
 template <class F> C12_HD Affine<F> ba_fetch(const uint32_t* vals, const Affine<F>* points, uint32_t j)
@@ -522,37 +543,6 @@ template <class F> C12_HD Affine<F> ba_finish(const Affine<F>& P, const Affine<F
     F x3 = sub(sub(sqr_hot(lam), P.x), Q.x);
     F y3 = sub(mul_hot(lam, sub(P.x, x3)), P.y);
     return Affine<F>{x3, y3};
-}
-
-// Bucket accumulation after `rounds` (0, 1, 2) pre-reduction rounds: see the layout above.
-template <class F>
-C12_HD Proj<F> msm_accumulate_reduced_body(uint32_t b, const uint32_t* start, const uint32_t* end, const uint32_t* vals, const Affine<F>* points,
-                                           uint32_t rounds, const uint32_t* o0, const Affine<F>* A0, const Affine<F>* A1)
-{
-    XYZZ<F> acc = xyzz_inf<F>();
-    const uint32_t lo = start[b], hi = end[b];
-    uint32_t p0 = 0;
-    if (rounds) {
-        p0 = ba_pairs0(hi - lo);
-        const uint32_t base0 = o0[b];
-        const Affine<F>* src = rounds == 2 ? A1 + (base0 + 1) / 2 : A0 + base0;
-        const uint32_t cnt = rounds == 2 ? p0 / 2 : p0;
-#pragma unroll 1
-        for (uint32_t i = 0; i < cnt; ++i) {
-            Affine<F> pt = src[i];
-            if (!affine_is_inf(pt)) xyzz_madd(acc, pt);
-        }
-        if (rounds == 2 && (p0 & 1u)) {
-            Affine<F> pt = A0[base0 + p0 - 1];
-            if (!affine_is_inf(pt)) xyzz_madd(acc, pt);
-        }
-    }
-#pragma unroll 1
-    for (uint32_t j = lo + 2 * p0; j < hi; ++j) {
-        Affine<F> pt = ba_fetch<F>(vals, points, j);
-        if (!affine_is_inf(pt)) xyzz_madd(acc, pt);
-    }
-    return xyzz_to_proj(acc);
 }
 
 // ---- bucket reduction:  S_w = sum_j (j + 1) B[j]  over the half buckets of window w ----------------------------------

@@ -13,7 +13,8 @@
 //   k_reduce_level0/k_reduce_level  multi-level running sums  sum_k k B_k  (upper levels lane-cooperative)
 //   k_reduce2         warp-shuffle tree sums of each level's segment sums
 //   k_finish          level recombination, Horner over windows (lane-cooperative doublings), normalisation, encoding
-// (optional, c12381_set_msm_batch_affine: k_ba_round pre-reduction rounds + k_accumulate_reduced instead of the chunked pair)
+// At large n the accumulation is preceded by batch-affine halving rounds of the bucket lists (k_ba_fwd / k_ba_inv / k_ba_bwd,
+// c12381_set_msm_batch_affine): k_accumulate then only walks what they leave, normally one sum per bucket.
 #pragma once
 #include "common.cuh"
 #include "scalar_mul.cuh"
@@ -83,97 +84,245 @@ __global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict_
 // defined once in msm_common.cu (kernels there are launched through these host functions)
 int launch_recode(const MsmPlan& pl, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s);
 int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s);
-// order[] = bucket ids sorted by decreasing size (one 8-bit radix pass on min(size, 255)); scratch: 4 * total + hist words
-int launch_bucket_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** order, cudaStream_t s);
-size_t bucket_order_scratch_words(const MsmPlan& pl);
 // chunking of the bucket lists: vstart[b] = first chunk of bucket b (total + 1 entries), vbucket[v] = bucket of chunk v,
 // order[] = chunk ids by decreasing length, padded with 0xffffffff up to pl.vmax
 int launch_chunk_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** vstart, uint32_t** vbucket,
                        uint32_t** order, cudaStream_t s);
 size_t chunk_order_scratch_words(const MsmPlan& pl);
 
-// p0 of every bucket: input of the exclusive scan that yields the A0 offsets (msm_common.cu)
-size_t ba_offsets_tile_words(const MsmPlan& pl);
-int launch_ba_offsets(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* o0, uint32_t* tile_sums, cudaStream_t s);
+// offsets of the bucket lists after every halving round (msm_common.cu): off[(r - 1) * (total + 1) + b] for r = 1 .. rounds,
+// total + 1 entries each (the last one is the round's slot count)
+size_t ba_plan_scratch_words(const MsmPlan& pl, uint32_t rounds);
+int launch_ba_plan(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s);
 
-// One pre-reduction round (msm_core.cuh "batch-affine pre-reduction"): thread t owns bucket order[t] and its k pairs.
-//   forward : running product of the k denominators, every prefix parked in `scratch` (slot i of thread t at [i * stride + t])
-//   block   : product tree over the 128 thread totals in shared memory, ONE inversion at the root, inverses pushed back down
-//   backward: unwind the prefixes -> 1 / den_i, finish each affine addition, write the result
-template <class F, int ROUND>
-__global__ void __launch_bounds__(128) k_ba_round(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                                  const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
-                                                  const uint32_t* __restrict__ order, const uint32_t* __restrict__ o0, Affine<F>* __restrict__ A0,
-                                                  Affine<F>* __restrict__ A1, F* __restrict__ scratch)
+// ---- batch-affine halving rounds (msm_core.cuh "batch-affine halving rounds") -----------------------------------------
+// k_ba_map (msm_common.cu, ONE launch for all rounds, scalar-only: it runs while the points are still being uploaded)
+// resolves every output slot of every round to the two inputs it adds: bucket search in the round's offsets, then either the
+// (term | sign) values of the sorted array (round 0) or positions in the previous round's list buffer.
+// One round is then three launches over the FLAT space of the round's output slots [off_out[b_lo], off_out[b_hi]):
+//   k_ba_fwd : warp w owns 32 J consecutive slots, lane l the slots  base + 32 i + l  (coalesced loads and stores).  A lane
+//              multiplies up the denominators of its J additions (prefixes parked in HBM, 48 B per slot); the 32 lane totals
+//              go through a 5-step shuffle butterfly that leaves in every lane the warp total AND the product of the OTHER
+//              lanes' totals; the warp total goes to the round's inversion pool.
+//   k_ba_inv : one thread per pool entry inverts it - all 32 lanes of a warp invert (SIMT makes one inversion cost a whole
+//              warp's issue slots, so they are pooled across the grid: one inversion per 32 J additions).
+//   k_ba_bwd : 1 / (lane total) = pool inverse x product of the others; the lane unwinds its prefixes (2 products per addition)
+//              and finishes each addition (lambda, lambda^2, y3).
+// Equal / opposite / identity operands are classified per pair (ba_denominator) and take no part in the inversion.
+// Pipelines run rounds apart from each other, and the slot numbering shrinks from round to round, so every pipeline keeps its
+// lists, prefixes and slot references in regions of its own, indexed from the start of ITS slot range; only the last round
+// writes in the global numbering (nothing reads that buffer before the pipelines have joined).
+constexpr uint32_t BA_MAX_ROUNDS = 16, BA_MAX_PIPES = 4, BA_NONE = 0xffffffffu;
+
+struct BaMapGeom {
+    const uint32_t* start;      // bucket lists in the sorted array
+    const uint32_t* end;
+    const uint32_t* off;        // off[(r - 1) * (total + 1) + b], r = 1 .. rounds (launch_ba_plan)
+    const uint32_t* vals;       // sorted (term | sign) values
+    uint2* refs;                // out: the two inputs of every slot (second = BA_NONE: the odd last entry of a list, carried over)
+    uint32_t total, rounds, pipes;
+    uint32_t b_lo[BA_MAX_PIPES + 1];                    // pipeline p owns buckets [b_lo[p], b_lo[p + 1])
+    uint32_t list_region[2][BA_MAX_PIPES];              // pipeline p's region in list buffer 0 / 1
+    uint32_t ref_region[BA_MAX_ROUNDS][BA_MAX_PIPES];   // where the slots of (round, pipeline) start in refs[]
+};
+int launch_ba_map(const BaMapGeom& g, uint32_t max_slots, cudaStream_t s);
+
+struct BaGeom {
+    const uint32_t* off_out;    // offsets of the round's OUTPUT lists (total + 1 entries): the slot numbering
+    const uint2* refs;          // this (round, pipeline)'s slot references
+    uint32_t b_lo, b_hi, J;
+    uint32_t out_region, scratch_region, last;
+};
+
+template <class F> struct BaIo {
+    const Affine<F>* pts;       // round 0: the parsed points (references are term | sign)
+    const Affine<F>* lists;     // rounds >= 1: the previous round's output (references are positions)
+    Affine<F>* out;
+    F* prefix;                  // per slot: running product of the lane's denominators up to and including this slot
+    F* pool;                    // per warp: total, replaced by its inverse (k_ba_inv)
+    F* others;                  // per lane: product of the other 31 lane totals
+};
+
+template <class F> __device__ __forceinline__ F shfl_xor_obj(const F& x, int mask)
 {
-    __shared__ F node[255];
-    const uint32_t tid = threadIdx.x, t = blockIdx.x * 128 + tid;
-    const size_t stride = (size_t)gridDim.x * 128;
-    uint32_t lo = 0, k = 0, base0 = 0;
-    if (t < total) {
-        const uint32_t b = order[t];
-        lo = start[b];
-        const uint32_t p0 = ba_pairs0(end[b] - lo);
-        k = ROUND == 0 ? p0 : p0 / 2;
-        base0 = o0[b];
-    }
-    const Affine<F>* in1 = A0 + base0;                                    // ROUND 1 reads round 0's results
-    Affine<F>* out = ROUND == 0 ? A0 + base0 : A1 + (base0 + 1) / 2;
-    F c = FieldOps<F>::one();
-#pragma unroll 1
-    for (uint32_t i = 0; i < k; ++i) {
-        Affine<F> P = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i) : in1[2 * i];
-        Affine<F> Q = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i + 1) : in1[2 * i + 1];
-        F den;
-        ba_denominator(P, Q, den);
-        c = mul_hot(c, den);
-        scratch[(size_t)i * stride + t] = c;
-    }
-    node[tid] = c;
-    uint32_t base = 0;
-#pragma unroll 1
-    for (uint32_t n = 64; n >= 1; n >>= 1) {         // level with n nodes from the 2n below it
-        __syncthreads();
-        if (tid < n) node[base + 2 * n + tid] = mul(node[base + 2 * tid], node[base + 2 * tid + 1]);
-        base += 2 * n;
-    }
-    __syncthreads();
-    if (tid == 0) node[254] = inv(node[254]);
-#pragma unroll 1
-    for (uint32_t n = 1; n <= 64; n <<= 1) {         // n parents hold inverses; give each child the inverse of its own product
-        base -= 2 * n;
-        __syncthreads();
-        if (tid < n) {
-            F iv = node[base + 2 * n + tid], a = node[base + 2 * tid], bb = node[base + 2 * tid + 1];
-            node[base + 2 * tid] = mul(iv, bb);
-            node[base + 2 * tid + 1] = mul(iv, a);
-        }
-    }
-    __syncthreads();
-    F iv = node[tid];                                // 1 / (den_0 ... den_(k-1)) of this thread
-#pragma unroll 1
-    for (uint32_t i = k; i-- > 0;) {
-        Affine<F> P = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i) : in1[2 * i];
-        Affine<F> Q = ROUND == 0 ? ba_fetch<F>(vals, pts, lo + 2 * i + 1) : in1[2 * i + 1];
-        F den;
-        const int kind = ba_denominator(P, Q, den);
-        F inv_den = i ? mul_hot(iv, scratch[(size_t)(i - 1) * stride + t]) : iv;
-        iv = mul_hot(iv, den);
-        out[i] = ba_finish(P, Q, kind, inv_den);
-    }
+    static_assert(sizeof(F) % 4 == 0, "word-sized objects only");
+    F r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(&x);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(F) / 4); ++i) d[i] = __shfl_xor_sync(0xffffffffu, s[i], mask);
+    return r;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_accumulate_reduced(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                                            const uint32_t* __restrict__ vals, const Affine<F>* __restrict__ pts,
-                                                            const uint32_t* __restrict__ order, uint32_t rounds, const uint32_t* __restrict__ o0,
-                                                            const Affine<F>* __restrict__ A0, const Affine<F>* __restrict__ A1,
-                                                            Proj<F>* __restrict__ buckets)
+#ifndef C12_BA_THREADS
+#define C12_BA_THREADS 128
+#endif
+#ifndef C12_BA_MIN_BLOCKS
+#define C12_BA_MIN_BLOCKS 3
+#endif
+#ifndef C12_BA2_MIN_BLOCKS
+#define C12_BA2_MIN_BLOCKS 2      // over Fp2 the unwinding pass holds twice the state: 168 registers spill, 255 do not
+#endif
+template <class F> struct BaShape {
+    static constexpr int MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? C12_BA_MIN_BLOCKS : C12_BA2_MIN_BLOCKS;
+};
+
+// the input a slot reference names, as a signed affine point
+template <class F, bool FIRST> __device__ __forceinline__ Affine<F> ba_input(const BaIo<F>& io, uint32_t ref)
 {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    uint32_t b = order[t];
-    buckets[b] = msm_accumulate_reduced_body<F>(b, start, end, vals, pts, rounds, o0, A0, A1);
+    if (!FIRST) return io.lists[ref];
+    Affine<F> pt = io.pts[ref & 0x7fffffffu];
+    if ((ref >> 31) && !affine_is_inf(pt)) pt.y = neg(pt.y);
+    return pt;
+}
+template <class F, bool FIRST> __device__ __forceinline__ const Affine<F>* ba_input_ptr(const BaIo<F>& io, uint32_t ref)
+{
+    return FIRST ? io.pts + (ref & 0x7fffffffu) : io.lists + ref;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// -DC12_BA_LOCKSTEP: the warps of a block walk the slot loops together (one barrier per slot, as k_accumulate does): the
+// unwinding pass is ~35 KB of straight-line products.  Every thread then stays in the loop for all J trips.
+#if defined(C12_BA_LOCKSTEP)
+#define C12_BA_ENTER(g, L)                  \
+    if (!ba_lane(g, L)) {                   \
+        L.count = 0;                        \
+        L.wl = 0;                           \
+    }
+#define C12_BA_TRIPS(g, L) (g).J
+#define C12_BA_STEP(i, L)     \
+    __syncthreads();          \
+    if ((i) >= (L).count) continue
+#define C12_BA_LEAVE(L) \
+    if ((L).n_slots <= (uint64_t)(L).gw * 32u * g.J) return
+#else
+#define C12_BA_ENTER(g, L) \
+    if (!ba_lane(g, L)) return
+#define C12_BA_TRIPS(g, L) (L).count
+#define C12_BA_STEP(i, L) ((void)0)
+#define C12_BA_LEAVE(L) ((void)0)
+#endif
+// slots of this lane: local indices  wl + 32 i + lane,  i < count  (wl = the warp's first local slot)
+struct BaLane {
+    uint32_t wl, count, gw, lane, n_slots, slot_lo;
+};
+__device__ __forceinline__ bool ba_lane(const BaGeom& g, BaLane& L)
+{
+    L.slot_lo = g.off_out[g.b_lo];
+    L.n_slots = g.off_out[g.b_hi] - L.slot_lo;
+    L.gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    L.lane = threadIdx.x & 31;
+    const uint64_t wl = (uint64_t)L.gw * 32u * g.J;
+    if (wl >= L.n_slots) return false;
+    L.wl = (uint32_t)wl;
+    const uint32_t left = L.n_slots - L.wl;
+    L.count = left > L.lane ? (left - L.lane + 31u) / 32u : 0u;
+    if (L.count > g.J) L.count = g.J;
+    return true;
+}
+
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(C12_BA_THREADS) k_ba_fwd(BaGeom g, BaIo<F> io)
+{
+    BaLane L;
+    C12_BA_ENTER(g, L);
+    const uint2* refs = g.refs + L.wl + L.lane;
+    F* prefix = io.prefix + g.scratch_region + L.wl + L.lane;
+    F c = FieldOps<F>::one();
+    // software pipeline: the references run two slots ahead, the x coordinates one slot ahead of the products
+    uint2 r1 = L.count > 0 ? refs[0] : make_uint2(0u, BA_NONE), r2 = L.count > 1 ? refs[32] : make_uint2(0u, BA_NONE);
+    F px = FieldOps<F>::zero(), qx = px;
+    if (L.count > 0 && r1.y != BA_NONE) {
+        px = ba_input_ptr<F, FIRST>(io, r1.x)->x;
+        qx = ba_input_ptr<F, FIRST>(io, r1.y)->x;
+    }
+#pragma unroll 1
+    for (uint32_t i = 0; i < C12_BA_TRIPS(g, L); ++i) {
+        C12_BA_STEP(i, L);
+        const uint2 r0 = r1;
+        const F px0 = px, qx0 = qx;
+        r1 = r2;
+        if (i + 2 < L.count) r2 = refs[(size_t)(i + 2) * 32u];
+        if (i + 1 < L.count && r1.y != BA_NONE) {
+            px = ba_input_ptr<F, FIRST>(io, r1.x)->x;
+            qx = ba_input_ptr<F, FIRST>(io, r1.y)->x;
+        }
+        if (r0.y != BA_NONE) {
+            // the common case needs the two x coordinates only; anything else (identity operands, equal x) is classified in full
+            F den = sub(qx0, px0);
+            bool use = !is_zero(den) && !is_zero(px0) && !is_zero(qx0);
+            if (!use) use = ba_denominator(ba_input<F, FIRST>(io, r0.x), ba_input<F, FIRST>(io, r0.y), den) < 2;
+            if (use) c = mul_hot(c, den);
+        }
+        prefix[(size_t)i * 32u] = c;
+    }
+    C12_BA_LEAVE(L);
+    // butterfly over the 32 lane totals: w = product of my group, o = product of everyone outside my lane
+    F w = c, o = FieldOps<F>::one();
+#pragma unroll 1
+    for (int k = 1; k < 32; k <<= 1) {
+        const F peer = shfl_xor_obj(w, k);
+        o = mul_hot(o, peer);
+        w = mul_hot(w, peer);
+    }
+    io.others[(size_t)L.gw * 32u + L.lane] = o;
+    if (L.lane == 0) io.pool[L.gw] = w;
+}
+
+template <class F> __global__ void __launch_bounds__(128) k_ba_inv(BaGeom g, F* pool)
+{
+    const uint32_t n_slots = g.off_out[g.b_hi] - g.off_out[g.b_lo];
+    const uint32_t t = blockIdx.x * 128 + threadIdx.x;
+    if ((uint64_t)t * 32u * g.J >= n_slots) return;
+    pool[t] = inv(pool[t]);
+}
+
+template <class F, bool FIRST>
+__global__ void __launch_bounds__(C12_BA_THREADS, BaShape<F>::MIN_BLOCKS) k_ba_bwd(BaGeom g, BaIo<F> io)
+{
+    BaLane L;
+    C12_BA_ENTER(g, L);
+    const uint2* refs = g.refs + L.wl + L.lane;
+    const F* prefix = io.prefix + g.scratch_region + L.wl + L.lane;
+    Affine<F>* out = io.out + (g.last ? L.slot_lo : g.out_region) + L.wl + L.lane;
+    F iv = FieldOps<F>::one();
+    if (L.count) iv = mul_hot(io.pool[L.gw], io.others[(size_t)L.gw * 32u + L.lane]);      // 1 / (this lane's total)
+    // the references run two slots ahead; the points of the next slot are pulled into L2 while this one is finished
+    uint2 r1 = L.count > 0 ? refs[(size_t)(L.count - 1) * 32u] : make_uint2(0u, BA_NONE);
+    uint2 r2 = L.count > 1 ? refs[(size_t)(L.count - 2) * 32u] : make_uint2(0u, BA_NONE);
+#pragma unroll 1
+    for (uint32_t i = C12_BA_TRIPS(g, L); i-- > 0;) {
+        C12_BA_STEP(i, L);
+        const uint2 r0 = r1;
+        r1 = r2;
+        if (i >= 2) r2 = refs[(size_t)(i - 2) * 32u];
+        if (i >= 1) {
+            const char* a = reinterpret_cast<const char*>(ba_input_ptr<F, FIRST>(io, r1.x));
+            prefetch_l2(a);
+            prefetch_l2(a + sizeof(Affine<F>) - 16);
+            if (FIRST && r1.y != BA_NONE) {      // later rounds: the partner is the next list entry, on the same or the following line
+                const char* b = reinterpret_cast<const char*>(ba_input_ptr<F, FIRST>(io, r1.y));
+                prefetch_l2(b);
+                prefetch_l2(b + sizeof(Affine<F>) - 16);
+            } else if (!FIRST) {
+                prefetch_l2(a + 2 * sizeof(Affine<F>) - 16);
+            }
+        }
+        const Affine<F> P = ba_input<F, FIRST>(io, r0.x);
+        if (r0.y == BA_NONE) {               // odd last entry of its list: carried over
+            out[(size_t)i * 32u] = P;
+            continue;
+        }
+        const Affine<F> Q = ba_input<F, FIRST>(io, r0.y);
+        F den;
+        const int kind = ba_denominator(P, Q, den);
+        F inv_den = iv;
+        if (kind < 2) {
+            if (i) inv_den = mul_hot(iv, prefix[(size_t)(i - 1) * 32u]);
+            iv = mul_hot(iv, den);
+        }
+        out[(size_t)i * 32u] = ba_finish(P, Q, kind, inv_den);
+    }
 }
 
 // Accumulation over CHUNKS of the bucket lists (virtual buckets): thread t takes chunk order[t] - chunks are visited in
@@ -199,7 +348,9 @@ template <class F> struct AccShape {
     static constexpr int THREADS = sizeof(F) == sizeof(Fp) ? 128 : 64, MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? 3 : C12_ACC2_MIN_BLOCKS;
 #endif
 };
-template <class F>
+// DIRECT: the lists are arrays of points already (the output of the batch-affine halving rounds: start[] / end[] are that
+// round's offsets), not (term | sign) values to be looked up in pts.
+template <class F, bool DIRECT>
 __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MIN_BLOCKS) k_accumulate(uint32_t vmax, uint32_t chunk, const uint32_t* __restrict__ start,
                                                     const uint32_t* __restrict__ end, const uint32_t* __restrict__ vals,
                                                     const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ order,
@@ -224,13 +375,13 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MIN_BLOCKS)
     __syncthreads();
     const uint32_t len = s_len;
     XYZZ<F> acc = xyzz_inf<F>();
-    uint32_t wnext = lo < hi ? vals[lo] : 0u;
+    uint32_t wnext = (!DIRECT && lo < hi) ? vals[lo] : 0u;
 #pragma unroll 1
     for (uint32_t i = 0; i < len; ++i) {
         __syncthreads();
         const uint32_t j = lo + i;
         if (j < hi) {
-            const uint32_t w = wnext;
+            const uint32_t w = DIRECT ? j : wnext;
             Affine<F> pt = pts[w & 0x7fffffffu];
 #if defined(C12_ACC_PREFETCH)
             // the index of the NEXT term is read one addition ahead and its point is pulled towards the SM while this one is added:
@@ -242,16 +393,17 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MIN_BLOCKS)
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + sizeof(Affine<F>) - 4));
             }
 #else
-            if (j + 1 < hi) wnext = vals[j + 1];
+            if (!DIRECT && j + 1 < hi) wnext = vals[j + 1];
 #endif
             if (!affine_is_inf(pt)) {
-                if (w >> 31) pt.y = neg(pt.y);
+                if (!DIRECT && (w >> 31)) pt.y = neg(pt.y);
                 xyzz_madd(acc, pt);
             }
         }
     }
     if (v != 0xffffffffu) vpartial[v] = xyzz_to_proj(acc);
 #else
+    static_assert(!DIRECT, "the direct lists need the lockstep build");
     if (t >= vmax) return;
     const uint32_t v = order[t];
     if (v == 0xffffffffu) return;                   // padding behind the last chunk
@@ -584,13 +736,81 @@ int sort_pairs_segmented(uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, 
                          uint32_t key_bits, uint32_t* hist, uint32_t* tile_sums, cudaStream_t s);
 size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words);
 
-// pre-reduction rounds for this plan: the context's setting (c12381_set_msm_batch_affine), none when the buckets are too
-// short for the rounds to pay for their launches
-inline uint32_t msm_ba_rounds(const MsmPlan& pl)
+// Schedule of the batch-affine halving rounds for this plan: how many rounds, which windows each pipeline owns, and for
+// every (round, pipeline) the slots per lane J and the launch bound in warps.  Everything is derived on the host from UPPER
+// bounds (a window holds at most pl.n entries; a round's slot count is at most entries / 2^r + one per bucket); the kernels read
+// the exact slot ranges from the offset arrays on the device.
+#ifndef C12_BA_AUTO_MIN_LOG
+#define C12_BA_AUTO_MIN_LOG 22      // automatic rounds only from 2^22 (term, window) entries on: below, a round's launches and its inversion latency cost more than they save
+#endif
+// Ctx::knob: [0] J is chosen so that a pipeline's round still spans about this many waves of resident warps; [1] its upper
+// limit; [2] the automatic round count stops this many halvings early - lists of a few entries are cheaper to finish with
+// XYZZ additions than with rounds that are all launch and inversion latency
+struct BaSchedule {
+    uint32_t rounds = 0, pipes = 1;
+    uint32_t b_lo[BA_MAX_PIPES + 1];
+    uint32_t J[BA_MAX_ROUNDS][BA_MAX_PIPES], warps[BA_MAX_ROUNDS][BA_MAX_PIPES];
+    uint32_t region[2][BA_MAX_PIPES];     // start of pipeline p's region in ping-pong buffer 0 (round-1 sized) / 1 (round-2 sized)
+    uint32_t ref_region[BA_MAX_ROUNDS][BA_MAX_PIPES];
+    size_t slots[3] = {0, 0, 0};          // sizes of the two ping-pong buffers ([1], [2]) and of the last round's output ([0])
+    size_t refs = 0;                      // slot references of all rounds
+    size_t pool_stride = 0;               // pool entries reserved per pipeline
+    uint32_t max_slots = 0;               // bound on the slot count of round 0 (the largest)
+};
+
+inline BaSchedule msm_ba_schedule(const MsmPlan& pl)
 {
-    uint32_t r = (uint32_t)ctx().ba_rounds;
-    if ((uint64_t)pl.n * pl.windows < 8ull * pl.total) return 0;
-    return r > 2 ? 2 : r;
+    BaSchedule sc;
+    const Ctx& c = ctx();
+    const uint64_t N = (uint64_t)pl.n * pl.windows;
+    if (c.ba_rounds == 0 || N >= (1ull << 31) || pl.total == 0) return sc;
+    uint32_t R = 0;
+    while (R < 12 && (1ull << R) * pl.total < 2 * N) ++R;      // lists of twice the mean load would end up as single sums
+    if (c.ba_rounds > 0)
+        R = (uint32_t)c.ba_rounds;
+    else if (N < (1ull << C12_BA_AUTO_MIN_LOG))
+        return sc;
+    else
+        R = R > (uint32_t)c.knob[2] ? R - (uint32_t)c.knob[2] : 0;
+    if (R == 0) return sc;
+    sc.rounds = R > BA_MAX_ROUNDS ? BA_MAX_ROUNDS : R;
+    sc.pipes = (uint32_t)c.ba_pipes < pl.windows ? (uint32_t)c.ba_pipes : pl.windows;
+    if (sc.pipes < 1) sc.pipes = 1;
+    const uint32_t resident = (uint32_t)(c.sm_count > 0 ? c.sm_count : 148) * (C12_BA_THREADS / 32) * C12_BA_MIN_BLOCKS;
+    for (uint32_t p = 0; p <= sc.pipes; ++p) sc.b_lo[p] = (pl.windows * p / sc.pipes) * pl.half;
+    // cap(k, p): bound on pipeline p's slot count in the numbering of round k (lists after k halvings)
+    auto cap = [&](uint32_t k, uint32_t p) {
+        const uint64_t wins = (sc.b_lo[p + 1] - sc.b_lo[p]) / pl.half;
+        return (size_t)((wins * pl.n) >> k) + (size_t)wins * pl.half + 1;
+    };
+    size_t ref_base = 0;
+    for (uint32_t r = 0; r < sc.rounds; ++r) {
+        size_t base = 0;
+        for (uint32_t p = 0; p < sc.pipes; ++p) {
+            const size_t slots = cap(r + 1, p);
+            const uint64_t jmax = c.knob[1] > 2 ? (uint64_t)c.knob[1] : 2;
+            uint64_t J = slots / (32ull * resident * (uint64_t)(c.knob[0] > 0 ? c.knob[0] : 1));
+            J = J < 2 ? 2 : (J > jmax ? jmax : J);
+            sc.J[r][p] = (uint32_t)J;
+            sc.warps[r][p] = (uint32_t)((slots + 32 * J - 1) / (32 * J));
+            if (sc.warps[r][p] + 1 > sc.pool_stride) sc.pool_stride = sc.warps[r][p] + 1;
+            sc.ref_region[r][p] = (uint32_t)(ref_base + base);
+            base += slots;
+        }
+        if (r == 0) sc.max_slots = (uint32_t)base;
+        ref_base += base;
+    }
+    sc.refs = ref_base;
+    for (uint32_t k = 1; k <= 2; ++k) {
+        size_t base = 0;
+        for (uint32_t p = 0; p < sc.pipes; ++p) {
+            sc.region[k - 1][p] = (uint32_t)base;
+            base += cap(k, p);
+        }
+        sc.slots[k] = base;
+    }
+    sc.slots[0] = (size_t)(N >> sc.rounds) + pl.total + 1;
+    return sc;
 }
 
 template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
@@ -603,17 +823,70 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
     b += 4 * align_up(4 * N);
     b += align_up(4 * hist_words) + align_up(4 * tile_words);
     b += 2 * align_up(4 * (size_t)pl.total);
-    b += align_up(4 * bucket_order_scratch_words(pl));
     b += align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
-    if (msm_ba_rounds(pl)) {
-        b += align_up(4 * ((size_t)pl.total + 1)) + align_up(4 * ba_offsets_tile_words(pl));
-        b += align_up(sizeof(Affine<F>) * (N / 2 + 1)) + align_up(sizeof(Affine<F>) * (N / 4 + 2));
-        b += align_up(sizeof(F) * BA_CAP * (size_t)cdiv(pl.total, 128) * 128);
+    const BaSchedule sc = msm_ba_schedule(pl);
+    if (sc.rounds) {
+        b += align_up(4 * (size_t)sc.rounds * ((size_t)pl.total + 1)) + align_up(4 * ba_plan_scratch_words(pl, sc.rounds));
+        b += align_up(sizeof(Affine<F>) * sc.slots[1]) + align_up(sizeof(Affine<F>) * sc.slots[2]) + align_up(sizeof(Affine<F>) * sc.slots[0]);
+        b += align_up(sizeof(F) * sc.slots[1]) + align_up(8 * sc.refs);
+        b += align_up(sizeof(F) * sc.pool_stride * sc.pipes) + align_up(sizeof(F) * sc.pool_stride * sc.pipes * 32);
     }
     b += align_up(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
     return b + 65536;
+}
+
+// the halving rounds of one MSM, enqueued behind everything already on `s` (pipeline 0 stays on `s`, the others fork onto the
+// context's side streams and join back); the slot references (launch_ba_map) are in place.  E[2] receives the reduced lists.
+template <class F>
+int msm_ba_rounds_run(const MsmPlan& pl, const BaSchedule& sc, const Affine<F>* pts, const uint32_t* off, const uint2* refs,
+                      Affine<F>* const E[3], F* prefix, F* pool, F* others, cudaStream_t s)
+{
+    Ctx& c = ctx();
+    if (sc.pipes > 1) {
+        C12_CUDA(cudaEventRecord(c.side_ev[0], s));
+        for (uint32_t p = 1; p < sc.pipes; ++p) C12_CUDA(cudaStreamWaitEvent(c.side[p - 1], c.side_ev[0], 0));
+    }
+    for (uint32_t r = 0; r < sc.rounds; ++r) {
+        for (uint32_t p = 0; p < sc.pipes; ++p) {
+            cudaStream_t sp = p ? c.side[p - 1] : s;
+            BaGeom g;
+            g.off_out = off + (size_t)r * (pl.total + 1);
+            g.refs = refs + sc.ref_region[r][p];
+            g.b_lo = sc.b_lo[p];
+            g.b_hi = sc.b_lo[p + 1];
+            g.J = sc.J[r][p];
+            g.last = r + 1 == sc.rounds ? 1u : 0u;
+            g.out_region = sc.region[r & 1][p];
+            g.scratch_region = sc.region[0][p];
+            BaIo<F> io;
+            io.pts = pts;
+            io.lists = r ? E[(r - 1) & 1] : nullptr;
+            io.out = g.last ? E[2] : E[r & 1];
+            io.prefix = prefix;
+            io.pool = pool + (size_t)p * sc.pool_stride;
+            io.others = others + (size_t)p * sc.pool_stride * 32;
+            const unsigned blocks = cdiv(sc.warps[r][p], C12_BA_THREADS / 32);
+            if (r == 0)
+                k_ba_fwd<F, true><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
+            else
+                k_ba_fwd<F, false><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
+            C12_LAUNCHED();
+            k_ba_inv<F><<<cdiv(sc.warps[r][p], 128), 128, 0, sp>>>(g, io.pool);
+            C12_LAUNCHED();
+            if (r == 0)
+                k_ba_bwd<F, true><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
+            else
+                k_ba_bwd<F, false><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
+            C12_LAUNCHED();
+        }
+    }
+    for (uint32_t p = 1; p < sc.pipes; ++p) {
+        C12_CUDA(cudaEventRecord(c.side_ev[p], c.side[p - 1]));
+        C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[p], 0));
+    }
+    return C12381_OK;
 }
 
 // scratch bound for an n-term MSM under the current window setting (callers arena_begin with at least this much)
@@ -662,20 +935,24 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* tiles = (uint32_t*)arena_take(4 * tile_words);
     uint32_t* start = (uint32_t*)arena_take(4 * (size_t)pl.total);
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)pl.total);
-    uint32_t* order_scratch = (uint32_t*)arena_take(4 * bucket_order_scratch_words(pl));
     uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));
     Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
-    const uint32_t ba_rounds = msm_ba_rounds(pl);
-    uint32_t *o0 = nullptr, *o0_tiles = nullptr;
-    Affine<F>*A0 = nullptr, *A1 = nullptr;
-    F* ba_scratch = nullptr;
-    if (ba_rounds) {
-        o0 = (uint32_t*)arena_take(4 * ((size_t)pl.total + 1));
-        o0_tiles = (uint32_t*)arena_take(4 * ba_offsets_tile_words(pl));
-        A0 = (Affine<F>*)arena_take(sizeof(Affine<F>) * (N / 2 + 1));
-        A1 = (Affine<F>*)arena_take(sizeof(Affine<F>) * (N / 4 + 2));
-        ba_scratch = (F*)arena_take(sizeof(F) * BA_CAP * (size_t)cdiv(pl.total, 128) * 128);
+    const BaSchedule sc = msm_ba_schedule(pl);
+    uint32_t *ba_off = nullptr, *ba_tiles = nullptr;
+    uint2* ba_refs = nullptr;
+    Affine<F>* ba_lists[3] = {nullptr, nullptr, nullptr};   // the two ping-pong buffers and the last round's output
+    F *ba_prefix = nullptr, *ba_pool = nullptr, *ba_others = nullptr;
+    if (sc.rounds) {
+        ba_off = (uint32_t*)arena_take(4 * (size_t)sc.rounds * ((size_t)pl.total + 1));
+        ba_tiles = (uint32_t*)arena_take(4 * ba_plan_scratch_words(pl, sc.rounds));
+        ba_lists[0] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[1]);
+        ba_lists[1] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[2]);
+        ba_lists[2] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[0]);
+        ba_prefix = (F*)arena_take(sizeof(F) * sc.slots[1]);
+        ba_refs = (uint2*)arena_take(8 * sc.refs);
+        ba_pool = (F*)arena_take(sizeof(F) * sc.pool_stride * sc.pipes);
+        ba_others = (F*)arena_take(sizeof(F) * sc.pool_stride * sc.pipes * 32);
     }
     Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
@@ -691,11 +968,33 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_CUDA(cudaEventRecord(c.pev[2], s));
     rc = launch_bucket_bounds(pl, keys, start, end, s);
     if (rc) return rc;
+    // the lists the accumulation walks: the sorted entries themselves, or what the halving rounds leave of them
+    const uint32_t *lstart = start, *lend = end;
+    if (sc.rounds) {
+        rc = launch_ba_plan(pl, start, end, sc.rounds, ba_off, ba_tiles, s);
+        if (rc) return rc;
+        lstart = ba_off + (size_t)(sc.rounds - 1) * (pl.total + 1);
+        lend = lstart + 1;
+        BaMapGeom mg;
+        mg.start = start;
+        mg.end = end;
+        mg.off = ba_off;
+        mg.vals = vals;
+        mg.refs = ba_refs;
+        mg.total = pl.total;
+        mg.rounds = sc.rounds;
+        mg.pipes = sc.pipes;
+        for (uint32_t p = 0; p <= sc.pipes; ++p) mg.b_lo[p] = sc.b_lo[p];
+        for (uint32_t p = 0; p < sc.pipes; ++p) {
+            mg.list_region[0][p] = sc.region[0][p];
+            mg.list_region[1][p] = sc.region[1][p];
+            for (uint32_t r = 0; r < sc.rounds; ++r) mg.ref_region[r][p] = sc.ref_region[r][p];
+        }
+        rc = launch_ba_map(mg, sc.max_slots, s);
+        if (rc) return rc;
+    }
     uint32_t *order = nullptr, *vstart = nullptr, *vbucket = nullptr;
-    if (msm_ba_rounds(pl))
-        rc = launch_bucket_order(pl, start, end, order_scratch, &order, s);
-    else
-        rc = launch_chunk_order(pl, start, end, chunk_scratch, &vstart, &vbucket, &order, s);
+    rc = launch_chunk_order(pl, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
     if (rc) return rc;
     if (points_ready) C12_CUDA(cudaStreamWaitEvent(s, points_ready, 0));
     C12_CUDA(cudaEventRecord(c.pev[3], s));
@@ -703,23 +1002,16 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
-    if (ba_rounds) {
-        rc = launch_ba_offsets(pl, start, end, o0, o0_tiles, s);
+    if (sc.rounds) {
+        rc = msm_ba_rounds_run<F>(pl, sc, pts, ba_off, ba_refs, ba_lists, ba_prefix, ba_pool, ba_others, s);
         if (rc) return rc;
-        k_ba_round<F, 0><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, o0, A0, A1, ba_scratch);
-        C12_LAUNCHED();
-        if (ba_rounds == 2) {
-            k_ba_round<F, 1><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, o0, A0, A1, ba_scratch);
-            C12_LAUNCHED();
-        }
-        k_accumulate_reduced<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, start, end, vals, pts, order, ba_rounds, o0, A0, A1, buckets);
-        C12_LAUNCHED();
+        k_accumulate<F, true><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, lstart, lend, nullptr, ba_lists[2], order, vbucket, vstart, vpartial);
     } else {
-        k_accumulate<F><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
-        C12_LAUNCHED();
-        k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, vstart, vpartial, buckets);
-        C12_LAUNCHED();
+        k_accumulate<F, false><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
     }
+    C12_LAUNCHED();
+    k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, vstart, vpartial, buckets);
+    C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));
     k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);

@@ -64,8 +64,14 @@ C12381_API int c12381_device(void);              /* bound device or -1 */
 C12381_API int c12381_sync_status(void* stream);
 /* testing/tuning knob: force the MSM window width (0 = automatic) */
 C12381_API void c12381_set_msm_window(int c);
-/* testing/tuning knob: batch-affine pre-reduction rounds before the bucket accumulation (0, 1 or 2; same results) */
+/* testing/tuning knob: batch-affine halving rounds of the bucket lists in front of the XYZZ accumulation
+ * (-1 = chosen from the bucket load, the default; 0 = none; k = k rounds; same results) */
 C12381_API void c12381_set_msm_batch_affine(int rounds);
+/* testing/tuning knob: independent pipelines (window groups on their own streams) the halving rounds are split into (1 .. 4) */
+C12381_API void c12381_set_msm_pipelines(int pipes);
+/* measurement knobs of the halving rounds (A/B runs; same results): id 0 = waves of resident warps a pipeline's round should
+ * span (slots per lane J follows), 1 = largest J, 2 = halvings left to the XYZZ accumulation by the automatic round count */
+C12381_API void c12381_set_knob(int id, int value);
 
 /* ---- multi-scalar multiplication ------------------------------------------------------------------------- */
 /* out = sum_i scalars[i] * points[i] over G1.

@@ -73,28 +73,41 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
             buckets[b] = msm_fold_body<F>(parts.data(), nch);
         }
     } else {
-        // the batch-affine pre-reduction rounds (k_ba_round), one inversion per pair here instead of one per block
-        std::vector<uint32_t> o0(pl.total + 1, 0);
-        for (uint32_t b = 0; b < pl.total; ++b) o0[b + 1] = o0[b] + ba_pairs0(end[b] - start[b]);
-        std::vector<Affine<F>> A0(o0[pl.total] + 1), A1(o0[pl.total] / 2 + 2);
-        for (uint32_t b = 0; b < pl.total; ++b) {
-            uint32_t p0 = ba_pairs0(end[b] - start[b]);
-            for (uint32_t i = 0; i < p0; ++i) {
-                Affine<F> X = ba_fetch<F>(sv.data(), P.data(), start[b] + 2 * i), Y = ba_fetch<F>(sv.data(), P.data(), start[b] + 2 * i + 1);
+        // the batch-affine halving rounds (k_ba_fwd / k_ba_inv / k_ba_bwd over the flat slot space), one inversion per pair here
+        // instead of one per 32 J additions; then the accumulation over what the rounds leave (k_accumulate<F, true>)
+        std::vector<std::vector<uint32_t>> off(rounds + 1, std::vector<uint32_t>(pl.total + 1, 0));
+        for (uint32_t r = 1; r <= rounds; ++r)
+            for (uint32_t b = 0; b < pl.total; ++b) off[r][b + 1] = off[r][b] + ba_len(end[b] - start[b], r);
+        std::vector<Affine<F>> cur, next;
+        for (uint32_t r = 0; r < rounds; ++r) {
+            const uint32_t* off_in = r ? off[r].data() : start.data();
+            const uint32_t* off_out = off[r + 1].data();
+            next.assign(off_out[pl.total], affine_inf<F>());
+            uint32_t hint = 0;
+            for (uint32_t slot = 0; slot < off_out[pl.total]; ++slot) {
+                const uint32_t b = ba_bucket_of(off_out, (slot & 7u) ? hint : 0u, pl.total, slot);   // with and without a hint
+                hint = b;
+                if (!(off_out[b] <= slot && slot < off_out[b + 1])) return -3;
+                const uint32_t ii = slot - off_out[b], len = ba_len(end[b] - start[b], r), in0 = off_in[b] + 2 * ii;
+                Affine<F> X = r ? cur[in0] : ba_fetch<F>(sv.data(), P.data(), in0);
+                if (2 * ii + 1 >= len) {
+                    next[slot] = X;
+                    continue;
+                }
+                Affine<F> Y = r ? cur[in0 + 1] : ba_fetch<F>(sv.data(), P.data(), in0 + 1);
                 F den;
                 int kind = ba_denominator(X, Y, den);
-                A0[o0[b] + i] = ba_finish(X, Y, kind, inv(den));
+                next[slot] = ba_finish(X, Y, kind, inv(den));
             }
-            if (rounds == 2)
-                for (uint32_t i = 0; i < p0 / 2; ++i) {
-                    Affine<F> X = A0[o0[b] + 2 * i], Y = A0[o0[b] + 2 * i + 1];
-                    F den;
-                    int kind = ba_denominator(X, Y, den);
-                    A1[(o0[b] + 1) / 2 + i] = ba_finish(X, Y, kind, inv(den));
-                }
+            cur.swap(next);
         }
-        for (uint32_t b = 0; b < pl.total; ++b)
-            buckets[b] = msm_accumulate_reduced_body<F>(b, start.data(), end.data(), sv.data(), P.data(), rounds, o0.data(), A0.data(), A1.data());
+        const uint32_t* lo = off[rounds].data();
+        for (uint32_t b = 0; b < pl.total; ++b) {
+            XYZZ<F> acc = xyzz_inf<F>();
+            for (uint32_t j = lo[b]; j < lo[b + 1]; ++j)
+                if (!affine_is_inf(cur[j])) xyzz_madd(acc, cur[j]);
+            buckets[b] = xyzz_to_proj(acc);
+        }
     }
     std::vector<Proj<F>> wsum(pl.windows);
     for (uint32_t w = 0; w < pl.windows; ++w) {

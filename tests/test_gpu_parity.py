@@ -84,12 +84,15 @@ def test_points_golden(cuda):
     ps.check_points(cuda)
 
 
-@pytest.fixture(params=[0, 1, 2], ids=["xyzz-only", "batch-affine-1", "batch-affine-2"])
+@pytest.fixture(params=[(0, 1), (1, 1), (3, 2), (9, 4)], ids=["xyzz-only", "batch-affine-1", "batch-affine-3x2", "batch-affine-9x4"])
 def ba_rounds(request):
+    """(forced batch-affine halving rounds, pipelines they are split into); -1 (the default) chooses from the bucket load"""
     from crypto12381_b200 import _lib
-    _lib.lib().c12381_set_msm_batch_affine(request.param)
+    _lib.lib().c12381_set_msm_batch_affine(request.param[0])
+    _lib.lib().c12381_set_msm_pipelines(request.param[1])
     yield request.param
-    _lib.lib().c12381_set_msm_batch_affine(0)
+    _lib.lib().c12381_set_msm_batch_affine(-1)
+    _lib.lib().c12381_set_msm_pipelines(2)
 
 
 def test_msm_golden_all_windows(cuda, ba_rounds):

@@ -187,8 +187,9 @@ def test_decompress_golden(golden_points):
 
 
 def test_msm_batch_affine_rounds(golden_msm):
-    """The batch-affine pre-reduction rounds (bodies of k_ba_round / k_accumulate_reduced) give the same sums, including on
-    repeated points, P and -P, identities and zero scalars; small windows make the bucket lists long enough to pair up."""
+    """The batch-affine halving rounds (the slot mapping and the pair bodies of k_ba_fwd / k_ba_bwd, then the accumulation over
+    the reduced lists) give the same sums, including on repeated points, P and -P, identities and zero scalars; small windows
+    make the bucket lists long enough for several rounds."""
     l = hm.lib()
     H = bytes.fromhex
     for case in golden_msm["cases"]:
@@ -196,7 +197,7 @@ def test_msm_batch_affine_rounds(golden_msm):
             continue
         g1 = case["group"] == "g1"
         pts = (hm.g1_fixed_base if g1 else hm.g2_fixed_base)(H(case["point_scalars"]))
-        for rounds in (1, 2):
+        for rounds in (1, 2, 5):
             for c in (2, 3, 5):
                 out = ctypes.create_string_buffer(49 if g1 else 97)
                 fn = l.hm_g1_msm_ba if g1 else l.hm_g2_msm_ba
@@ -205,7 +206,7 @@ def test_msm_batch_affine_rounds(golden_msm):
     for key, want in (("edge_g1", None), ("cancel_g1", bytes(49))):
         e = golden_msm[key]
         n = len(H(e["scalars"])) // 32
-        for rounds in (1, 2):
+        for rounds in (1, 3, 9):
             for c in (2, 4):
                 out = ctypes.create_string_buffer(49)
                 assert l.hm_g1_msm_ba(H(e["points"]), H(e["scalars"]), n, c, rounds, out) == 0
