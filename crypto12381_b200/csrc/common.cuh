@@ -14,7 +14,7 @@ namespace c12 {
 
 struct MsmStats {
     double accumulate_ms = 0, total_ms = 0;
-    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // recode, sort, bounds+order, parse, accumulate, reduce levels, reduce2, finish
+    double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // recode, sort, bounds+order, parse, accumulate, segment sums, plane sums, finish
     unsigned long long bucket_adds = 0;
     int window_bits = 0;
 };
@@ -48,7 +48,9 @@ struct Ctx {
     int forced_window = 0;
     int ba_rounds = -1;     // batch-affine halving rounds in front of the XYZZ accumulation: -1 = chosen from the bucket load, 0 = none, k = k rounds
     int ba_pipes = 2;       // independent round pipelines (groups of windows on their own streams: one's inversion kernel hides behind the other's additions)
-    int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation
+    int upload_groups = 2;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
+    cudaEvent_t group_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation, [3] threads the segment running sums of the bucket reduction should fill (0 = default)
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // streams of pipelines 1 .. 3 (pipeline 0 runs on the caller's stream)
     cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork + one join per side stream
     void* fb_table[2] = {nullptr, nullptr};   // fixed-base window tables (G1, G2), built on first use

@@ -188,6 +188,7 @@ int c12381_init(int device)
     C12_CUDA(cudaEventCreateWithFlags(&c.arena_ev, cudaEventDisableTiming));
     for (auto& st : c.side) C12_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& ev : c.side_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c.group_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
     C12_CUDA(cudaMalloc(&c.d_flags, 64 * sizeof(int)));
@@ -219,6 +220,8 @@ void c12381_shutdown(void)
     if (c.arena_ev) cudaEventDestroy(c.arena_ev);
     for (auto& ev : c.side_ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c.group_ev)
+        if (ev) cudaEventDestroy(ev);
     for (auto& st : c.side)
         if (st) cudaStreamDestroy(st);
     if (c.copy_stream) {
@@ -236,6 +239,7 @@ void c12381_set_msm_batch_affine(int rounds) { ctx().ba_rounds = rounds < 0 ? -1
 void c12381_set_knob(int id, int value)
 {
     if (id >= 0 && id < 4) ctx().knob[id] = value;
+    if (id == 4) ctx().upload_groups = value < 1 ? 1 : (value > 4 ? 4 : value);
 }
 void c12381_set_msm_pipelines(int pipes) { ctx().ba_pipes = pipes < 1 ? 1 : (pipes > 4 ? 4 : pipes); }
 unsigned long long c12381_launch_count(void) { return ctx().launches; }

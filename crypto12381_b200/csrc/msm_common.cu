@@ -10,14 +10,17 @@ __global__ void __launch_bounds__(128) k_recode(MsmPlan pl, const uint8_t* __res
                                                 uint32_t* __restrict__ vals, int* flags)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pl.n_in) return;
+    if (i >= pl.n_in) {
+        if (i < pl.groups * pl.n_group) msm_recode_pad_body(pl, i, keys, vals);
+        return;
+    }
     if (!scalar_is_canonical(scalar_from_be32(scalars + 32ull * i))) atomicOr(flags, FLAG_BAD_SCALAR);
     msm_recode_body(pl, i, scalars, keys, vals);
 }
 
 int launch_recode(const MsmPlan& pl, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s)
 {
-    k_recode<<<cdiv(pl.n_in, 128), 128, 0, s>>>(pl, d_scalars, keys, vals, flags);
+    k_recode<<<cdiv((size_t)pl.groups * pl.n_group, 128), 128, 0, s>>>(pl, d_scalars, keys, vals, flags);
     C12_LAUNCHED();
     return C12381_OK;
 }

@@ -24,17 +24,8 @@
 
 namespace c12 {
 
-constexpr uint32_t MSM_MAX_LEVELS = 8;
-#ifndef C12_MSM_LEVEL_LOG
-#define C12_MSM_LEVEL_LOG 3
-#endif
-#ifndef C12_MSM_REDUCE2_SPLIT
-#define C12_MSM_REDUCE2_SPLIT 8
-#endif
-constexpr uint32_t MSM_LEVEL_LOG = C12_MSM_LEVEL_LOG;
-constexpr uint32_t MSM_LEVEL_LEN = 1u << MSM_LEVEL_LOG;   // segment length of reduction levels >= 1 (a power of two)
-constexpr uint32_t MSM_REDUCE2_SPLIT = C12_MSM_REDUCE2_SPLIT;  // tree-sum jobs per window over the level-0 sums (a power of two <= 32)
-constexpr uint32_t MSM_WPART_SLOTS = MSM_REDUCE2_SPLIT + MSM_MAX_LEVELS;
+constexpr uint32_t MSM_MAX_PLANES = 16;      // bit planes of the segment index: at most 2^15 buckets per window / 1 per segment
+constexpr uint32_t MSM_WPART_SLOTS = MSM_MAX_PLANES + 1;
 
 struct MsmPlan {
     uint32_t n;           // terms fed to the bucket pipeline = parts * n_in
@@ -45,14 +36,17 @@ struct MsmPlan {
     uint32_t half;        // 2^(c-1) buckets per window
     uint32_t total;       // W * half
     uint32_t seg_len;     // buckets per level-0 reduction thread (a power of two)
-    uint32_t segs;        // segments per window = ceil(half / seg_len) = count[1]
-    // multi-level bucket reduction: level k turns count[k] entries per window into count[k+1] (sum, total) pairs
-    uint32_t levels;
-    uint32_t count[MSM_MAX_LEVELS + 1];
+    uint32_t segs;        // segments per window = ceil(half / seg_len)
+    uint32_t plane_bits;  // bits of a segment index: the segment totals are summed once per bit plane (see "bucket reduction")
     // bucket lists longer than `chunk` entries are accumulated by several threads (one per chunk) and folded afterwards:
     // bounds the serial chain of a thread under skewed scalars and evens out the load at large n
     uint32_t chunk;       // entries per accumulation thread, a power of two in [32, 256]
     uint32_t vmax;        // upper bound on the number of chunks (virtual buckets): total + n W / chunk
+    // upload groups (msm_list_plan): the terms are cut into `groups` runs of n_group consecutive terms, and every
+    // (group, window) pair is a sort segment with buckets of its own - "virtual windows" group * real_windows + w - so the
+    // bucket lists of a group need only that group's points (the host entry uploads the points group by group while the
+    // earlier groups are already being added up).  The groups' buckets are merged after the accumulation (k_fold).
+    uint32_t groups, n_group, real_windows;
 };
 
 // Window width for n pipeline terms of `bits`-bit pieces (256: unsplit scalars < r; 128: GLV halves; 64: GLS quarters),
@@ -87,23 +81,17 @@ inline uint32_t msm_choose_window(uint64_t n, uint32_t bits = 256)
     return best;
 }
 
-// fills seg_len / segs / levels / count[] for a level-0 segment length (a power of two <= half)
+// fills seg_len / segs / plane_bits for a segment length (a power of two <= half)
 inline void msm_plan_levels(MsmPlan& pl, uint32_t seg_len)
 {
     pl.seg_len = seg_len;
     pl.segs = (pl.half + seg_len - 1) / seg_len;
-    for (uint32_t k = 0; k <= MSM_MAX_LEVELS; ++k) pl.count[k] = 1;
-    pl.count[0] = pl.half;
-    pl.count[1] = pl.segs;
-    pl.levels = 1;
-    while (pl.count[pl.levels] > 1 && pl.levels < MSM_MAX_LEVELS) {
-        pl.count[pl.levels + 1] = (pl.count[pl.levels] + MSM_LEVEL_LEN - 1) / MSM_LEVEL_LEN;
-        ++pl.levels;
-    }
+    pl.plane_bits = 0;
+    while ((1u << pl.plane_bits) < pl.segs) ++pl.plane_bits;
 }
 
 // n_in caller terms; every scalar is split into `parts` (1, 2 or 4) signed pieces of 256 / parts bits
-inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, uint32_t parts = 1)
+inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, uint32_t parts = 1, uint32_t seg_wave = 0)
 {
     MsmPlan pl;
     pl.n_in = n_in;
@@ -117,8 +105,9 @@ inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, uint32_t parts = 1)
 #ifndef C12_MSM_SEG_WAVE
 #define C12_MSM_SEG_WAVE 49152u
 #endif
-    uint32_t seg = 4;
-    while (seg < 64 && pl.total / seg > C12_MSM_SEG_WAVE) seg <<= 1;
+    if (!seg_wave) seg_wave = C12_MSM_SEG_WAVE;
+    uint32_t seg = 2;
+    while (seg < 64 && pl.total / seg > seg_wave) seg <<= 1;
     if (seg > pl.half) seg = pl.half;
     msm_plan_levels(pl, seg);
     const uint64_t N = (uint64_t)pl.n * pl.windows;
@@ -126,7 +115,29 @@ inline MsmPlan msm_make_plan(uint32_t n_in, uint32_t c, uint32_t parts = 1)
     while (chunk < 256 && (uint64_t)chunk * pl.total < 2 * N) chunk <<= 1;      // about twice the mean bucket load
     pl.chunk = chunk;
     pl.vmax = pl.total + (uint32_t)(N / chunk) + 1;
+    pl.groups = 1;
+    pl.n_group = n_in;
+    pl.real_windows = pl.windows;
     return pl;
+}
+
+// the plan of the LIST side of the pipeline (recode, sort, bucket bounds, halving rounds, accumulation) for `groups` upload
+// groups: windows / total / n describe the virtual windows and the entries per sort segment; the reduction keeps the plain plan
+inline MsmPlan msm_list_plan(const MsmPlan& pl, uint32_t groups)
+{
+    MsmPlan lp = pl;
+    if (groups <= 1) return lp;
+    lp.groups = groups;
+    lp.n_group = (pl.n_in + groups - 1) / groups;
+    lp.n = pl.parts * lp.n_group;
+    lp.windows = pl.windows * groups;
+    lp.total = lp.windows * pl.half;
+    const uint64_t N = (uint64_t)lp.n * lp.windows;
+    uint32_t chunk = 32;
+    while (chunk < 256 && (uint64_t)chunk * lp.total < 2 * N) chunk <<= 1;
+    lp.chunk = chunk;
+    lp.vmax = lp.total + (uint32_t)(N / chunk) + 1;
+    return lp;
 }
 
 C12_HD uint32_t msm_invalid_key(const MsmPlan& pl) { return pl.half; }
@@ -394,6 +405,9 @@ template <> struct MsmTraits<Fp2> {
 C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalars_be32, uint32_t* keys, uint32_t* vals)
 {
     Scalar256 s = scalar_from_be32(scalars_be32 + 32ull * i);
+    // segment of (group, window w) = virtual window group * real_windows + w; the term's place inside its group's segments
+    const uint32_t grp = i / pl.n_group, li = i - grp * pl.n_group;
+    const uint64_t seg0 = (uint64_t)grp * pl.real_windows;
     if (pl.parts > 1) {
         ScalarParts sp;
         msm_split(s, pl.parts, sp);
@@ -401,7 +415,7 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
             const uint32_t sgn = sp.neg[part];
             const uint32_t idx = i + part * pl.n_in;
             uint32_t carry = 0;
-            for (uint32_t w = 0; w < pl.windows; ++w) {
+            for (uint32_t w = 0; w < pl.real_windows; ++w) {
                 uint32_t d = limbs_bits<4>(sp.mag[part], w * pl.c, pl.c) + carry;
                 uint32_t neg = 0;
                 carry = 0;
@@ -410,7 +424,7 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
                     neg = 1;
                     carry = 1;
                 }
-                uint64_t o = (uint64_t)w * pl.n + idx;
+                uint64_t o = (seg0 + w) * pl.n + (uint64_t)part * pl.n_group + li;
                 if (d == 0) {
                     keys[o] = msm_invalid_key(pl);
                     vals[o] = idx;
@@ -423,7 +437,7 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
         return;
     }
     uint32_t carry = 0;
-    for (uint32_t w = 0; w < pl.windows; ++w) {
+    for (uint32_t w = 0; w < pl.real_windows; ++w) {
         uint32_t d = scalar_bits(s, w * pl.c, pl.c) + carry;
         uint32_t neg = 0;
         carry = 0;
@@ -432,7 +446,7 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
             neg = 1;
             carry = 1;
         }
-        uint64_t o = (uint64_t)w * pl.n + i;
+        uint64_t o = (seg0 + w) * pl.n + li;
         if (d == 0) {
             keys[o] = msm_invalid_key(pl);
             vals[o] = i;
@@ -441,6 +455,18 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
             vals[o] = i | (neg << 31);
         }
     }
+}
+
+// the unused tail of the last group's segments (n_in is not a multiple of the group count): entries that own no bucket
+C12_HD void msm_recode_pad_body(const MsmPlan& pl, uint32_t i, uint32_t* keys, uint32_t* vals)
+{
+    const uint32_t grp = i / pl.n_group, li = i - grp * pl.n_group;
+    for (uint32_t part = 0; part < pl.parts; ++part)
+        for (uint32_t w = 0; w < pl.real_windows; ++w) {
+            const uint64_t o = ((uint64_t)grp * pl.real_windows + w) * pl.n + (uint64_t)part * pl.n_group + li;
+            keys[o] = msm_invalid_key(pl);
+            vals[o] = 0;
+        }
 }
 
 // Body of the bucket-accumulation kernel for one chunk [lo, hi) of a bucket's sorted list: sum of its (signed) affine terms.
@@ -546,29 +572,18 @@ template <class F> C12_HD Affine<F> ba_finish(const Affine<F>& P, const Affine<F
 }
 
 // ---- bucket reduction:  S_w = sum_j (j + 1) B[j]  over the half buckets of window w ----------------------------------
-// Level 0 cuts the buckets into segments of L_0 = seg_len: segment t yields sum0_t = sum_i (i + 1) B[t L_0 + i] and the
-// plain total R1[t], so  S_w = sum_t sum0_t + L_0 sum_t t R1[t].  The second term is the same problem on the (8 x shorter)
-// array R1 with weights starting at 0; level k >= 1 cuts R_k into segments of 8 and yields sum_k,u = sum_i i R_k[8u + i]
-// and totals R_(k+1)[u].  With s_k = sum over the segments of level k:
-//     S_w = s_0 + L_0 (s_1 + 8 (s_2 + 8 (s_3 + ...)))
-// i.e. two additions per entry per level, no scalar multiplications, and only doublings to recombine.
-// Offsets (in points) of the per-level arrays inside the reduction scratch: sums of level k hold W * count[k+1] points,
-// totals feeding level k >= 1 hold W * count[k].
-C12_HD size_t msm_sums_offset(const MsmPlan& pl, uint32_t k)
-{
-    size_t o = 0;
-    for (uint32_t j = 0; j < k; ++j) o += (size_t)pl.windows * pl.count[j + 1];
-    return o;
-}
-C12_HD size_t msm_runs_offset(const MsmPlan& pl, uint32_t k)   // k >= 1
-{
-    size_t o = msm_sums_offset(pl, pl.levels);
-    for (uint32_t j = 1; j < k; ++j) o += (size_t)pl.windows * pl.count[j];
-    return o;
-}
-C12_HD size_t msm_reduce_scratch_points(const MsmPlan& pl) { return msm_runs_offset(pl, pl.levels + 1); }
+// The buckets are cut into segments of L = seg_len: segment t yields sum0[t] = sum_i (i + 1) B[t L + i] by a running sum and the
+// plain total run1[t], so  S_w = sum_t sum0[t] + L sum_t t run1[t].  The second term is a sum with SMALL INTEGER weights, and
+// those are taken bit by bit:  sum_t t run1[t] = sum_j 2^j P_j  with  P_j = the sum of the totals whose segment index has bit j
+// set - plane_bits independent tree sums (plus one for sum_t sum0[t]) instead of a chain of ever shorter running-sum levels,
+// and a Horner recombination of plane_bits + log2 L doublings per window:
+//     S_w = T + L (P_0 + 2 (P_1 + 2 (P_2 + ...))),   T = sum_t sum0[t]
+// Layout of the reduction scratch (in points): sum0 of window w at [w segs, (w + 1) segs), run1 behind all the sum0's.
+C12_HD size_t msm_sum0_offset(const MsmPlan& pl, uint32_t w) { return (size_t)w * pl.segs; }
+C12_HD size_t msm_run1_offset(const MsmPlan& pl, uint32_t w) { return (size_t)(pl.windows + w) * pl.segs; }
+C12_HD size_t msm_reduce_scratch_points(const MsmPlan& pl) { return 2 * (size_t)pl.windows * pl.segs; }
 
-// one segment [lo, hi) of one level: sum = sum_i (i + w0) in[lo + i]  (w0 = 1 at level 0, 0 above), run = sum_i in[lo + i]
+// one segment [lo, hi): sum = sum_i (i + w0) in[lo + i]  (w0 = 1: the weights start at 1), run = sum_i in[lo + i]
 template <class F>
 C12_HD void msm_reduce_level_body(const Proj<F>* in, uint32_t lo, uint32_t hi, uint32_t w0, Proj<F>& sum, Proj<F>& run)
 {
@@ -581,18 +596,29 @@ C12_HD void msm_reduce_level_body(const Proj<F>* in, uint32_t lo, uint32_t hi, u
     }
 }
 
-// S_w from the per-level sums s_0 .. s_(levels-1) of one window
-template <class F> C12_HD Proj<F> msm_combine_levels_body(const MsmPlan& pl, const Proj<F>* s)
+// plane j of one window: j < plane_bits: the totals whose segment index has bit j set; j = plane_bits: all the sum0's
+// (the slice of entries t = first, first + stride, ... : the kernel's threads take one slice each and tree-sum the results)
+template <class F>
+C12_HD Proj<F> msm_plane_slice_body(const MsmPlan& pl, const Proj<F>* sum0, const Proj<F>* run1, uint32_t j, uint32_t first, uint32_t stride)
 {
-    Proj<F> acc = s[pl.levels - 1];
+    Proj<F> acc = proj_inf<F>();
+    const bool all = j == pl.plane_bits;
 #pragma unroll 1
-    for (uint32_t k = pl.levels - 1; k > 0; --k) {
-        uint32_t len = k - 1 == 0 ? pl.seg_len : MSM_LEVEL_LEN;   // L_(k-1)
-#pragma unroll 1
-        for (; len > 1; len >>= 1) acc = proj_dbl(acc);
-        acc = proj_add(acc, s[k - 1]);
-    }
+    for (uint32_t t = first; t < pl.segs; t += stride)
+        if (all || ((t >> j) & 1u)) acc = proj_add(acc, all ? sum0[t] : run1[t]);
     return acc;
+}
+
+// S_w from the planes of one window: planes[0 .. plane_bits - 1] = P_j, planes[plane_bits] = T
+template <class F> C12_HD Proj<F> msm_combine_planes_body(const MsmPlan& pl, const Proj<F>* planes)
+{
+    if (pl.plane_bits == 0) return planes[0];
+    Proj<F> acc = planes[pl.plane_bits - 1];
+#pragma unroll 1
+    for (uint32_t j = pl.plane_bits - 1; j > 0; --j) acc = proj_add(proj_dbl(acc), planes[j - 1]);
+#pragma unroll 1
+    for (uint32_t len = pl.seg_len; len > 1; len >>= 1) acc = proj_dbl(acc);
+    return proj_add(acc, planes[pl.plane_bits]);
 }
 
 // Horner over window sums S_w (w = W-1 .. 0): acc = 2^c acc + S_w

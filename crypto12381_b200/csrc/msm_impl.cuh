@@ -10,9 +10,9 @@
 //   k_parse_points    wire bytes -> Montgomery affine points + endomorphism images (canonical + on-curve checks)
 //   k_accumulate      one thread per chunk: XYZZ mixed additions of its terms         <- the dominant kernel
 //   k_fold            partial sums of a bucket's chunks -> the bucket
-//   k_reduce_level0/k_reduce_level  multi-level running sums  sum_k k B_k  (upper levels lane-cooperative)
-//   k_reduce2         warp-shuffle tree sums of each level's segment sums
-//   k_finish          level recombination, Horner over windows (lane-cooperative doublings), normalisation, encoding
+//   k_reduce_level0   running sums over segments of the buckets:  sum_i (i + 1) B_i  and the plain total of each segment
+//   k_reduce_planes   one tree sum per bit plane of the segment index over the totals (+ one over the segment sums)
+//   k_finish          plane recombination, Horner over windows (lane-cooperative doublings), normalisation, encoding
 // At large n the accumulation is preceded by batch-affine halving rounds of the bucket lists (k_ba_fwd / k_ba_inv / k_ba_bwd,
 // c12381_set_msm_batch_affine): k_accumulate then only walks what they leave, normally one sum per bucket.
 #pragma once
@@ -70,11 +70,11 @@ template <class F> __device__ Proj<F> block_sum_256(Proj<F> acc)
 }
 
 template <class F>
-__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t n, uint32_t parts, Affine<F>* __restrict__ pts,
-                                                      int* flags)
+__global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict__ bytes, uint32_t first, uint32_t last, uint32_t n, uint32_t parts,
+                                                      Affine<F>* __restrict__ pts, int* flags)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;      // terms [first, last) of n: one upload group
+    if (i >= last) return;
     Affine<F> p;
     if (!Wire<F>::parse(p, bytes + (size_t)Wire<F>::AFFINE * i)) atomicOr(flags, FLAG_BAD_POINT);
     pts[i] = p;
@@ -415,14 +415,21 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MIN_BLOCKS)
 #endif
 }
 
+// bucket b = the partial sums of its chunks, over all upload groups (group g's copy of the bucket is list g * total + b)
 template <class F>
-__global__ void __launch_bounds__(128) k_fold(uint32_t total, const uint32_t* __restrict__ vstart, const Proj<F>* __restrict__ vpartial,
+__global__ void __launch_bounds__(128) k_fold(uint32_t total, uint32_t groups, const uint32_t* __restrict__ vstart, const Proj<F>* __restrict__ vpartial,
                                               Proj<F>* __restrict__ buckets)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total) return;
     const uint32_t v0 = vstart[b];
-    buckets[b] = msm_fold_body<F>(vpartial + v0, vstart[b + 1] - v0);
+    Proj<F> acc = msm_fold_body<F>(vpartial + v0, vstart[b + 1] - v0);
+#pragma unroll 1
+    for (uint32_t g = 1; g < groups; ++g) {
+        const uint32_t v = vstart[g * total + b];
+        acc = proj_add(acc, msm_fold_body<F>(vpartial + v, vstart[g * total + b + 1] - v));
+    }
+    buckets[b] = acc;
 }
 
 // level 0 of the bucket reduction: one thread per (window, segment of seg_len buckets)
@@ -436,8 +443,8 @@ __global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? 3 : 1) k_reduce
     if (hi > pl.half) hi = pl.half;
     Proj<F> sum, run;
     msm_reduce_level_body<F>(buckets + (size_t)w * pl.half, lo, hi, 1u, sum, run);
-    scratch[msm_sums_offset(pl, 0) + (size_t)w * pl.segs + t] = sum;
-    scratch[msm_runs_offset(pl, 1) + (size_t)w * pl.segs + t] = run;
+    scratch[msm_sum0_offset(pl, w) + t] = sum;
+    scratch[msm_run1_offset(pl, w) + t] = run;
 }
 
 // ---- lane-cooperative point arithmetic (the serial tail of an MSM) -------------------------------------------------
@@ -506,52 +513,67 @@ template <class F> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& 
     return Proj<F>{sub(n[1], n[0]), add(n[2], n[3]), add(n[5], n[4])};
 }
 
-// levels >= 1 of the bucket reduction: a group of 8 lanes per (window, segment of 8 totals) - these levels are short
-// dependent chains over few items, so latency (not throughput) is what counts
-template <class F>
-__global__ void __launch_bounds__(128) k_reduce_level(MsmPlan pl, uint32_t k, Proj<F>* __restrict__ scratch)
+// Sum of one value per thread over a block of THREADS (128 or 256), built for LATENCY: a thread's own complete addition is
+// a chain of 14 dependent products (~14 us with one or two warps per scheduler), the lane-cooperative one ~3 us.  Two shuffle
+// levels on whole threads (32 -> 8 per warp), then the remaining levels on groups of 8 lanes through shared memory.  Fixed
+// tree: deterministic.  Result in sh[0] after the call (all threads must call; sh holds THREADS / 4 points).
+template <class F, int THREADS> __device__ void block_sum_coop(Proj<F> acc, Proj<F>* sh)
 {
-    const uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    const uint32_t count = pl.count[k], next = pl.count[k + 1];
-    if (g >= next) return;
-    const uint32_t w = blockIdx.y;
-    const uint32_t mask = 0xffu << (threadIdx.x & 24);
-    const Proj<F>* in = scratch + msm_runs_offset(pl, k) + (size_t)w * count;
-    uint32_t lo = g * MSM_LEVEL_LEN, hi = lo + MSM_LEVEL_LEN;
-    if (hi > count) hi = count;
-    Proj<F> run = proj_inf<F>(), sum = proj_inf<F>();
+    const uint32_t tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    acc = proj_add(acc, shfl_down_obj(acc, 16));
+    acc = proj_add(acc, shfl_down_obj(acc, 8));
+    if (lane < 8) sh[w * 8 + lane] = acc;
+    __syncthreads();
+    const uint32_t g = tid >> 3, mask = 0xffu << (tid & 24);
 #pragma unroll 1
-    for (uint32_t j = hi; j > lo; --j) {
-        run = coop_add(run, in[j - 1], mask);
-        if (j - 1 > lo) sum = coop_add(sum, run, mask);
-    }
-    if ((threadIdx.x & 7) == 0) {
-        scratch[msm_sums_offset(pl, k) + (size_t)w * next + g] = sum;
-        scratch[msm_runs_offset(pl, k + 1) + (size_t)w * next + g] = run;
+    for (uint32_t n = THREADS / 8; n >= 1; n >>= 1) {
+        if (g < n) {
+            const Proj<F> r = coop_add(sh[g], sh[g + n], mask);
+            if ((tid & 7) == 0) sh[g] = r;
+        }
+        __syncthreads();
     }
 }
 
-// tree sums of the per-level sums: block (w, y) -> wpart[w][y].  y < MSM_REDUCE2_SPLIT: a slice of the level-0 sums;
-// y = MSM_REDUCE2_SPLIT + k - 1: all sums of level k >= 1.
+// the bit planes of the segment index (msm_core.cuh "bucket reduction"): blocks (j, w, z < splits) tree-sum plane j of window w
+// (j = plane_bits: the sum of all sum0's, twice the entries, twice the blocks); the block that finishes last adds up the
+// partials in block order -> planes[w][j].  Every plane is an independent sum: one launch, all in parallel, and sized to be
+// resident at once (two blocks per SM: 256 threads at 128 registers over Fp, 128 threads at 255 over Fp2).
+template <class F> struct PlaneShape {
+    static constexpr int THREADS = sizeof(F) == sizeof(Fp) ? 256 : 128;
+    static constexpr uint32_t SPLITS = sizeof(F) == sizeof(Fp) ? 2 : 4;      // blocks per bit plane (the plane of the sum0's takes twice as many)
+};
 template <class F>
-__global__ void __launch_bounds__(256) k_reduce2(MsmPlan pl, const Proj<F>* __restrict__ scratch, Proj<F>* __restrict__ wpart)
+__global__ void __launch_bounds__(PlaneShape<F>::THREADS, 2) k_reduce_planes(MsmPlan pl, const Proj<F>* __restrict__ scratch, Proj<F>* __restrict__ parts,
+                                                                            uint32_t* __restrict__ tickets, Proj<F>* __restrict__ planes)
 {
-    const uint32_t w = blockIdx.x, y = blockIdx.y;
-    uint32_t k = 0, lo = 0, hi;
-    if (y < MSM_REDUCE2_SPLIT) {
-        uint32_t chunk = (pl.count[1] + MSM_REDUCE2_SPLIT - 1) / MSM_REDUCE2_SPLIT;
-        lo = y * chunk;
-        hi = lo + chunk;
-        if (hi > pl.count[1]) hi = pl.count[1];
-    } else {
-        k = y - MSM_REDUCE2_SPLIT + 1;
-        hi = pl.count[k + 1];
+    constexpr int THREADS = PlaneShape<F>::THREADS;
+    constexpr uint32_t SPLITS = PlaneShape<F>::SPLITS;
+    __shared__ Proj<F> sh[THREADS / 4];
+    __shared__ uint32_t s_last;
+    const uint32_t j = blockIdx.x, w = blockIdx.y, z = blockIdx.z;
+    const uint32_t splits = j == pl.plane_bits ? 2 * SPLITS : SPLITS;
+    if (z >= splits) return;
+    Proj<F> acc = msm_plane_slice_body<F>(pl, scratch + msm_sum0_offset(pl, w), scratch + msm_run1_offset(pl, w), j, z * THREADS + threadIdx.x,
+                                          splits * THREADS);
+    block_sum_coop<F, THREADS>(acc, sh);
+    const size_t slot = (size_t)w * MSM_WPART_SLOTS + j;
+    Proj<F>* mine = parts + slot * (2 * SPLITS);
+    if (threadIdx.x == 0) {
+        mine[z] = sh[0];
+        __threadfence();
+        s_last = atomicAdd(&tickets[slot], 1u) == splits - 1 ? 1u : 0u;
     }
-    const Proj<F>* in = scratch + msm_sums_offset(pl, k) + (size_t)w * pl.count[k + 1];
-    Proj<F> acc = proj_inf<F>();
-    for (uint32_t t = lo + threadIdx.x; t < hi; t += 256) acc = proj_add(acc, in[t]);
-    acc = block_sum_256(acc);
-    if (threadIdx.x == 0) wpart[(size_t)w * MSM_WPART_SLOTS + y] = acc;
+    __syncthreads();
+    if (!s_last || threadIdx.x >= 8) return;
+    __threadfence();
+    Proj<F> sum = mine[0];
+#pragma unroll 1
+    for (uint32_t k = 1; k < splits; ++k) sum = coop_add(sum, mine[k], 0xffu);
+    if (threadIdx.x == 0) {
+        planes[slot] = sum;
+        tickets[slot] = 0;          // ready for the next call on this arena layout
+    }
 }
 
 template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, int out_mode)
@@ -563,34 +585,28 @@ template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, i
         Wire<F>::compress(out, a);
 }
 
-// One block of 8 warps.  Warp v, for windows v, v + 8, ...: merges the level-0 slices (shuffle tree) and recombines the
-// levels  S_w = s_0 + L_0 (s_1 + 8 (s_2 + ...))  with lane-cooperative doublings.  Then warp 0 runs the Horner
-// combination over windows  acc = 2^c acc + S_w, normalises and encodes.
-template <class F> __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __restrict__ wpart, uint8_t* out, int out_mode)
+// One block of 8 warps.  Warp v, for windows v, v + 8, ...: recombines the planes  S_w = T + L (P_0 + 2 (P_1 + ...))  with
+// lane-cooperative doublings and additions.  Then warp 0 runs the Horner combination over windows  acc = 2^c acc + S_w,
+// normalises and encodes.
+template <class F> __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __restrict__ planes, uint8_t* out, int out_mode)
 {
     extern __shared__ __align__(16) unsigned char finish_smem[];
     Proj<F>* wsum = reinterpret_cast<Proj<F>*>(finish_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t full = 0xffffffffu;
     for (uint32_t w = warp; w < pl.windows; w += 8) {
-        const Proj<F>* slot = wpart + (size_t)w * MSM_WPART_SLOTS;
-        Proj<F> s0 = lane < (int)MSM_REDUCE2_SPLIT ? slot[lane] : proj_inf<F>();
+        const Proj<F>* slot = planes + (size_t)w * MSM_WPART_SLOTS;
+        Proj<F> acc = slot[pl.plane_bits];
+        if (pl.plane_bits > 0) {
+            acc = slot[pl.plane_bits - 1];
 #pragma unroll 1
-        for (int off = MSM_REDUCE2_SPLIT / 2; off >= 1; off >>= 1) {
-            Proj<F> o = shfl_down_obj(s0, off);
-            s0 = proj_add(s0, o);
-        }
-        s0 = shfl_bcast_obj(s0, 0);
-        Proj<F> acc = s0;
-        if (pl.levels > 1) {
-            acc = slot[MSM_REDUCE2_SPLIT + pl.levels - 2];
-#pragma unroll 1
-            for (uint32_t k = pl.levels - 1; k > 0; --k) {
-                uint32_t len = k - 1 == 0 ? pl.seg_len : MSM_LEVEL_LEN;
-#pragma unroll 1
-                for (; len > 1; len >>= 1) acc = coop_dbl(acc, full);
-                acc = coop_add(acc, k - 1 == 0 ? s0 : slot[MSM_REDUCE2_SPLIT + k - 2], full);
+            for (uint32_t j = pl.plane_bits - 1; j > 0; --j) {
+                acc = coop_dbl(acc, full);
+                acc = coop_add(acc, slot[j - 1], full);
             }
+#pragma unroll 1
+            for (uint32_t len = pl.seg_len; len > 1; len >>= 1) acc = coop_dbl(acc, full);
+            acc = coop_add(acc, slot[pl.plane_bits], full);
         }
         if (lane == 0) wsum[w] = acc;
     }
@@ -776,6 +792,7 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl)
     sc.rounds = R > BA_MAX_ROUNDS ? BA_MAX_ROUNDS : R;
     sc.pipes = (uint32_t)c.ba_pipes < pl.windows ? (uint32_t)c.ba_pipes : pl.windows;
     if (sc.pipes < 1) sc.pipes = 1;
+    if (pl.groups > 1) sc.pipes = pl.groups;       // one pipeline per upload group: it starts when its group's points are there
     const uint32_t resident = (uint32_t)(c.sm_count > 0 ? c.sm_count : 148) * (C12_BA_THREADS / 32) * C12_BA_MIN_BLOCKS;
     for (uint32_t p = 0; p <= sc.pipes; ++p) sc.b_lo[p] = (pl.windows * p / sc.pipes) * pl.half;
     // cap(k, p): bound on pipeline p's slot count in the numbering of round k (lists after k halvings)
@@ -813,41 +830,38 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl)
     return sc;
 }
 
-template <class F> size_t msm_scratch_bytes(const MsmPlan& pl)
+// lp: the list-side plan (msm_list_plan), pl: the plain plan of the reduction
+template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp)
 {
-    size_t N = (size_t)pl.n * pl.windows;
+    size_t N = (size_t)lp.n * lp.windows;
     size_t tile_words = 0;
-    size_t hist_words = sort_scratch_words(pl.n, pl.windows, &tile_words);
+    size_t hist_words = sort_scratch_words(lp.n, lp.windows, &tile_words);
     size_t b = 0;
     b += align_up(sizeof(Affine<F>) * (size_t)pl.n);
     b += 4 * align_up(4 * N);
     b += align_up(4 * hist_words) + align_up(4 * tile_words);
-    b += 2 * align_up(4 * (size_t)pl.total);
-    b += align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax);
+    b += 2 * align_up(4 * (size_t)lp.total);
+    b += align_up(4 * chunk_order_scratch_words(lp)) + align_up(sizeof(Proj<F>) * (size_t)lp.vmax);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(pl);
+    const BaSchedule sc = msm_ba_schedule(lp);
     if (sc.rounds) {
-        b += align_up(4 * (size_t)sc.rounds * ((size_t)pl.total + 1)) + align_up(4 * ba_plan_scratch_words(pl, sc.rounds));
+        b += align_up(4 * (size_t)sc.rounds * ((size_t)lp.total + 1)) + align_up(4 * ba_plan_scratch_words(lp, sc.rounds));
         b += align_up(sizeof(Affine<F>) * sc.slots[1]) + align_up(sizeof(Affine<F>) * sc.slots[2]) + align_up(sizeof(Affine<F>) * sc.slots[0]);
         b += align_up(sizeof(F) * sc.slots[1]) + align_up(8 * sc.refs);
         b += align_up(sizeof(F) * sc.pool_stride * sc.pipes) + align_up(sizeof(F) * sc.pool_stride * sc.pipes * 32);
     }
     b += align_up(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
-    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
+    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS) * (1 + 2 * PlaneShape<F>::SPLITS) + align_up(4 * (size_t)pl.windows * MSM_WPART_SLOTS);
     return b + 65536;
 }
 
-// the halving rounds of one MSM, enqueued behind everything already on `s` (pipeline 0 stays on `s`, the others fork onto the
-// context's side streams and join back); the slot references (launch_ba_map) are in place.  E[2] receives the reduced lists.
+// the halving rounds of one MSM: pipeline 0 on `s`, the others on the context's side streams (the caller has forked them off
+// `s`); joins them back into `s`.  The slot references (launch_ba_map) are in place.  E[2] receives the reduced lists.
 template <class F>
 int msm_ba_rounds_run(const MsmPlan& pl, const BaSchedule& sc, const Affine<F>* pts, const uint32_t* off, const uint2* refs,
                       Affine<F>* const E[3], F* prefix, F* pool, F* others, cudaStream_t s)
 {
     Ctx& c = ctx();
-    if (sc.pipes > 1) {
-        C12_CUDA(cudaEventRecord(c.side_ev[0], s));
-        for (uint32_t p = 1; p < sc.pipes; ++p) C12_CUDA(cudaStreamWaitEvent(c.side[p - 1], c.side_ev[0], 0));
-    }
     for (uint32_t r = 0; r < sc.rounds; ++r) {
         for (uint32_t p = 0; p < sc.pipes; ++p) {
             cudaStream_t sp = p ? c.side[p - 1] : s;
@@ -889,25 +903,39 @@ int msm_ba_rounds_run(const MsmPlan& pl, const BaSchedule& sc, const Affine<F>* 
     return C12381_OK;
 }
 
-// scratch bound for an n-term MSM under the current window setting (callers arena_begin with at least this much)
-template <class F> size_t msm_scratch_for(size_t n)
+// the plans of an n-term MSM under the current settings: window width, then the list-side plan for `groups` upload groups
+// (groups only exist where the halving rounds run - they are what makes the lists independent of the later groups' points)
+template <class F> bool msm_plans(size_t n, uint32_t groups, MsmPlan& pl, MsmPlan& lp)
 {
-    if (n == 0 || n > (1ull << 26) / MsmTraits<F>::PARTS * 2) return 0;
+    if (n == 0 || n > (1ull << 26) / MsmTraits<F>::PARTS * 2) return false;
     constexpr uint32_t parts = MsmTraits<F>::PARTS;
     uint32_t cbits = ctx().forced_window ? (uint32_t)ctx().forced_window : msm_choose_window(parts * n, 256 / parts);
-    if (cbits < 2 || cbits > 16) return 0;
-    return msm_scratch_bytes<F>(msm_make_plan((uint32_t)n, cbits, parts));
+    if (cbits < 2 || cbits > 16) return false;
+    pl = msm_make_plan((uint32_t)n, cbits, parts, ctx().knob[3] > 0 ? (uint32_t)ctx().knob[3] : 0u);
+    if (groups > BA_MAX_PIPES) groups = BA_MAX_PIPES;
+    lp = msm_list_plan(pl, groups);
+    if (groups > 1 && msm_ba_schedule(lp).rounds == 0) lp = pl;
+    return true;
 }
 
-// The caller has arena_begin()'d at least msm_scratch_for<F>(n) bytes beyond what it took itself.
+// scratch bound for an n-term MSM under the current settings (callers arena_begin with at least this much)
+template <class F> size_t msm_scratch_for(size_t n, uint32_t groups = 1)
+{
+    MsmPlan pl, lp;
+    if (!msm_plans<F>(n, groups, pl, lp)) return 0;
+    return msm_scratch_bytes<F>(pl, lp);
+}
+
+// The caller has arena_begin()'d at least msm_scratch_for<F>(n, groups) bytes beyond what it took itself.
 // d_points: n wire-format affine points; d_scalars: n x 32 B big-endian; d_out: Wire<F>::COMPRESSED or ::AFFINE bytes.
-// Everything is enqueued on `s`; malformed input is reported through the context flag word (c12381_sync_status /
-// the host entry's return code), never by a different code path.
-// points_ready: optional event after which d_points is valid (host entries upload the points on a second stream while
-// the scalar-only stages - recode, sort, bucket bounds - already run).
+// Everything is enqueued on `s` (and the context's side streams, forked from and joined back into `s`); malformed input is
+// reported through the context flag word (c12381_sync_status / the host entry's return code), never by a different code path.
+// points_ready: optional events, one per upload group, after which that group's slice of d_points is valid (host entries
+// upload the points group by group on a second stream while the scalar-only stages - recode, sort, bucket bounds, the slot map -
+// and then the earlier groups' additions already run); the groups are ceil(n / groups) consecutive terms each.
 template <class F>
 int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint8_t* d_out, int out_mode, cudaStream_t s,
-            cudaEvent_t points_ready = nullptr)
+            uint32_t groups = 1, const cudaEvent_t* points_ready = nullptr)
 {
     Ctx& c = ctx();
     const int out_bytes = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
@@ -917,15 +945,15 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     }
     if (n_sz > (1ull << 26) / MsmTraits<F>::PARTS * 2) return set_error(C12381_EARG, "msm: too many terms per call (2^26 over G1, 2^25 over G2)");
     const uint32_t n = (uint32_t)n_sz;
-    constexpr uint32_t parts = MsmTraits<F>::PARTS;
-    uint32_t cbits = c.forced_window ? (uint32_t)c.forced_window : msm_choose_window((uint64_t)parts * n, 256 / parts);
-    if (cbits < 2 || cbits > 16) return set_error(C12381_EARG, "msm: window width must be in [2, 16]");
-    const MsmPlan pl = msm_make_plan(n, cbits, parts);
-    const size_t N = (size_t)pl.n * pl.windows;
+    MsmPlan pl, lp;
+    if (!msm_plans<F>(n_sz, groups, pl, lp)) return set_error(C12381_EARG, "msm: window width must be in [2, 16]");
+    const uint32_t groups_req = groups;
+    groups = lp.groups;
+    const size_t N = (size_t)lp.n * lp.windows;
 
     int rc;
     size_t tile_words = 0;
-    size_t hist_words = sort_scratch_words(pl.n, pl.windows, &tile_words);
+    size_t hist_words = sort_scratch_words(lp.n, lp.windows, &tile_words);
     Affine<F>* pts = (Affine<F>*)arena_take(sizeof(Affine<F>) * (size_t)pl.n);
     uint32_t* keys = (uint32_t*)arena_take(4 * N);
     uint32_t* vals = (uint32_t*)arena_take(4 * N);
@@ -933,19 +961,19 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* vals2 = (uint32_t*)arena_take(4 * N);
     uint32_t* hist = (uint32_t*)arena_take(4 * hist_words);
     uint32_t* tiles = (uint32_t*)arena_take(4 * tile_words);
-    uint32_t* start = (uint32_t*)arena_take(4 * (size_t)pl.total);
-    uint32_t* end = (uint32_t*)arena_take(4 * (size_t)pl.total);
-    uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));
-    Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
+    uint32_t* start = (uint32_t*)arena_take(4 * (size_t)lp.total);
+    uint32_t* end = (uint32_t*)arena_take(4 * (size_t)lp.total);
+    uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(lp));
+    Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)lp.vmax);
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(pl);
+    const BaSchedule sc = msm_ba_schedule(lp);
     uint32_t *ba_off = nullptr, *ba_tiles = nullptr;
     uint2* ba_refs = nullptr;
     Affine<F>* ba_lists[3] = {nullptr, nullptr, nullptr};   // the two ping-pong buffers and the last round's output
     F *ba_prefix = nullptr, *ba_pool = nullptr, *ba_others = nullptr;
     if (sc.rounds) {
-        ba_off = (uint32_t*)arena_take(4 * (size_t)sc.rounds * ((size_t)pl.total + 1));
-        ba_tiles = (uint32_t*)arena_take(4 * ba_plan_scratch_words(pl, sc.rounds));
+        ba_off = (uint32_t*)arena_take(4 * (size_t)sc.rounds * ((size_t)lp.total + 1));
+        ba_tiles = (uint32_t*)arena_take(4 * ba_plan_scratch_words(lp, sc.rounds));
         ba_lists[0] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[1]);
         ba_lists[1] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[2]);
         ba_lists[2] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[0]);
@@ -956,24 +984,27 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     }
     Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
-    if (!wsum) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
+    Proj<F>* plane_parts = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS * 2 * PlaneShape<F>::SPLITS);
+    uint32_t* plane_tickets = (uint32_t*)arena_take(4 * (size_t)pl.windows * MSM_WPART_SLOTS);
+    if (!plane_tickets) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
+    C12_CUDA(cudaMemsetAsync(plane_tickets, 0, 4 * (size_t)pl.windows * MSM_WPART_SLOTS, s));
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
     C12_CUDA(cudaEventRecord(c.pev[0], s));
-    rc = launch_recode(pl, d_scalars, keys, vals, flags_word(), s);
+    rc = launch_recode(lp, d_scalars, keys, vals, flags_word(), s);
     if (rc) return rc;
     C12_CUDA(cudaEventRecord(c.pev[1], s));
-    rc = sort_pairs_segmented(keys, vals, keys2, vals2, pl.n, pl.windows, pl.c, hist, tiles, s);
+    rc = sort_pairs_segmented(keys, vals, keys2, vals2, lp.n, lp.windows, lp.c, hist, tiles, s);
     if (rc) return rc;
     C12_CUDA(cudaEventRecord(c.pev[2], s));
-    rc = launch_bucket_bounds(pl, keys, start, end, s);
+    rc = launch_bucket_bounds(lp, keys, start, end, s);
     if (rc) return rc;
     // the lists the accumulation walks: the sorted entries themselves, or what the halving rounds leave of them
     const uint32_t *lstart = start, *lend = end;
     if (sc.rounds) {
-        rc = launch_ba_plan(pl, start, end, sc.rounds, ba_off, ba_tiles, s);
+        rc = launch_ba_plan(lp, start, end, sc.rounds, ba_off, ba_tiles, s);
         if (rc) return rc;
-        lstart = ba_off + (size_t)(sc.rounds - 1) * (pl.total + 1);
+        lstart = ba_off + (size_t)(sc.rounds - 1) * (lp.total + 1);
         lend = lstart + 1;
         BaMapGeom mg;
         mg.start = start;
@@ -981,7 +1012,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         mg.off = ba_off;
         mg.vals = vals;
         mg.refs = ba_refs;
-        mg.total = pl.total;
+        mg.total = lp.total;
         mg.rounds = sc.rounds;
         mg.pipes = sc.pipes;
         for (uint32_t p = 0; p <= sc.pipes; ++p) mg.b_lo[p] = sc.b_lo[p];
@@ -994,34 +1025,51 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         if (rc) return rc;
     }
     uint32_t *order = nullptr, *vstart = nullptr, *vbucket = nullptr;
-    rc = launch_chunk_order(pl, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
+    rc = launch_chunk_order(lp, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
     if (rc) return rc;
-    if (points_ready) C12_CUDA(cudaStreamWaitEvent(s, points_ready, 0));
-    C12_CUDA(cudaEventRecord(c.pev[3], s));
-    k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, n, pl.parts, pts, flags_word());
-    C12_LAUNCHED();
+    // the points: all at once in front of everything that reads them, or - with upload groups - each group in front of the
+    // pipeline that owns its lists (pipeline p = group p)
+    if (groups == 1) {
+        if (points_ready)
+            for (uint32_t g = 0; g < groups_req; ++g) C12_CUDA(cudaStreamWaitEvent(s, points_ready[g], 0));
+        C12_CUDA(cudaEventRecord(c.pev[3], s));
+        k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, 0, n, n, pl.parts, pts, flags_word());
+        C12_LAUNCHED();
+    }
+    if (sc.pipes > 1) {
+        C12_CUDA(cudaEventRecord(c.side_ev[0], s));
+        for (uint32_t p = 1; p < sc.pipes; ++p) C12_CUDA(cudaStreamWaitEvent(c.side[p - 1], c.side_ev[0], 0));
+    }
+    if (groups > 1) {
+        for (uint32_t g = 0; g < groups; ++g) {
+            cudaStream_t sp = g ? c.side[g - 1] : s;
+            if (points_ready) C12_CUDA(cudaStreamWaitEvent(sp, points_ready[g], 0));
+            if (g == 0) C12_CUDA(cudaEventRecord(c.pev[3], s));
+            const uint32_t first = g * lp.n_group, last = first + lp.n_group < n ? first + lp.n_group : n;
+            if (first < last) {
+                k_parse_points<F><<<cdiv(last - first, 128), 128, 0, sp>>>(d_points, first, last, n, pl.parts, pts, flags_word());
+                C12_LAUNCHED();
+            }
+        }
+    }
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
     if (sc.rounds) {
-        rc = msm_ba_rounds_run<F>(pl, sc, pts, ba_off, ba_refs, ba_lists, ba_prefix, ba_pool, ba_others, s);
+        rc = msm_ba_rounds_run<F>(lp, sc, pts, ba_off, ba_refs, ba_lists, ba_prefix, ba_pool, ba_others, s);
         if (rc) return rc;
-        k_accumulate<F, true><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, lstart, lend, nullptr, ba_lists[2], order, vbucket, vstart, vpartial);
+        k_accumulate<F, true><<<cdiv(lp.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(lp.vmax, lp.chunk, lstart, lend, nullptr, ba_lists[2], order, vbucket, vstart, vpartial);
     } else {
-        k_accumulate<F, false><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
+        k_accumulate<F, false><<<cdiv(lp.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(lp.vmax, lp.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
     }
     C12_LAUNCHED();
-    k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, vstart, vpartial, buckets);
+    k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, groups, vstart, vpartial, buckets);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));
     k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);
     C12_LAUNCHED();
-    for (uint32_t k = 1; k < pl.levels; ++k) {
-        k_reduce_level<F><<<dim3(cdiv((size_t)pl.count[k + 1] * 8, 128), pl.windows), 128, 0, s>>>(pl, k, partial);
-        C12_LAUNCHED();
-    }
     C12_CUDA(cudaEventRecord(c.pev[6], s));
-    k_reduce2<F><<<dim3(pl.windows, MSM_REDUCE2_SPLIT + pl.levels - 1), 256, 0, s>>>(pl, partial, wsum);
+    k_reduce_planes<F><<<dim3(pl.plane_bits + 1, pl.windows, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, s>>>(pl, partial, plane_parts, plane_tickets, wsum);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.pev[7], s));
     k_finish<F><<<1, 256, sizeof(Proj<F>) * pl.windows, s>>>(pl, wsum, d_out, out_mode);
@@ -1215,27 +1263,38 @@ template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scal
     HostScope scope;
     const size_t out_bytes = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
     // scalars go up on the context stream (the first stages need only them); the points - three quarters of the bytes -
-    // follow on the copy stream and are awaited right before k_parse_points
+    // follow on the copy stream in upload groups, each awaited by the pipeline that adds up that group's bucket lists
     Ctx& c = ctx();
     cudaStream_t s = c.stream;
     const size_t pb = n * Wire<F>::AFFINE, sb = n * 32;
-    int rc = arena_begin(msm_scratch_for<F>(n) + align_up(pb) + align_up(sb) + 8192, s);
+    uint32_t groups = (uint32_t)c.upload_groups;
+    {
+        MsmPlan pl, lp;
+        if (!msm_plans<F>(n, groups, pl, lp)) groups = 1; else groups = lp.groups;
+    }
+    int rc = arena_begin(msm_scratch_for<F>(n, groups) + align_up(pb) + align_up(sb) + 8192, s);
     if (rc) return rc;
     uint8_t* d_pts = (uint8_t*)arena_take(pb ? pb : 4);
     uint8_t* d_sc = (uint8_t*)arena_take(sb ? sb : 4);
     uint8_t* d_out = (uint8_t*)arena_take(out_bytes);
     rc = flags_reset(s);
     if (rc) return rc;
-    cudaEvent_t ready = nullptr;
+    cudaEvent_t ready[BA_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
     if (n) {
         C12_CUDA(cudaMemcpyAsync(d_sc, scalars, sb, cudaMemcpyHostToDevice, s));
         C12_CUDA(cudaEventRecord(c.copy_ev[0], s));                        // the arena is ours from here on
         C12_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_ev[0], 0));
-        C12_CUDA(cudaMemcpyAsync(d_pts, points, pb, cudaMemcpyHostToDevice, c.copy_stream));
-        C12_CUDA(cudaEventRecord(c.copy_ev[1], c.copy_stream));
-        ready = c.copy_ev[1];
+        const size_t per = (n + groups - 1) / groups;
+        for (uint32_t g = 0; g < groups; ++g) {
+            const size_t first = (size_t)g * per, last = first + per < n ? first + per : n;
+            if (first < last)
+                C12_CUDA(cudaMemcpyAsync(d_pts + first * Wire<F>::AFFINE, points + first * Wire<F>::AFFINE, (last - first) * Wire<F>::AFFINE,
+                                         cudaMemcpyHostToDevice, c.copy_stream));
+            C12_CUDA(cudaEventRecord(c.group_ev[g], c.copy_stream));
+            ready[g] = c.group_ev[g];
+        }
     }
-    rc = msm_run<F>(d_pts, d_sc, n, d_out, out_mode, s, ready);
+    rc = msm_run<F>(d_pts, d_sc, n, d_out, out_mode, s, groups, n ? ready : nullptr);
     if (rc) {
         cudaStreamSynchronize(c.copy_stream);
         cudaStreamSynchronize(s);

@@ -70,7 +70,10 @@ C12381_API void c12381_set_msm_batch_affine(int rounds);
 /* testing/tuning knob: independent pipelines (window groups on their own streams) the halving rounds are split into (1 .. 4) */
 C12381_API void c12381_set_msm_pipelines(int pipes);
 /* measurement knobs of the halving rounds (A/B runs; same results): id 0 = waves of resident warps a pipeline's round should
- * span (slots per lane J follows), 1 = largest J, 2 = halvings left to the XYZZ accumulation by the automatic round count */
+ * span (slots per lane J follows), 1 = largest J, 2 = halvings left to the XYZZ accumulation by the automatic round count,
+ * 3 = threads the segment running sums of the bucket reduction should fill (sets the segment length; 0 = default),
+ * 4 = upload groups of the host-pointer MSM entries (1 .. 4: the points are uploaded in that many pieces, each in front of its
+ * own pipeline of halving rounds) */
 C12381_API void c12381_set_knob(int id, int value);
 
 /* ---- multi-scalar multiplication ------------------------------------------------------------------------- */

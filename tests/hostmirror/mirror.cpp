@@ -24,23 +24,30 @@ MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, uint32_t parts)
 }
 
 // parts = 1: no split; MsmTraits<F>::PARTS: the split the device entries use
-template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0, uint32_t chunk_override = 0)
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0, uint32_t chunk_override = 0, uint32_t groups = 1)
 {
     using W = Wire<F>;
     if (n_in == 0) {
         W::compress(out, affine_inf<F>());
         return 0;
     }
-    MsmPlan pl = make_plan(n_in, c, seg_len, parts);
+    const MsmPlan rpl = make_plan(n_in, c, seg_len, parts);     // the reduction's plan
+    MsmPlan pl = msm_list_plan(rpl, groups);                    // the list side: (group, window) segments with buckets of their own
     const uint32_t n = pl.n;
-    std::vector<Affine<F>> P(n);
+    std::vector<Affine<F>> P(rpl.n);
     for (uint32_t i = 0; i < n_in; ++i) {
         if (!W::parse(P[i], pts + (size_t)W::AFFINE * i)) return -1;
         for (uint32_t q = 1; q < parts; ++q) P[(size_t)q * n_in + i] = MsmTraits<F>::endo(q, P[i]);
     }
     size_t N = (size_t)n * pl.windows;
-    std::vector<uint32_t> keys(N), vals(N);
+    std::vector<uint32_t> keys(N, 0xdeadbeefu), vals(N, 0xdeadbeefu);
     for (uint32_t i = 0; i < n_in; ++i) msm_recode_body(pl, i, sc, keys.data(), vals.data());
+    for (uint32_t i = n_in; i < pl.groups * pl.n_group; ++i) msm_recode_pad_body(pl, i, keys.data(), vals.data());
+    for (size_t i = 0; i < N; ++i)
+        if (keys[i] == 0xdeadbeefu) return -4;          // every entry of every segment is written
+    if (groups > 1)                                     // a group's lists name that group's terms only
+        for (size_t i = 0; i < N; ++i)
+            if (keys[i] < pl.half && ((vals[i] & 0x7fffffffu) % n_in) / pl.n_group != (i / n) / pl.real_windows) return -5;
     // segmented stable sort: window w owns [w*n, (w+1)*n), keys are window-local (as the device sort does)
     std::vector<uint32_t> order(N);
     for (size_t i = 0; i < N; ++i) order[i] = (uint32_t)i;
@@ -109,26 +116,32 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
             buckets[b] = xyzz_to_proj(acc);
         }
     }
+    if (groups > 1) {       // k_fold: the groups' copies of a bucket are added up
+        std::vector<Proj<F>> merged(rpl.total);
+        for (uint32_t b = 0; b < rpl.total; ++b) {
+            Proj<F> acc = buckets[b];
+            for (uint32_t g = 1; g < groups; ++g) acc = proj_add(acc, buckets[(size_t)g * rpl.total + b]);
+            merged[b] = acc;
+        }
+        buckets.swap(merged);
+    }
+    pl = rpl;
     std::vector<Proj<F>> wsum(pl.windows);
     for (uint32_t w = 0; w < pl.windows; ++w) {
-        // the multi-level reduction of msm_core.cuh, level by level (k_reduce_level0 / k_reduce_level / k_reduce2 / k_finish)
-        std::vector<Proj<F>> cur(buckets.begin() + (size_t)w * pl.half, buckets.begin() + (size_t)(w + 1) * pl.half);
-        std::vector<Proj<F>> s(pl.levels);
-        for (uint32_t k = 0; k < pl.levels; ++k) {
-            uint32_t len = k == 0 ? pl.seg_len : MSM_LEVEL_LEN, next = pl.count[k + 1];
-            if (cur.size() != pl.count[k]) return -2;
-            std::vector<Proj<F>> runs(next);
-            Proj<F> tot = proj_inf<F>();
-            for (uint32_t t = 0; t < next; ++t) {
-                uint32_t lo = t * len, hi = lo + len > pl.count[k] ? pl.count[k] : lo + len;
-                Proj<F> sum;
-                msm_reduce_level_body<F>(cur.data(), lo, hi, k == 0 ? 1u : 0u, sum, runs[t]);
-                tot = proj_add(tot, sum);
-            }
-            s[k] = tot;
-            cur.swap(runs);
+        // the reduction of msm_core.cuh: segment running sums (k_reduce_level0), one tree sum per bit plane of the segment
+        // index (k_reduce_planes, here with 3 threads' slices per plane), recombination (k_finish)
+        const Proj<F>* B = buckets.data() + (size_t)w * pl.half;
+        std::vector<Proj<F>> sum0(pl.segs), run1(pl.segs), planes(pl.plane_bits + 1);
+        for (uint32_t t = 0; t < pl.segs; ++t) {
+            uint32_t lo = t * pl.seg_len, hi = lo + pl.seg_len > pl.half ? pl.half : lo + pl.seg_len;
+            msm_reduce_level_body<F>(B, lo, hi, 1u, sum0[t], run1[t]);
         }
-        wsum[w] = msm_combine_levels_body<F>(pl, s.data());
+        for (uint32_t j = 0; j <= pl.plane_bits; ++j) {
+            Proj<F> acc = proj_inf<F>();
+            for (uint32_t first = 0; first < 3; ++first) acc = proj_add(acc, msm_plane_slice_body<F>(pl, sum0.data(), run1.data(), j, first, 3));
+            planes[j] = acc;
+        }
+        wsum[w] = msm_combine_planes_body<F>(pl, planes.data());
     }
     Proj<F> r = msm_horner_body<F>(pl, wsum.data());
     W::compress(out, proj_to_affine(r));
@@ -169,6 +182,15 @@ int hm_g1_msm_ba(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uin
 int hm_g2_msm_ba(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint8_t* out97)
 {
     return msm<Fp2>(p, s, n, c, 0, out97, MsmTraits<Fp2>::PARTS, rounds);
+}
+// the same with the terms cut into `groups` upload groups (virtual windows per group, merged after the accumulation)
+int hm_g1_msm_groups(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint32_t groups, uint8_t* out49)
+{
+    return msm<Fp>(p, s, n, c, 0, out49, MsmTraits<Fp>::PARTS, rounds, 0, groups);
+}
+int hm_g2_msm_groups(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint32_t groups, uint8_t* out97)
+{
+    return msm<Fp2>(p, s, n, c, 0, out97, MsmTraits<Fp2>::PARTS, rounds, 0, groups);
 }
 
 int hm_g1_mul(const uint8_t* p96, const uint8_t* s32, uint32_t n, uint8_t* out49)

@@ -84,15 +84,19 @@ def test_points_golden(cuda):
     ps.check_points(cuda)
 
 
-@pytest.fixture(params=[(0, 1), (1, 1), (3, 2), (9, 4)], ids=["xyzz-only", "batch-affine-1", "batch-affine-3x2", "batch-affine-9x4"])
+@pytest.fixture(params=[(0, 1, 1), (1, 1, 1), (3, 2, 2), (9, 4, 3), (2, 1, 4)],
+                ids=["xyzz-only", "batch-affine-1", "batch-affine-3x2-groups2", "batch-affine-9-groups3", "batch-affine-2-groups4"])
 def ba_rounds(request):
-    """(forced batch-affine halving rounds, pipelines they are split into); -1 (the default) chooses from the bucket load"""
+    """(forced batch-affine halving rounds, pipelines they are split into, upload groups of the host entry);
+    the defaults are -1 (rounds chosen from the bucket load), 2 and 2"""
     from crypto12381_b200 import _lib
     _lib.lib().c12381_set_msm_batch_affine(request.param[0])
     _lib.lib().c12381_set_msm_pipelines(request.param[1])
+    _lib.lib().c12381_set_knob(4, request.param[2])
     yield request.param
     _lib.lib().c12381_set_msm_batch_affine(-1)
     _lib.lib().c12381_set_msm_pipelines(2)
+    _lib.lib().c12381_set_knob(4, 2)
 
 
 def test_msm_golden_all_windows(cuda, ba_rounds):

@@ -213,6 +213,27 @@ def test_msm_batch_affine_rounds(golden_msm):
                 assert out.raw == (want if want is not None else H(e["result"])), (key, rounds, c)
 
 
+def test_msm_upload_groups(golden_msm):
+    """Terms cut into upload groups: every (group, window) pair is a sort segment with buckets of its own (msm_list_plan, the
+    recode layout and its padding), a group's lists name that group's terms only, and the groups' buckets merge into the same sum -
+    also when the term count is not a multiple of the group count, and with fewer terms than groups."""
+    l = hm.lib()
+    H = bytes.fromhex
+    for case in golden_msm["cases"]:
+        if case["n"] > 300:
+            continue
+        g1 = case["group"] == "g1"
+        pts = (hm.g1_fixed_base if g1 else hm.g2_fixed_base)(H(case["point_scalars"]))
+        for groups, rounds, c in ((2, 0, 4), (2, 2, 3), (3, 1, 5), (4, 3, 2)):
+            out = ctypes.create_string_buffer(49 if g1 else 97)
+            fn = l.hm_g1_msm_groups if g1 else l.hm_g2_msm_groups
+            assert fn(pts, H(case["scalars"]), case["n"], c, rounds, groups, out) == 0, (case["group"], case["n"], groups, rounds, c)
+            assert out.raw == H(case["result"]), (case["group"], case["n"], groups, rounds, c)
+    e = golden_msm["edge_g1"]
+    out = ctypes.create_string_buffer(49)
+    assert l.hm_g1_msm_groups(H(e["points"]), H(e["scalars"]), len(H(e["scalars"])) // 32, 4, 2, 3, out) == 0 and out.raw == H(e["result"])
+
+
 def test_msm_chunked_accumulation(golden_msm):
     """Bucket lists cut into chunks (k_accumulate over virtual buckets + k_fold), down to chunks of one and three entries."""
     l = hm.lib()
