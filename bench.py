@@ -37,7 +37,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "g1_msm_points_per_s"
 UNIT = "points/s"
-FP_MUL_PER_BUCKET_ADD = 10      # XYZZ mixed addition: 8 M + 2 S
+FP_MUL_PER_XYZZ_ADD = 10        # XYZZ mixed addition: 8 M + 2 S
+FP_MUL_PER_AFFINE_ADD = 6       # batch-affine addition: 3 for Montgomery's trick + lambda, lambda^2, y3 (SURVEY §8d's unit)
 MAC_PER_FP_MUL = 300            # 12x12 product + 12x12 reduction + 12 quotient digits
 R_TOP = 0x73
 PAIRING_FP_MUL_KERNEL_COUNT = 30751   # Montgomery products per 4-pair product + final exponentiation (tools/count_fp_mul.py)
@@ -355,26 +356,40 @@ def run_ours(args):
         peak_gmacs = max(probes["imad_wide"]["gops"], probes["madc_pairs"]["gops"] / 2.0)
         adds = stats["bucket_adds"]
         acc = statistics.mean(acc_ms)
-        achieved = adds * FP_MUL_PER_BUCKET_ADD * MAC_PER_FP_MUL / (acc * 1e-3) / 1e9
-        traffic, traffic_src = None, None
-        try:   # DRAM bytes of one k_accumulate launch from the committed ncu --set full capture (same n, same plan)
+        # The bucket accumulation: with the batch-affine halving rounds on (the default at this size) every bucket addition is
+        # counted at SURVEY §8(d)'s unit, 6 Fp-mul; the kernels execute a little more (the shuffle butterfly of a warp's
+        # totals, ~11 / J products per addition, and 10 per XYZZ addition for the last 2^-rounds of the entries).
+        ba_rounds = stats.get("ba_rounds", 0)
+        per_add = FP_MUL_PER_AFFINE_ADD if ba_rounds else FP_MUL_PER_XYZZ_ADD
+        achieved = adds * per_add * MAC_PER_FP_MUL / (acc * 1e-3) / 1e9
+        executed_per_add = ((1 - 2.0 ** -ba_rounds) * (FP_MUL_PER_AFFINE_ADD + 11.0 / 32) + 2.0 ** -ba_rounds * FP_MUL_PER_XYZZ_ADD) if ba_rounds else FP_MUL_PER_XYZZ_ADD
+        kname = "k_ba_bwd<Fp, first round>" if ba_rounds else "k_accumulate<Fp>"
+        traffic, traffic_src, traffic_alg = None, None, None
+        try:   # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (same n, same plan)
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                tr = json.load(f)["k_accumulate<Fp>"]
+                tr = json.load(f)[kname]
             if args.log_n == 20:
-                traffic, traffic_src = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"]
+                traffic, traffic_src, traffic_alg = tr["dram_bytes_read"] + tr["dram_bytes_write"], tr["source"], tr.get("algorithmic_bytes")
         except Exception:
             pass
-        roofline = {"bound": "int32_mad", "kernel": "k_accumulate<Fp>", "achieved": achieved, "peak": peak_gmacs, "unit": "GMAC/s (32x32->64 multiply-adds)",
-                    "frac": achieved / peak_gmacs, "traffic": traffic, "traffic_unit": "DRAM bytes per launch", "traffic_source": traffic_src,
+        roofline = {"bound": "int32_mad",
+                    "kernel": ("bucket accumulation: k_ba_fwd + k_ba_inv + k_ba_bwd halving rounds (dominant launch: k_ba_bwd<Fp>, first round), k_accumulate<Fp> on the rest"
+                               if ba_rounds else "k_accumulate<Fp>"),
+                    "achieved": achieved, "peak": peak_gmacs, "unit": "GMAC/s (32x32->64 multiply-adds)",
+                    "frac": achieved / peak_gmacs, "traffic": traffic, "traffic_unit": "DRAM bytes per launch of " + kname, "traffic_source": traffic_src,
+                    "traffic_algorithmic_bytes": traffic_alg,
                     "gather_bytes_algorithmic": adds * 96,
                     "peak_source": "measured live: c12381_probe kind 2 (mad.wide.u32 chains) / kind 1 (mad.lo.cc+madc.hi.cc pairs), same GPU, same run",
-                    "algorithmic": f"{adds} bucket additions/launch x {FP_MUL_PER_BUCKET_ADD} Fp-mul x {MAC_PER_FP_MUL} MAC",
+                    "algorithmic": f"{adds} bucket additions/step x {per_add} Fp-mul x {MAC_PER_FP_MUL} MAC over the accumulation phase (CUDA events around it)",
                     "kernel_ms": acc, "kernel_share_of_step": acc / statistics.mean(tot_ms), "window_bits": stats["window_bits"],
+                    "ba_rounds": ba_rounds, "ba_pipelines": stats.get("ba_pipelines"), "fp_mul_executed_per_add": executed_per_add,
+                    "frac_executed": adds * executed_per_add * MAC_PER_FP_MUL / (acc * 1e-3) / 1e9 / peak_gmacs,
                     "fp_mul_gops": probes["fp_mul"]["gops"], "fp_sqr_gops": probes["fp_sqr"]["gops"],
                     "imad_gops": probes["imad"]["gops"], "imad_wide_gops": probes["imad_wide"]["gops"], "madc_pair_gops": probes["madc_pairs"]["gops"],
-                    # SURVEY §8(d)'s algorithmic unit beside the executed one: 6 Fp-mul per batch-affine addition
+                    # SURVEY §8(d)'s algorithmic unit whatever the kernels are: 6 Fp-mul per bucket addition
                     "frac_algorithmic_6mul": adds * 6 * MAC_PER_FP_MUL / (acc * 1e-3) / 1e9 / peak_gmacs,
-                    "frac_of_step_executed": adds * FP_MUL_PER_BUCKET_ADD * MAC_PER_FP_MUL / (statistics.mean(tot_ms) * 1e-3) / 1e9 / peak_gmacs}
+                    "frac_of_step_algorithmic": adds * 6 * MAC_PER_FP_MUL / (statistics.mean(tot_ms) * 1e-3) / 1e9 / peak_gmacs,
+                    "frac_of_step_executed": adds * executed_per_add * MAC_PER_FP_MUL / (statistics.mean(tot_ms) * 1e-3) / 1e9 / peak_gmacs}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                 hbm = json.load(f)["hbm_gbs"]
@@ -498,8 +513,10 @@ def run_ours(args):
         g2 = {"metric": "g2_msm_points_per_s", "value": n2 * world / (ms * 1e-3), "unit": "points/s", "n_per_gpu": n2, "ms": ms,
               "window_bits": st2["window_bits"], "phases_ms": st2["phases_ms"], "result_hex": r2b.hex(),
               "strong": {"n_total": ns2 * world, "ms": ms_strong, "points_per_s": ns2 * world / (ms_strong * 1e-3)},
-              # Fp2 XYZZ mixed addition: 8 Fp2-mul + 2 Fp2-sqr = 8 x 3 + 2 x 2 = 28 Fp-mul
-              "accumulate_ms": acc2, "accumulate_frac_of_mad_peak": adds2 * 28 * MAC_PER_FP_MUL / (acc2 * 1e-3) / 1e9 / line["roofline"]["peak"]}
+              # Fp2 XYZZ mixed addition: 8 Fp2-mul + 2 Fp2-sqr = 8 x 3 + 2 x 2 = 28 Fp-mul; batch-affine addition over Fp2
+              # (the halving rounds, on at this size): 5 Fp2-mul + 1 Fp2-sqr = 17 Fp-mul - the unit the fraction is counted in
+              "ba_rounds": st2.get("ba_rounds", 0), "fp_mul_per_add_counted": 17 if st2.get("ba_rounds", 0) else 28,
+              "accumulate_ms": acc2, "accumulate_frac_of_mad_peak": adds2 * (17 if st2.get("ba_rounds", 0) else 28) * MAC_PER_FP_MUL / (acc2 * 1e-3) / 1e9 / line["roofline"]["peak"]}
         try:
             ks_all = np.concatenate([k2n] + [rand_scalars(n2, 5000 + r) for r in range(1, world)])
             ss_all = np.concatenate([s2n] + [rand_scalars(n2, 6000 + r) for r in range(1, world)])

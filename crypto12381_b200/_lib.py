@@ -101,6 +101,7 @@ SIGNATURES = {
     "c12381_last_msm_stats": (_i, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                    ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(_i)]),
     "c12381_last_msm_phases": (_i, [ctypes.POINTER(ctypes.c_double)]),
+    "c12381_last_msm_shape": (_i, [ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "c12381_set_pairing_kernel": (None, [_i]),
 }
 

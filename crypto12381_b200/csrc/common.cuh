@@ -17,6 +17,7 @@ struct MsmStats {
     double phase_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // recode, sort, bounds+order, parse, accumulate, segment sums, plane sums, finish
     unsigned long long bucket_adds = 0;
     int window_bits = 0;
+    int ba_rounds = 0, ba_pipes = 0, groups = 1;     // batch-affine halving rounds / pipelines / upload groups the last MSM ran with
 };
 
 struct Ctx {

@@ -267,6 +267,14 @@ int c12381_last_msm_stats(double* accumulate_ms, double* total_ms, unsigned long
     return C12381_OK;
 }
 
+int c12381_last_msm_shape(int* ba_rounds, int* ba_pipelines, int* upload_groups)
+{
+    if (ba_rounds) *ba_rounds = ctx().stats.ba_rounds;
+    if (ba_pipelines) *ba_pipelines = ctx().stats.ba_pipes;
+    if (upload_groups) *upload_groups = ctx().stats.groups;
+    return C12381_OK;
+}
+
 int c12381_last_msm_phases(double* phase_ms8)
 {
     int rc = c12381_last_msm_stats(nullptr, nullptr, nullptr, nullptr);

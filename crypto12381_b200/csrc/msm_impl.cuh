@@ -1077,6 +1077,9 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_CUDA(cudaEventRecord(c.pev[8], s));
     C12_CUDA(cudaEventRecord(c.ev[3], s));
     c.stats.window_bits = (int)pl.c;
+    c.stats.ba_rounds = (int)sc.rounds;
+    c.stats.ba_pipes = (int)sc.pipes;
+    c.stats.groups = (int)groups;
     c.stats.bucket_adds = N;
     c.stats.accumulate_ms = -1.0;  // resolved lazily by c12381_last_msm_stats
     return C12381_OK;

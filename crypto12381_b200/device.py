@@ -274,8 +274,10 @@ def last_msm_stats() -> dict:
     ph = (ctypes.c_double * 8)()
     check(lib().c12381_last_msm_phases(ph))
     names = ["recode", "sort", "bounds_order", "parse", "accumulate", "reduce1", "reduce2", "finish"]
+    r, p, g = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    check(lib().c12381_last_msm_shape(ctypes.byref(r), ctypes.byref(p), ctypes.byref(g)))
     return {"accumulate_ms": a.value, "total_ms": t.value, "bucket_adds": adds.value, "window_bits": c.value,
-            "phases_ms": dict(zip(names, list(ph)))}
+            "ba_rounds": r.value, "ba_pipelines": p.value, "upload_groups": g.value, "phases_ms": dict(zip(names, list(ph)))}
 
 
 def probe(kind: int, iters: int = 2000) -> dict:

@@ -244,6 +244,9 @@ C12381_API int c12381_last_msm_stats(double* accumulate_ms, double* total_ms, un
 /* CUDA-event times (ms) of the eight phases of the most recent MSM call: recode, sort, bucket bounds + order, parse
  * (includes waiting for the point upload in the host entry), accumulate, reduction levels, reduce-2, finish */
 C12381_API int c12381_last_msm_phases(double* phase_ms8);
+/* how the last MSM on this context formed its bucket sums: batch-affine halving rounds (0 = XYZZ additions only), the pipelines
+ * they ran in, the upload groups of a host-pointer call */
+C12381_API int c12381_last_msm_shape(int* ba_rounds, int* ba_pipelines, int* upload_groups);
 
 #ifdef __cplusplus
 }
