@@ -158,7 +158,7 @@ template <class F> __device__ __forceinline__ F shfl_xor_obj(const F& x, int mas
 #define C12_BA_THREADS 128
 #endif
 #ifndef C12_BA_MIN_BLOCKS
-#define C12_BA_MIN_BLOCKS 3
+#define C12_BA_MIN_BLOCKS 4       // 128 registers (16 bytes of spill) and 16 warps per SM against 138 and 12: accumulation 4.85 -> 4.71 ms (profiles/r02q)
 #endif
 #ifndef C12_BA2_MIN_BLOCKS
 #define C12_BA2_MIN_BLOCKS 2      // over Fp2 the unwinding pass holds twice the state: 168 registers spill, 255 do not
@@ -179,7 +179,11 @@ template <class F, bool FIRST> __device__ __forceinline__ const Affine<F>* ba_in
 {
     return FIRST ? io.pts + (ref & 0x7fffffffu) : io.lists + ref;
 }
+#if defined(C12_BA_PREFETCH_L1)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 
 // -DC12_BA_LOCKSTEP: the warps of a block walk the slot loops together (one barrier per slot, as k_accumulate does): the
 // unwinding pass is ~35 KB of straight-line products.  Every thread then stays in the loop for all J trips.
@@ -793,7 +797,7 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl)
     sc.pipes = (uint32_t)c.ba_pipes < pl.windows ? (uint32_t)c.ba_pipes : pl.windows;
     if (sc.pipes < 1) sc.pipes = 1;
     if (pl.groups > 1) sc.pipes = pl.groups;       // one pipeline per upload group: it starts when its group's points are there
-    const uint32_t resident = (uint32_t)(c.sm_count > 0 ? c.sm_count : 148) * (C12_BA_THREADS / 32) * C12_BA_MIN_BLOCKS;
+    const uint32_t resident = (uint32_t)(c.sm_count > 0 ? c.sm_count : 148) * (C12_BA_THREADS / 32) * 3;
     for (uint32_t p = 0; p <= sc.pipes; ++p) sc.b_lo[p] = (pl.windows * p / sc.pipes) * pl.half;
     // cap(k, p): bound on pipeline p's slot count in the numbering of round k (lists after k halvings)
     auto cap = [&](uint32_t k, uint32_t p) {

@@ -15,7 +15,7 @@
 #if !defined(C12_PAIR_LOCKSTEP)
 #define C12_PAIR_LOCKSTEP 1
 #endif
-#if !defined(C12_FP2_INLINE_MULS)
+#if !defined(C12_FP2_INLINE_MULS) && !defined(C12_PAIR_NO_FP2_INLINE)
 #define C12_FP2_INLINE_MULS 1
 #endif
 #endif
