@@ -50,7 +50,7 @@ struct Ctx {
     int ba_rounds = -1;     // batch-affine halving rounds in front of the XYZZ accumulation: -1 = chosen from the bucket load, 0 = none, k = k rounds
     int ba_pipes = 2;       // independent round pipelines (groups of windows on their own streams: one's inversion kernel hides behind the other's additions)
     int upload_groups = 2;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
-    cudaEvent_t group_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t group_ev[4] = {nullptr, nullptr, nullptr, nullptr}, sgroup_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // a group's points / scalars have arrived
     int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation, [3] threads the segment running sums of the bucket reduction should fill (0 = default)
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // streams of pipelines 1 .. 3 (pipeline 0 runs on the caller's stream)
     cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork + one join per side stream

@@ -189,6 +189,7 @@ int c12381_init(int device)
     for (auto& st : c.side) C12_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& ev : c.side_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.group_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c.sgroup_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
     C12_CUDA(cudaMalloc(&c.d_flags, 64 * sizeof(int)));
@@ -221,6 +222,8 @@ void c12381_shutdown(void)
     for (auto& ev : c.side_ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : c.group_ev)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c.sgroup_ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& st : c.side)
         if (st) cudaStreamDestroy(st);

@@ -6,30 +6,38 @@
 
 namespace c12 {
 
-__global__ void __launch_bounds__(128) k_recode(MsmPlan pl, const uint8_t* __restrict__ scalars, uint32_t* __restrict__ keys,
+__global__ void __launch_bounds__(128) k_recode(MsmPlan pl, uint32_t first, uint32_t last, const uint8_t* __restrict__ scalars, uint32_t* __restrict__ keys,
                                                 uint32_t* __restrict__ vals, int* flags)
 {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= pl.n_in) {
-        if (i < pl.groups * pl.n_group) msm_recode_pad_body(pl, i, keys, vals);
+    uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;       // terms [first, last): everything, or one upload group
+    if (i >= last) return;
+    if (i >= pl.n_in) {         // the unused tail of the last group's segments
+        msm_recode_pad_body(pl, i, keys, vals);
         return;
     }
     if (!scalar_is_canonical(scalar_from_be32(scalars + 32ull * i))) atomicOr(flags, FLAG_BAD_SCALAR);
     msm_recode_body(pl, i, scalars, keys, vals);
 }
 
-int launch_recode(const MsmPlan& pl, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s)
+// group < 0: all terms; else the terms of upload group `group` (and, for the last group, the padding of its segments)
+int launch_recode(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s)
 {
-    k_recode<<<cdiv((size_t)pl.groups * pl.n_group, 128), 128, 0, s>>>(pl, d_scalars, keys, vals, flags);
+    uint32_t first = 0, last = pl.groups * pl.n_group;
+    if (group >= 0) {
+        first = (uint32_t)group * pl.n_group;
+        last = first + pl.n_group;
+    }
+    if (last > first) k_recode<<<cdiv(last - first, 128), 128, 0, s>>>(pl, first, last, d_scalars, keys, vals, flags);
     C12_LAUNCHED();
     return C12381_OK;
 }
 
-int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s)
+// segments [seg0, seg0 + nseg) of the sorted key array -> bounds of their buckets (global positions, global bucket ids)
+int launch_bucket_bounds(const MsmPlan& pl, uint32_t seg0, uint32_t nseg, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s)
 {
-    C12_CUDA(cudaMemsetAsync(start, 0, 4 * (size_t)pl.total, s));
-    C12_CUDA(cudaMemsetAsync(end, 0, 4 * (size_t)pl.total, s));
-    k_bucket_bounds<<<dim3(cdiv(pl.n, 256), pl.windows), 256, 0, s>>>(keys, pl.n, pl.half, start, end);
+    C12_CUDA(cudaMemsetAsync(start + (size_t)seg0 * pl.half, 0, 4 * (size_t)nseg * pl.half, s));
+    C12_CUDA(cudaMemsetAsync(end + (size_t)seg0 * pl.half, 0, 4 * (size_t)nseg * pl.half, s));
+    k_bucket_bounds<<<dim3(cdiv(pl.n, 256), nseg), 256, 0, s>>>(keys, pl.n, pl.half, start, end, seg0);
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -90,16 +98,38 @@ __global__ void __launch_bounds__(256) k_ba_plan_apply(uint32_t total, const uin
     }
 }
 
-size_t ba_plan_scratch_words(const MsmPlan& pl, uint32_t rounds) { return (size_t)rounds * (cdiv((size_t)pl.total + 1, BA_PLAN_TILE) + 1) + 64; }
+size_t ba_plan_scratch_words(uint32_t total, uint32_t rounds) { return (size_t)rounds * (cdiv((size_t)total + 1, BA_PLAN_TILE) + 1) + 64; }
 
-int launch_ba_plan(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s)
+// `total` buckets with bounds start[] / end[] -> off[(r - 1) * (total + 1) + b], numbered from 0 (one upload group, or everything)
+int launch_ba_plan(uint32_t total, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s)
 {
-    const uint32_t ntiles = cdiv((size_t)pl.total + 1, BA_PLAN_TILE);
-    k_ba_plan_tiles<<<dim3(ntiles, rounds), 256, 0, s>>>(pl.total, start, end, tile_sums, ntiles);
+    const uint32_t ntiles = cdiv((size_t)total + 1, BA_PLAN_TILE);
+    k_ba_plan_tiles<<<dim3(ntiles, rounds), 256, 0, s>>>(total, start, end, tile_sums, ntiles);
     C12_LAUNCHED();
     k_ba_plan_top<<<rounds, 256, 0, s>>>(tile_sums, ntiles);
     C12_LAUNCHED();
-    k_ba_plan_apply<<<dim3(ntiles, rounds), 256, 0, s>>>(pl.total, start, end, tile_sums, ntiles, off);
+    k_ba_plan_apply<<<dim3(ntiles, rounds), 256, 0, s>>>(total, start, end, tile_sums, ntiles, off);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
+// where the accumulation finds what the halving rounds left of every bucket list: lane l (a pipeline of a group) wrote its last
+// round's output from final_region[l] on, in its own slot numbering
+__global__ void __launch_bounds__(256) k_ba_list_bounds(BaListGeom g, uint32_t* __restrict__ lstart, uint32_t* __restrict__ lend)
+{
+    const uint32_t vb = blockIdx.x * 256 + threadIdx.x;
+    if (vb >= g.vtotal) return;
+    uint32_t l = 0;
+    while (l + 1 < g.lanes && vb >= g.vb0[l + 1]) ++l;
+    const uint32_t b = g.b_lo[l] + (vb - g.vb0[l]);
+    const uint32_t org = g.off[l][g.b_lo[l]];
+    lstart[vb] = g.final_region[l] + (g.off[l][b] - org);
+    lend[vb] = g.final_region[l] + (g.off[l][b + 1] - org);
+}
+
+int launch_ba_list_bounds(const BaListGeom& g, uint32_t* lstart, uint32_t* lend, cudaStream_t s)
+{
+    k_ba_list_bounds<<<cdiv(g.vtotal, 256), 256, 0, s>>>(g, lstart, lend);
     C12_LAUNCHED();
     return C12381_OK;
 }

@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict_
 }
 
 // defined once in msm_common.cu (kernels there are launched through these host functions)
-int launch_recode(const MsmPlan& pl, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s);
-int launch_bucket_bounds(const MsmPlan& pl, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s);
+int launch_recode(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s);
+int launch_bucket_bounds(const MsmPlan& pl, uint32_t seg0, uint32_t nseg, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s);
 // chunking of the bucket lists: vstart[b] = first chunk of bucket b (total + 1 entries), vbucket[v] = bucket of chunk v,
 // order[] = chunk ids by decreasing length, padded with 0xffffffff up to pl.vmax
 int launch_chunk_order(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t* scratch, uint32_t** vstart, uint32_t** vbucket,
@@ -92,8 +92,8 @@ size_t chunk_order_scratch_words(const MsmPlan& pl);
 
 // offsets of the bucket lists after every halving round (msm_common.cu): off[(r - 1) * (total + 1) + b] for r = 1 .. rounds,
 // total + 1 entries each (the last one is the round's slot count)
-size_t ba_plan_scratch_words(const MsmPlan& pl, uint32_t rounds);
-int launch_ba_plan(const MsmPlan& pl, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s);
+size_t ba_plan_scratch_words(uint32_t total, uint32_t rounds);
+int launch_ba_plan(uint32_t total, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s);
 
 // ---- batch-affine halving rounds (msm_core.cuh "batch-affine halving rounds") -----------------------------------------
 // k_ba_map (msm_common.cu, ONE launch for all rounds, scalar-only: it runs while the points are still being uploaded)
@@ -110,8 +110,8 @@ int launch_ba_plan(const MsmPlan& pl, const uint32_t* start, const uint32_t* end
 //              and finishes each addition (lambda, lambda^2, y3).
 // Equal / opposite / identity operands are classified per pair (ba_denominator) and take no part in the inversion.
 // Pipelines run rounds apart from each other, and the slot numbering shrinks from round to round, so every pipeline keeps its
-// lists, prefixes and slot references in regions of its own, indexed from the start of ITS slot range; only the last round
-// writes in the global numbering (nothing reads that buffer before the pipelines have joined).
+// lists, prefixes and slot references in regions of its own, indexed from the start of ITS slot range (k_ba_list_bounds turns
+// the last round's regions into one pair of bound arrays for the accumulation).
 constexpr uint32_t BA_MAX_ROUNDS = 16, BA_MAX_PIPES = 4, BA_NONE = 0xffffffffu;
 
 struct BaMapGeom {
@@ -131,8 +131,19 @@ struct BaGeom {
     const uint32_t* off_out;    // offsets of the round's OUTPUT lists (total + 1 entries): the slot numbering
     const uint2* refs;          // this (round, pipeline)'s slot references
     uint32_t b_lo, b_hi, J;
-    uint32_t out_region, scratch_region, last;
+    uint32_t out_region, scratch_region;
 };
+
+// k_ba_list_bounds (msm_common.cu): the reduced lists of all lanes (a lane = one pipeline of one upload group) as ONE pair of
+// bound arrays over the virtual buckets, for the chunking and the accumulation
+struct BaListGeom {
+    const uint32_t* off[BA_MAX_PIPES];      // the lane's last-round offsets (its group's array)
+    uint32_t b_lo[BA_MAX_PIPES];            // first bucket of the lane in that array
+    uint32_t vb0[BA_MAX_PIPES + 1];         // first virtual bucket of the lane
+    uint32_t final_region[BA_MAX_PIPES];    // where the lane's last round wrote
+    uint32_t lanes, vtotal;
+};
+int launch_ba_list_bounds(const BaListGeom& g, uint32_t* lstart, uint32_t* lend, cudaStream_t s);
 
 template <class F> struct BaIo {
     const Affine<F>* pts;       // round 0: the parsed points (references are term | sign)
@@ -288,7 +299,7 @@ __global__ void __launch_bounds__(C12_BA_THREADS, BaShape<F>::MIN_BLOCKS) k_ba_b
     C12_BA_ENTER(g, L);
     const uint2* refs = g.refs + L.wl + L.lane;
     const F* prefix = io.prefix + g.scratch_region + L.wl + L.lane;
-    Affine<F>* out = io.out + (g.last ? L.slot_lo : g.out_region) + L.wl + L.lane;
+    Affine<F>* out = io.out + g.out_region + L.wl + L.lane;
     F iv = FieldOps<F>::one();
     if (L.count) iv = mul_hot(io.pool[L.gw], io.others[(size_t)L.gw * 32u + L.lane]);      // 1 / (this lane's total)
     // the references run two slots ahead; the points of the next slot are pulled into L2 while this one is finished
@@ -772,6 +783,7 @@ struct BaSchedule {
     uint32_t J[BA_MAX_ROUNDS][BA_MAX_PIPES], warps[BA_MAX_ROUNDS][BA_MAX_PIPES];
     uint32_t region[2][BA_MAX_PIPES];     // start of pipeline p's region in ping-pong buffer 0 (round-1 sized) / 1 (round-2 sized)
     uint32_t ref_region[BA_MAX_ROUNDS][BA_MAX_PIPES];
+    uint32_t final_region[BA_MAX_PIPES];  // start of lane p's region in the last round's output buffer
     size_t slots[3] = {0, 0, 0};          // sizes of the two ping-pong buffers ([1], [2]) and of the last round's output ([0])
     size_t refs = 0;                      // slot references of all rounds
     size_t pool_stride = 0;               // pool entries reserved per pipeline
@@ -830,7 +842,14 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl)
         }
         sc.slots[k] = base;
     }
-    sc.slots[0] = (size_t)(N >> sc.rounds) + pl.total + 1;
+    {
+        size_t base = 0;
+        for (uint32_t p = 0; p < sc.pipes; ++p) {
+            sc.final_region[p] = (uint32_t)base;
+            base += cap(sc.rounds, p);
+        }
+        sc.slots[0] = base;
+    }
     return sc;
 }
 
@@ -849,7 +868,9 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
     const BaSchedule sc = msm_ba_schedule(lp);
     if (sc.rounds) {
-        b += align_up(4 * (size_t)sc.rounds * ((size_t)lp.total + 1)) + align_up(4 * ba_plan_scratch_words(lp, sc.rounds));
+        // offsets and plan scratch: one array per upload group (+ one entry each), the list bounds of the accumulation
+        b += align_up(4 * (size_t)sc.rounds * ((size_t)lp.total + lp.groups)) + align_up(4 * lp.groups * ba_plan_scratch_words(lp.total / lp.groups, sc.rounds));
+        b += 2 * align_up(4 * ((size_t)lp.total + 1));
         b += align_up(sizeof(Affine<F>) * sc.slots[1]) + align_up(sizeof(Affine<F>) * sc.slots[2]) + align_up(sizeof(Affine<F>) * sc.slots[0]);
         b += align_up(sizeof(F) * sc.slots[1]) + align_up(8 * sc.refs);
         b += align_up(sizeof(F) * sc.pool_stride * sc.pipes) + align_up(sizeof(F) * sc.pool_stride * sc.pipes * 32);
@@ -859,29 +880,37 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     return b + 65536;
 }
 
-// the halving rounds of one MSM: pipeline 0 on `s`, the others on the context's side streams (the caller has forked them off
-// `s`); joins them back into `s`.  The slot references (launch_ba_map) are in place.  E[2] receives the reduced lists.
+// one lane of the halving rounds: a pipeline (window group) of the single group, or a whole upload group
+template <class F> struct BaLaneArgs {
+    cudaStream_t stream;
+    const uint32_t* off;        // the offsets of the lane's group: off[r * (total + 1) + b]
+    uint32_t total;             // buckets of that group
+    uint32_t b_lo, b_hi;        // the lane's buckets in it
+};
+
+// the halving rounds of all lanes, issued round by round (lane p on lanes[p].stream, already ordered behind whatever that
+// lane needs).  The slot references (launch_ba_map) are in place.  E[2] receives the reduced lists, lane by lane.
 template <class F>
-int msm_ba_rounds_run(const MsmPlan& pl, const BaSchedule& sc, const Affine<F>* pts, const uint32_t* off, const uint2* refs,
-                      Affine<F>* const E[3], F* prefix, F* pool, F* others, cudaStream_t s)
+int msm_ba_rounds_run(const BaSchedule& sc, const BaLaneArgs<F>* lanes, const Affine<F>* pts, const uint2* refs, Affine<F>* const E[3], F* prefix,
+                      F* pool, F* others)
 {
     Ctx& c = ctx();
     for (uint32_t r = 0; r < sc.rounds; ++r) {
         for (uint32_t p = 0; p < sc.pipes; ++p) {
-            cudaStream_t sp = p ? c.side[p - 1] : s;
+            cudaStream_t sp = lanes[p].stream;
+            const bool last = r + 1 == sc.rounds;
             BaGeom g;
-            g.off_out = off + (size_t)r * (pl.total + 1);
+            g.off_out = lanes[p].off + (size_t)r * (lanes[p].total + 1);
             g.refs = refs + sc.ref_region[r][p];
-            g.b_lo = sc.b_lo[p];
-            g.b_hi = sc.b_lo[p + 1];
+            g.b_lo = lanes[p].b_lo;
+            g.b_hi = lanes[p].b_hi;
             g.J = sc.J[r][p];
-            g.last = r + 1 == sc.rounds ? 1u : 0u;
-            g.out_region = sc.region[r & 1][p];
+            g.out_region = last ? sc.final_region[p] : sc.region[r & 1][p];
             g.scratch_region = sc.region[0][p];
             BaIo<F> io;
             io.pts = pts;
             io.lists = r ? E[(r - 1) & 1] : nullptr;
-            io.out = g.last ? E[2] : E[r & 1];
+            io.out = last ? E[2] : E[r & 1];
             io.prefix = prefix;
             io.pool = pool + (size_t)p * sc.pool_stride;
             io.others = others + (size_t)p * sc.pool_stride * 32;
@@ -899,10 +928,6 @@ int msm_ba_rounds_run(const MsmPlan& pl, const BaSchedule& sc, const Affine<F>* 
                 k_ba_bwd<F, false><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
             C12_LAUNCHED();
         }
-    }
-    for (uint32_t p = 1; p < sc.pipes; ++p) {
-        C12_CUDA(cudaEventRecord(c.side_ev[p], c.side[p - 1]));
-        C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[p], 0));
     }
     return C12381_OK;
 }
@@ -934,12 +959,13 @@ template <class F> size_t msm_scratch_for(size_t n, uint32_t groups = 1)
 // d_points: n wire-format affine points; d_scalars: n x 32 B big-endian; d_out: Wire<F>::COMPRESSED or ::AFFINE bytes.
 // Everything is enqueued on `s` (and the context's side streams, forked from and joined back into `s`); malformed input is
 // reported through the context flag word (c12381_sync_status / the host entry's return code), never by a different code path.
-// points_ready: optional events, one per upload group, after which that group's slice of d_points is valid (host entries
-// upload the points group by group on a second stream while the scalar-only stages - recode, sort, bucket bounds, the slot map -
-// and then the earlier groups' additions already run); the groups are ceil(n / groups) consecutive terms each.
+// scalars_ready / points_ready: optional events, one per upload group, after which that group's slice of d_scalars / d_points is
+// valid.  The host entries upload group by group on a second stream; every group is a pipeline of its own from its scalars to
+// its reduced bucket lists (recode, sort, bounds, slot map; then parse and the halving rounds), so group 0's additions start
+// while the later groups are still on the wire.  The groups are ceil(n / groups) consecutive terms each.
 template <class F>
 int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint8_t* d_out, int out_mode, cudaStream_t s,
-            uint32_t groups = 1, const cudaEvent_t* points_ready = nullptr)
+            uint32_t groups = 1, const cudaEvent_t* scalars_ready = nullptr, const cudaEvent_t* points_ready = nullptr)
 {
     Ctx& c = ctx();
     const int out_bytes = out_mode == OUT_AFFINE ? Wire<F>::AFFINE : Wire<F>::COMPRESSED;
@@ -954,30 +980,35 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     const uint32_t groups_req = groups;
     groups = lp.groups;
     const size_t N = (size_t)lp.n * lp.windows;
+    const uint32_t gtotal = lp.total / groups;                  // buckets of one group
 
     int rc;
-    size_t tile_words = 0;
-    size_t hist_words = sort_scratch_words(lp.n, lp.windows, &tile_words);
+    const size_t hist_words = sort_scratch_words(lp.n, lp.windows, nullptr);
+    size_t gtile_words = 0;
+    const size_t ghist_words = sort_scratch_words(lp.n, pl.windows, &gtile_words);      // one group's segments
     Affine<F>* pts = (Affine<F>*)arena_take(sizeof(Affine<F>) * (size_t)pl.n);
     uint32_t* keys = (uint32_t*)arena_take(4 * N);
     uint32_t* vals = (uint32_t*)arena_take(4 * N);
     uint32_t* keys2 = (uint32_t*)arena_take(4 * N);
     uint32_t* vals2 = (uint32_t*)arena_take(4 * N);
     uint32_t* hist = (uint32_t*)arena_take(4 * hist_words);
-    uint32_t* tiles = (uint32_t*)arena_take(4 * tile_words);
+    uint32_t* tiles = (uint32_t*)arena_take(4 * (size_t)groups * (gtile_words + 2));
     uint32_t* start = (uint32_t*)arena_take(4 * (size_t)lp.total);
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)lp.total);
     uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(lp));
     Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)lp.vmax);
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
     const BaSchedule sc = msm_ba_schedule(lp);
-    uint32_t *ba_off = nullptr, *ba_tiles = nullptr;
+    uint32_t *ba_off = nullptr, *ba_tiles = nullptr, *ba_lstart = nullptr, *ba_lend = nullptr;
     uint2* ba_refs = nullptr;
     Affine<F>* ba_lists[3] = {nullptr, nullptr, nullptr};   // the two ping-pong buffers and the last round's output
     F *ba_prefix = nullptr, *ba_pool = nullptr, *ba_others = nullptr;
+    const size_t off_words = (size_t)sc.rounds * ((size_t)gtotal + 1), plan_words = ba_plan_scratch_words(gtotal, sc.rounds ? sc.rounds : 1);
     if (sc.rounds) {
-        ba_off = (uint32_t*)arena_take(4 * (size_t)sc.rounds * ((size_t)lp.total + 1));
-        ba_tiles = (uint32_t*)arena_take(4 * ba_plan_scratch_words(lp, sc.rounds));
+        ba_off = (uint32_t*)arena_take(4 * off_words * groups);
+        ba_tiles = (uint32_t*)arena_take(4 * plan_words * groups);
+        ba_lstart = (uint32_t*)arena_take(4 * ((size_t)lp.total + 1));
+        ba_lend = (uint32_t*)arena_take(4 * ((size_t)lp.total + 1));
         ba_lists[0] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[1]);
         ba_lists[1] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[2]);
         ba_lists[2] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[0]);
@@ -995,63 +1026,108 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
     C12_CUDA(cudaEventRecord(c.pev[0], s));
-    rc = launch_recode(lp, d_scalars, keys, vals, flags_word(), s);
-    if (rc) return rc;
-    C12_CUDA(cudaEventRecord(c.pev[1], s));
-    rc = sort_pairs_segmented(keys, vals, keys2, vals2, lp.n, lp.windows, lp.c, hist, tiles, s);
-    if (rc) return rc;
-    C12_CUDA(cudaEventRecord(c.pev[2], s));
-    rc = launch_bucket_bounds(lp, keys, start, end, s);
-    if (rc) return rc;
-    // the lists the accumulation walks: the sorted entries themselves, or what the halving rounds leave of them
-    const uint32_t *lstart = start, *lend = end;
-    if (sc.rounds) {
-        rc = launch_ba_plan(lp, start, end, sc.rounds, ba_off, ba_tiles, s);
-        if (rc) return rc;
-        lstart = ba_off + (size_t)(sc.rounds - 1) * (lp.total + 1);
-        lend = lstart + 1;
-        BaMapGeom mg;
-        mg.start = start;
-        mg.end = end;
-        mg.off = ba_off;
-        mg.vals = vals;
-        mg.refs = ba_refs;
-        mg.total = lp.total;
-        mg.rounds = sc.rounds;
-        mg.pipes = sc.pipes;
-        for (uint32_t p = 0; p <= sc.pipes; ++p) mg.b_lo[p] = sc.b_lo[p];
-        for (uint32_t p = 0; p < sc.pipes; ++p) {
-            mg.list_region[0][p] = sc.region[0][p];
-            mg.list_region[1][p] = sc.region[1][p];
-            for (uint32_t r = 0; r < sc.rounds; ++r) mg.ref_region[r][p] = sc.ref_region[r][p];
-        }
-        rc = launch_ba_map(mg, sc.max_slots, s);
-        if (rc) return rc;
+    // ---- the scalar-only stages, group by group: recode, sort, bucket bounds, round offsets, slot map ---------------------
+    // group g > 0 runs on side stream g - 1, forked off `s` here (the arena is ours from this point of `s` on)
+    if (groups > 1) {
+        C12_CUDA(cudaEventRecord(c.side_ev[0], s));
+        for (uint32_t g = 1; g < groups; ++g) C12_CUDA(cudaStreamWaitEvent(c.side[g - 1], c.side_ev[0], 0));
     }
+    uint32_t *skeys = keys, *svals = vals;       // where the sorted pairs end up (the passes ping-pong between the two buffers)
+    for (uint32_t g = 0; g < groups; ++g) {
+        cudaStream_t sg = g ? c.side[g - 1] : s;
+        if (scalars_ready) {
+            if (groups > 1)
+                C12_CUDA(cudaStreamWaitEvent(sg, scalars_ready[g], 0));
+            else
+                for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(s, scalars_ready[q], 0));
+        }
+        rc = launch_recode(lp, groups > 1 ? (int)g : -1, d_scalars, keys, vals, flags_word(), sg);
+        if (rc) return rc;
+        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[1], s));
+        const size_t seg_off = (size_t)g * pl.windows * lp.n;
+        uint32_t *k1 = keys + seg_off, *v1 = vals + seg_off, *k2 = keys2 + seg_off, *v2 = vals2 + seg_off;
+        rc = sort_pairs_segmented(k1, v1, k2, v2, lp.n, pl.windows, lp.c, hist + g * ghist_words, tiles + g * (gtile_words + 2), sg);
+        if (rc) return rc;
+        skeys = k1 - seg_off;
+        svals = v1 - seg_off;
+        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[2], s));
+        rc = launch_bucket_bounds(lp, g * pl.windows, pl.windows, skeys, start, end, sg);
+        if (rc) return rc;
+        if (sc.rounds) {
+            uint32_t* off_g = ba_off + g * off_words;
+            rc = launch_ba_plan(gtotal, start + (size_t)g * gtotal, end + (size_t)g * gtotal, sc.rounds, off_g, ba_tiles + g * plan_words, sg);
+            if (rc) return rc;
+            // the lanes of this group: the schedule's pipelines (one group: window groups of it; upload groups: the group itself)
+            BaMapGeom mg;
+            mg.start = start + (size_t)g * gtotal;
+            mg.end = end + (size_t)g * gtotal;
+            mg.off = off_g;
+            mg.vals = svals;
+            mg.refs = ba_refs;
+            mg.total = gtotal;
+            mg.rounds = sc.rounds;
+            mg.pipes = groups > 1 ? 1 : sc.pipes;
+            for (uint32_t p = 0; p < mg.pipes; ++p) {
+                const uint32_t lane = groups > 1 ? g : p;
+                mg.b_lo[p] = groups > 1 ? 0 : sc.b_lo[p];
+                mg.list_region[0][p] = sc.region[0][lane];
+                mg.list_region[1][p] = sc.region[1][lane];
+                for (uint32_t r = 0; r < sc.rounds; ++r) mg.ref_region[r][p] = sc.ref_region[r][lane];
+            }
+            mg.b_lo[mg.pipes] = gtotal;
+            rc = launch_ba_map(mg, groups > 1 ? sc.max_slots / groups + 1 : sc.max_slots, sg);
+            if (rc) return rc;
+        }
+    }
+    // ---- the points: all at once in front of everything that reads them, or each upload group in front of its own lane -------
     uint32_t *order = nullptr, *vstart = nullptr, *vbucket = nullptr;
-    rc = launch_chunk_order(lp, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
-    if (rc) return rc;
-    // the points: all at once in front of everything that reads them, or - with upload groups - each group in front of the
-    // pipeline that owns its lists (pipeline p = group p)
+    const uint32_t *lstart = start, *lend = end;
+    BaLaneArgs<F> lanes[BA_MAX_PIPES];
+    BaListGeom lg;
+    if (sc.rounds) {
+        lg.lanes = sc.pipes;
+        lg.vtotal = lp.total;
+        for (uint32_t p = 0; p < sc.pipes; ++p) {
+            const uint32_t g = groups > 1 ? p : 0;
+            lanes[p].stream = p ? c.side[p - 1] : s;
+            lanes[p].off = ba_off + g * off_words;
+            lanes[p].total = gtotal;
+            lanes[p].b_lo = groups > 1 ? 0 : sc.b_lo[p];
+            lanes[p].b_hi = groups > 1 ? gtotal : sc.b_lo[p + 1];
+            lg.off[p] = lanes[p].off + (size_t)(sc.rounds - 1) * (gtotal + 1);
+            lg.b_lo[p] = lanes[p].b_lo;
+            lg.vb0[p] = sc.b_lo[p];
+            lg.final_region[p] = sc.final_region[p];
+        }
+        lg.vb0[sc.pipes] = lp.total;
+        lstart = ba_lstart;
+        lend = ba_lend;
+    }
     if (groups == 1) {
+        // one group: the lists the accumulation will walk are known from the scalars alone - cut them into chunks now
+        if (sc.rounds) {
+            rc = launch_ba_list_bounds(lg, ba_lstart, ba_lend, s);
+            if (rc) return rc;
+        }
+        rc = launch_chunk_order(lp, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
+        if (rc) return rc;
         if (points_ready)
-            for (uint32_t g = 0; g < groups_req; ++g) C12_CUDA(cudaStreamWaitEvent(s, points_ready[g], 0));
+            for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(s, points_ready[q], 0));
         C12_CUDA(cudaEventRecord(c.pev[3], s));
         k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, 0, n, n, pl.parts, pts, flags_word());
         C12_LAUNCHED();
-    }
-    if (sc.pipes > 1) {
-        C12_CUDA(cudaEventRecord(c.side_ev[0], s));
-        for (uint32_t p = 1; p < sc.pipes; ++p) C12_CUDA(cudaStreamWaitEvent(c.side[p - 1], c.side_ev[0], 0));
-    }
-    if (groups > 1) {
+        if (sc.pipes > 1) {     // the pipelines of the single group fork here, behind the parsed points
+            C12_CUDA(cudaEventRecord(c.side_ev[0], s));
+            for (uint32_t p = 1; p < sc.pipes; ++p) C12_CUDA(cudaStreamWaitEvent(c.side[p - 1], c.side_ev[0], 0));
+        }
+    } else {
         for (uint32_t g = 0; g < groups; ++g) {
-            cudaStream_t sp = g ? c.side[g - 1] : s;
-            if (points_ready) C12_CUDA(cudaStreamWaitEvent(sp, points_ready[g], 0));
+            cudaStream_t sg = g ? c.side[g - 1] : s;
+            if (points_ready) C12_CUDA(cudaStreamWaitEvent(sg, points_ready[g], 0));
             if (g == 0) C12_CUDA(cudaEventRecord(c.pev[3], s));
             const uint32_t first = g * lp.n_group, last = first + lp.n_group < n ? first + lp.n_group : n;
             if (first < last) {
-                k_parse_points<F><<<cdiv(last - first, 128), 128, 0, sp>>>(d_points, first, last, n, pl.parts, pts, flags_word());
+                k_parse_points<F><<<cdiv(last - first, 128), 128, 0, sg>>>(d_points, first, last, n, pl.parts, pts, flags_word());
                 C12_LAUNCHED();
             }
         }
@@ -1059,11 +1135,22 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_CUDA(cudaEventRecord(c.ev[1], s));
     C12_CUDA(cudaEventRecord(c.pev[4], s));
     if (sc.rounds) {
-        rc = msm_ba_rounds_run<F>(lp, sc, pts, ba_off, ba_refs, ba_lists, ba_prefix, ba_pool, ba_others, s);
+        rc = msm_ba_rounds_run<F>(sc, lanes, pts, ba_refs, ba_lists, ba_prefix, ba_pool, ba_others);
         if (rc) return rc;
+        for (uint32_t p = 1; p < sc.pipes; ++p) {       // join
+            C12_CUDA(cudaEventRecord(c.side_ev[p], c.side[p - 1]));
+            C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[p], 0));
+        }
+        if (groups > 1) {
+            // what the rounds left of every group's lists, as one pair of bound arrays; cut into chunks
+            rc = launch_ba_list_bounds(lg, ba_lstart, ba_lend, s);
+            if (rc) return rc;
+            rc = launch_chunk_order(lp, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
+            if (rc) return rc;
+        }
         k_accumulate<F, true><<<cdiv(lp.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(lp.vmax, lp.chunk, lstart, lend, nullptr, ba_lists[2], order, vbucket, vstart, vpartial);
     } else {
-        k_accumulate<F, false><<<cdiv(lp.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(lp.vmax, lp.chunk, start, end, vals, pts, order, vbucket, vstart, vpartial);
+        k_accumulate<F, false><<<cdiv(lp.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(lp.vmax, lp.chunk, start, end, svals, pts, order, vbucket, vstart, vpartial);
     }
     C12_LAUNCHED();
     k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, groups, vstart, vpartial, buckets);
@@ -1286,22 +1373,25 @@ template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scal
     uint8_t* d_out = (uint8_t*)arena_take(out_bytes);
     rc = flags_reset(s);
     if (rc) return rc;
-    cudaEvent_t ready[BA_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ready_s[BA_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr}, ready_p[BA_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
     if (n) {
-        C12_CUDA(cudaMemcpyAsync(d_sc, scalars, sb, cudaMemcpyHostToDevice, s));
-        C12_CUDA(cudaEventRecord(c.copy_ev[0], s));                        // the arena is ours from here on
+        // copy stream, behind the point of `s` from which the arena is ours: scalars and points of group 0, of group 1, ...
+        C12_CUDA(cudaEventRecord(c.copy_ev[0], s));
         C12_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_ev[0], 0));
         const size_t per = (n + groups - 1) / groups;
         for (uint32_t g = 0; g < groups; ++g) {
             const size_t first = (size_t)g * per, last = first + per < n ? first + per : n;
+            if (first < last) C12_CUDA(cudaMemcpyAsync(d_sc + first * 32, scalars + first * 32, (last - first) * 32, cudaMemcpyHostToDevice, c.copy_stream));
+            C12_CUDA(cudaEventRecord(c.sgroup_ev[g], c.copy_stream));
+            ready_s[g] = c.sgroup_ev[g];
             if (first < last)
                 C12_CUDA(cudaMemcpyAsync(d_pts + first * Wire<F>::AFFINE, points + first * Wire<F>::AFFINE, (last - first) * Wire<F>::AFFINE,
                                          cudaMemcpyHostToDevice, c.copy_stream));
             C12_CUDA(cudaEventRecord(c.group_ev[g], c.copy_stream));
-            ready[g] = c.group_ev[g];
+            ready_p[g] = c.group_ev[g];
         }
     }
-    rc = msm_run<F>(d_pts, d_sc, n, d_out, out_mode, s, groups, n ? ready : nullptr);
+    rc = msm_run<F>(d_pts, d_sc, n, d_out, out_mode, s, groups, n ? ready_s : nullptr, n ? ready_p : nullptr);
     if (rc) {
         cudaStreamSynchronize(c.copy_stream);
         cudaStreamSynchronize(s);

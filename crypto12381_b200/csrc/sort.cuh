@@ -204,15 +204,15 @@ __global__ void __launch_bounds__(SORT_THREADS) k_radix_scatter(const uint32_t* 
 // bucket boundaries in the sorted key array of segment (window) blockIdx.y: start[w*half + k] = first GLOBAL index
 // with key k, end[...] = one past the last; keys >= half (zero digits) own no bucket.  start/end are pre-zeroed.
 __global__ void k_bucket_bounds(const uint32_t* __restrict__ keys, uint32_t n, uint32_t half, uint32_t* __restrict__ start,
-                                uint32_t* __restrict__ end)
+                                uint32_t* __restrict__ end, uint32_t seg0)
 {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t off = (uint64_t)blockIdx.y * n;
+    const uint64_t off = (uint64_t)(seg0 + blockIdx.y) * n;       // segments seg0 .. seg0 + gridDim.y - 1 of the whole array
     const uint32_t* seg_keys = keys + off;
     uint32_t k = seg_keys[i];
     if (k >= half) return;
-    uint64_t b = (uint64_t)blockIdx.y * half + k;
+    uint64_t b = (uint64_t)(seg0 + blockIdx.y) * half + k;
     if (i == 0 || seg_keys[i - 1] != k) start[b] = (uint32_t)(off + i);
     if (i + 1 == n || seg_keys[i + 1] != k) end[b] = (uint32_t)(off + i + 1);
 }
