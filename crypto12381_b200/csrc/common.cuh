@@ -52,7 +52,9 @@ struct Ctx {
     int upload_groups = 2;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
     cudaEvent_t group_ev[4] = {nullptr, nullptr, nullptr, nullptr}, sgroup_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // a group's points / scalars have arrived
     int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation, [3] threads the segment running sums of the bucket reduction should fill (0 = default)
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // streams of pipelines 1 .. 3 (pipeline 0 runs on the caller's stream)
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // streams of lanes 1 .. 3 (lane 0 runs on the caller's stream)
+    cudaStream_t plan_stream = nullptr;                      // several upload groups: the merged plan, beside the groups' own stages
+    cudaEvent_t msm_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // a group's bucket bounds are in place (0 .. 3); the merged plan is (4)
     cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork + one join per side stream
     void* fb_table[2] = {nullptr, nullptr};   // fixed-base window tables (G1, G2), built on first use
     MsmStats stats;

@@ -187,6 +187,8 @@ int c12381_init(int device)
     for (auto& ev : c.copy_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaEventCreateWithFlags(&c.arena_ev, cudaEventDisableTiming));
     for (auto& st : c.side) C12_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    C12_CUDA(cudaStreamCreateWithFlags(&c.plan_stream, cudaStreamNonBlocking));
+    for (auto& ev : c.msm_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.side_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.group_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.sgroup_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -227,6 +229,9 @@ void c12381_shutdown(void)
         if (ev) cudaEventDestroy(ev);
     for (auto& st : c.side)
         if (st) cudaStreamDestroy(st);
+    if (c.plan_stream) cudaStreamDestroy(c.plan_stream);
+    for (auto& ev : c.msm_ev)
+        if (ev) cudaEventDestroy(ev);
     if (c.copy_stream) {
         cudaStreamSynchronize(c.copy_stream);
         cudaStreamDestroy(c.copy_stream);

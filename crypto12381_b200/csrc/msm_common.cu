@@ -43,22 +43,33 @@ int launch_bucket_bounds(const MsmPlan& pl, uint32_t seg0, uint32_t nseg, const 
 }
 
 // ---- offsets of the bucket lists after each batch-affine halving round ------------------------------------------------
-// off_r[b] = sum over b' < b of ceil(m_b' / 2^r), r = 1 .. rounds (blockIdx.y = r - 1), total + 1 entries per round: three
-// launches for all rounds together (tile sums, scan of the tile sums, apply).
+// Level k = the lists after k halvings.  Level 1 is per upload group (round 0 adds up each group's sorted entries pairwise);
+// from there on a bucket's list is the CONCATENATION of its groups' level-1 lists (msm_impl.cuh), so with
+//   M1_b = sum over groups of ceil(m_(g,b) / 2)      the level-k list of bucket b holds  ceil(M1_b / 2^(k-1))  entries.
+// off_k[b] = sum over b' < b of that, total + 1 entries per level; three launches for all requested levels together
+// (blockIdx.y = level - first level): tile sums, scan of the tile sums, apply.
 constexpr int BA_PLAN_ITEMS = 8, BA_PLAN_TILE = 256 * BA_PLAN_ITEMS;
 
-__device__ __forceinline__ uint32_t ba_plan_len(const uint32_t* start, const uint32_t* end, uint32_t total, uint32_t b, uint32_t r)
+struct BaPlanGeom {
+    const uint32_t* start;      // bucket bounds: group g's copy of bucket b is entry g * gstride + b
+    const uint32_t* end;
+    uint32_t total, groups, gstride, first_level;
+};
+
+__device__ __forceinline__ uint32_t ba_plan_len(const BaPlanGeom& g, uint32_t b, uint32_t level)
 {
-    return b < total ? ba_len(end[b] - start[b], r) : 0u;
+    if (b >= g.total) return 0u;
+    uint32_t m1 = 0;
+    for (uint32_t q = 0; q < g.groups; ++q) m1 += ba_len(g.end[(size_t)q * g.gstride + b] - g.start[(size_t)q * g.gstride + b], 1);
+    return ba_len(m1, level - 1);
 }
 
-__global__ void __launch_bounds__(256) k_ba_plan_tiles(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                                       uint32_t* __restrict__ tile_sums, uint32_t ntiles)
+__global__ void __launch_bounds__(256) k_ba_plan_tiles(BaPlanGeom g, uint32_t* __restrict__ tile_sums, uint32_t ntiles)
 {
-    const uint32_t r = blockIdx.y + 1, base = blockIdx.x * BA_PLAN_TILE + threadIdx.x * BA_PLAN_ITEMS;
+    const uint32_t level = g.first_level + blockIdx.y, base = blockIdx.x * BA_PLAN_TILE + threadIdx.x * BA_PLAN_ITEMS;
     uint32_t s = 0;
 #pragma unroll
-    for (int i = 0; i < BA_PLAN_ITEMS; ++i) s += ba_plan_len(start, end, total, base + i, r);
+    for (int i = 0; i < BA_PLAN_ITEMS; ++i) s += ba_plan_len(g, base + i, level);
     uint32_t tot;
     block_exclusive_scan_256(s, &tot);
     if (threadIdx.x == 0) tile_sums[(size_t)blockIdx.y * ntiles + blockIdx.x] = tot;
@@ -78,37 +89,46 @@ __global__ void __launch_bounds__(256) k_ba_plan_top(uint32_t* __restrict__ tile
     }
 }
 
-__global__ void __launch_bounds__(256) k_ba_plan_apply(uint32_t total, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                                       const uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ off)
+__global__ void __launch_bounds__(256) k_ba_plan_apply(BaPlanGeom g, const uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ off)
 {
-    const uint32_t r = blockIdx.y + 1, base = blockIdx.x * BA_PLAN_TILE + threadIdx.x * BA_PLAN_ITEMS;
+    const uint32_t level = g.first_level + blockIdx.y, base = blockIdx.x * BA_PLAN_TILE + threadIdx.x * BA_PLAN_ITEMS;
     uint32_t v[BA_PLAN_ITEMS], s = 0;
 #pragma unroll
     for (int i = 0; i < BA_PLAN_ITEMS; ++i) {
-        v[i] = ba_plan_len(start, end, total, base + i, r);
+        v[i] = ba_plan_len(g, base + i, level);
         s += v[i];
     }
     uint32_t tot;
     uint32_t e = block_exclusive_scan_256(s, &tot) + tile_sums[(size_t)blockIdx.y * ntiles + blockIdx.x];
-    uint32_t* o = off + (size_t)blockIdx.y * (total + 1);
+    uint32_t* o = off + (size_t)blockIdx.y * (g.total + 1);
 #pragma unroll
     for (int i = 0; i < BA_PLAN_ITEMS; ++i) {
-        if (base + i <= total) o[base + i] = e;       // entry `total` is the round's slot count
+        if (base + i <= g.total) o[base + i] = e;       // entry `total` is the level's slot count
         e += v[i];
     }
 }
 
-size_t ba_plan_scratch_words(uint32_t total, uint32_t rounds) { return (size_t)rounds * (cdiv((size_t)total + 1, BA_PLAN_TILE) + 1) + 64; }
+size_t ba_plan_scratch_words(uint32_t total, uint32_t levels) { return (size_t)levels * (cdiv((size_t)total + 1, BA_PLAN_TILE) + 1) + 64; }
 
-// `total` buckets with bounds start[] / end[] -> off[(r - 1) * (total + 1) + b], numbered from 0 (one upload group, or everything)
-int launch_ba_plan(uint32_t total, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s)
+// off[(k - first_level) * (total + 1) + b] for k = first_level .. first_level + levels - 1, numbered from 0.
+// One group's level 1: groups = 1 with that group's bounds; the merged levels >= 2: all groups' bounds, gstride apart.
+int launch_ba_plan(uint32_t total, const uint32_t* start, const uint32_t* end, uint32_t groups, uint32_t gstride, uint32_t first_level, uint32_t levels,
+                   uint32_t* off, uint32_t* tile_sums, cudaStream_t s)
 {
+    if (levels == 0) return C12381_OK;
+    BaPlanGeom g;
+    g.start = start;
+    g.end = end;
+    g.total = total;
+    g.groups = groups;
+    g.gstride = gstride;
+    g.first_level = first_level;
     const uint32_t ntiles = cdiv((size_t)total + 1, BA_PLAN_TILE);
-    k_ba_plan_tiles<<<dim3(ntiles, rounds), 256, 0, s>>>(total, start, end, tile_sums, ntiles);
+    k_ba_plan_tiles<<<dim3(ntiles, levels), 256, 0, s>>>(g, tile_sums, ntiles);
     C12_LAUNCHED();
-    k_ba_plan_top<<<rounds, 256, 0, s>>>(tile_sums, ntiles);
+    k_ba_plan_top<<<levels, 256, 0, s>>>(tile_sums, ntiles);
     C12_LAUNCHED();
-    k_ba_plan_apply<<<dim3(ntiles, rounds), 256, 0, s>>>(total, start, end, tile_sums, ntiles, off);
+    k_ba_plan_apply<<<dim3(ntiles, levels), 256, 0, s>>>(g, tile_sums, ntiles, off);
     C12_LAUNCHED();
     return C12381_OK;
 }
@@ -134,53 +154,58 @@ int launch_ba_list_bounds(const BaListGeom& g, uint32_t* lstart, uint32_t* lend,
     return C12381_OK;
 }
 
-// every output slot of every round -> the two inputs it adds (blockIdx.y = round; see msm_impl.cuh).  A thread resolves
-// BA_MAP_RUN consecutive slots: one binary search for the first, then the bucket only moves forward by a step or two.
+// every output slot of the rounds [g.first_round, g.first_round + g.rounds) -> the two inputs it adds (blockIdx.y = round -
+// first round; see msm_impl.cuh).  A thread resolves BA_MAP_RUN consecutive slots: one binary search for the first, then the
+// bucket only moves forward by a step or two.
+//   round 0 (a group's own): inputs are (term | sign) values of the group's sorted entries
+//   round 1: inputs are positions in the groups' level-1 lists, a bucket's list being their concatenation in group order
+//   rounds >= 2: positions in the previous round's output, pipeline by pipeline
 constexpr uint32_t BA_MAP_RUN = 8;
 __global__ void __launch_bounds__(256) k_ba_map(BaMapGeom g)
 {
-    const uint32_t r = blockIdx.y;
-    const uint32_t* off_out = g.off + (size_t)r * (g.total + 1);
-    const uint32_t* off_in = r ? g.off + (size_t)(r - 1) * (g.total + 1) : g.start;
+    const uint32_t r = g.first_round + blockIdx.y;
+    const uint32_t* off_out = g.off_out[blockIdx.y];
     const uint32_t n_slots = off_out[g.total];
     uint32_t t = (blockIdx.x * 256 + threadIdx.x) * BA_MAP_RUN;
     if (t >= n_slots) return;
     const uint32_t t_end = t + BA_MAP_RUN < n_slots ? t + BA_MAP_RUN : n_slots;
+    const uint32_t* off_in = g.off_in[blockIdx.y];       // rounds >= 2
     uint32_t b = ba_bucket_of(off_out, 0u, g.total, t), p = 0;
-    uint32_t lo = off_out[b], hi = off_out[b + 1], len = ba_len(g.end[b] - g.start[b], r), in0 = off_in[b];
     while (p + 1 < g.pipes && b >= g.b_lo[p + 1]) ++p;
-    uint32_t p_slot0 = off_out[g.b_lo[p]], p_in0 = r ? off_in[g.b_lo[p]] : 0u;
+    uint32_t lo = 0, hi = 0, p_slot0 = off_out[g.b_lo[p]];
+    bool fresh = true;
     for (; t < t_end; ++t) {
-        if (t >= hi) {
-            b = ba_bucket_of(off_out, b + 1, g.total, t);
+        if (fresh || t >= hi) {
+            if (!fresh) b = ba_bucket_of(off_out, b + 1, g.total, t);
+            fresh = false;
             lo = off_out[b];
             hi = off_out[b + 1];
-            len = ba_len(g.end[b] - g.start[b], r);
-            in0 = off_in[b];
             if (p + 1 < g.pipes && b >= g.b_lo[p + 1]) {
                 while (p + 1 < g.pipes && b >= g.b_lo[p + 1]) ++p;
                 p_slot0 = off_out[g.b_lo[p]];
-                p_in0 = r ? off_in[g.b_lo[p]] : 0u;
             }
         }
         const uint32_t ii = t - lo;
-        const bool has2 = 2 * ii + 1 < len;
         uint2 ref;
         if (r == 0) {
-            const uint32_t pos = in0 + 2 * ii;
+            const uint32_t m = g.end[b] - g.start[b], pos = g.start[b] + 2 * ii;
             ref.x = g.vals[pos];
-            ref.y = has2 ? g.vals[pos + 1] : BA_NONE;
+            ref.y = 2 * ii + 1 < m ? g.vals[pos + 1] : BA_NONE;
+        } else if (r == 1) {
+            ba_ref_level1(g.level1, b, ii, ref.x, ref.y);
         } else {
-            const uint32_t pos = g.list_region[(r - 1) & 1][p] + (in0 + 2 * ii - p_in0);
+            const uint32_t len = off_in[b + 1] - off_in[b];
+            const uint32_t pos = g.list_region[(r - 1) & 1][p] + (off_in[b] + 2 * ii - off_in[g.b_lo[p]]);
             ref.x = pos;
-            ref.y = has2 ? pos + 1 : BA_NONE;
+            ref.y = 2 * ii + 1 < len ? pos + 1 : BA_NONE;
         }
-        g.refs[(size_t)g.ref_region[r][p] + (t - p_slot0)] = ref;
+        g.refs[(size_t)g.ref_region[blockIdx.y][p] + (t - p_slot0)] = ref;
     }
 }
 
 int launch_ba_map(const BaMapGeom& g, uint32_t max_slots, cudaStream_t s)
 {
+    if (g.rounds == 0) return C12381_OK;
     k_ba_map<<<dim3(cdiv(max_slots, 256 * BA_MAP_RUN), g.rounds), 256, 0, s>>>(g);
     C12_LAUNCHED();
     return C12381_OK;

@@ -534,6 +534,30 @@ C12_HD uint32_t ba_bucket_of(const uint32_t* off, uint32_t hint, uint32_t hi, ui
     return lo;
 }
 
+// Round 1 works on the MERGED level-1 lists: bucket b's list is the concatenation, in group order, of what round 0 left of
+// the groups' copies of it (group q's at position region1[q] + off1[q][b] of list buffer 0).  Output slot ii of the bucket adds
+// entries 2 ii and 2 ii + 1 of that concatenation; ry = 0xffffffff when there is no second entry.
+constexpr uint32_t BA_MAX_GROUPS = 4;
+struct BaLevel1 {
+    const uint32_t* off1[BA_MAX_GROUPS];
+    uint32_t region1[BA_MAX_GROUPS];
+    uint32_t groups;
+};
+C12_HD void ba_ref_level1(const BaLevel1& L, uint32_t b, uint32_t ii, uint32_t& rx, uint32_t& ry)
+{
+    uint32_t cum = 0, j = 2 * ii;
+    rx = ry = 0xffffffffu;
+    for (uint32_t q = 0; q < L.groups; ++q) {
+        const uint32_t o = L.off1[q][b], len = L.off1[q][b + 1] - o;
+        if (rx == 0xffffffffu && j < cum + len) {
+            rx = L.region1[q] + o + (j - cum);
+            ++j;
+        }
+        if (rx != 0xffffffffu && ry == 0xffffffffu && j >= cum && j < cum + len) ry = L.region1[q] + o + (j - cum);
+        cum += len;
+    }
+}
+
 // entry j of a bucket's sorted list as a signed affine point
 template <class F> C12_HD Affine<F> ba_fetch(const uint32_t* vals, const Affine<F>* points, uint32_t j)
 {

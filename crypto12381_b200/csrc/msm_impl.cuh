@@ -90,10 +90,11 @@ int launch_chunk_order(const MsmPlan& pl, const uint32_t* start, const uint32_t*
                        uint32_t** order, cudaStream_t s);
 size_t chunk_order_scratch_words(const MsmPlan& pl);
 
-// offsets of the bucket lists after every halving round (msm_common.cu): off[(r - 1) * (total + 1) + b] for r = 1 .. rounds,
-// total + 1 entries each (the last one is the round's slot count)
-size_t ba_plan_scratch_words(uint32_t total, uint32_t rounds);
-int launch_ba_plan(uint32_t total, const uint32_t* start, const uint32_t* end, uint32_t rounds, uint32_t* off, uint32_t* tile_sums, cudaStream_t s);
+// offsets of the bucket lists after k halvings, for a run of levels k (msm_common.cu): total + 1 entries per level, the last
+// one being the level's slot count
+size_t ba_plan_scratch_words(uint32_t total, uint32_t levels);
+int launch_ba_plan(uint32_t total, const uint32_t* start, const uint32_t* end, uint32_t groups, uint32_t gstride, uint32_t first_level, uint32_t levels,
+                   uint32_t* off, uint32_t* tile_sums, cudaStream_t s);
 
 // ---- batch-affine halving rounds (msm_core.cuh "batch-affine halving rounds") -----------------------------------------
 // k_ba_map (msm_common.cu, ONE launch for all rounds, scalar-only: it runs while the points are still being uploaded)
@@ -112,18 +113,22 @@ int launch_ba_plan(uint32_t total, const uint32_t* start, const uint32_t* end, u
 // Pipelines run rounds apart from each other, and the slot numbering shrinks from round to round, so every pipeline keeps its
 // lists, prefixes and slot references in regions of its own, indexed from the start of ITS slot range (k_ba_list_bounds turns
 // the last round's regions into one pair of bound arrays for the accumulation).
-constexpr uint32_t BA_MAX_ROUNDS = 16, BA_MAX_PIPES = 4, BA_NONE = 0xffffffffu;
+constexpr uint32_t BA_MAX_ROUNDS = 16, BA_MAX_PIPES = BA_MAX_GROUPS, BA_NONE = 0xffffffffu;
 
 struct BaMapGeom {
-    const uint32_t* start;      // bucket lists in the sorted array
+    // round 0 (a group's own): its bucket bounds in the sorted array and the sorted (term | sign) values
+    const uint32_t* start;
     const uint32_t* end;
-    const uint32_t* off;        // off[(r - 1) * (total + 1) + b], r = 1 .. rounds (launch_ba_plan)
-    const uint32_t* vals;       // sorted (term | sign) values
-    uint2* refs;                // out: the two inputs of every slot (second = BA_NONE: the odd last entry of a list, carried over)
-    uint32_t total, rounds, pipes;
-    uint32_t b_lo[BA_MAX_PIPES + 1];                    // pipeline p owns buckets [b_lo[p], b_lo[p + 1])
-    uint32_t list_region[2][BA_MAX_PIPES];              // pipeline p's region in list buffer 0 / 1
+    const uint32_t* vals;
+    // the rounds resolved by this launch: first_round .. first_round + rounds - 1, arrays indexed by round - first_round
+    const uint32_t* off_out[BA_MAX_ROUNDS];             // offsets of the round's OUTPUT lists (total + 1 entries): the slot numbering
+    const uint32_t* off_in[BA_MAX_ROUNDS];              // offsets of its INPUT lists (rounds >= 2)
     uint32_t ref_region[BA_MAX_ROUNDS][BA_MAX_PIPES];   // where the slots of (round, pipeline) start in refs[]
+    BaLevel1 level1;            // round 1: a bucket's input list is the concatenation of the groups' level-1 lists (msm_core.cuh)
+    uint2* refs;                // out: the two inputs of every slot (second = BA_NONE: the odd last entry of a list, carried over)
+    uint32_t total, first_round, rounds, pipes;
+    uint32_t b_lo[BA_MAX_PIPES + 1];                    // pipeline p owns buckets [b_lo[p], b_lo[p + 1])
+    uint32_t list_region[2][BA_MAX_PIPES];              // pipeline p's region in list buffer 0 / 1 (rounds >= 2)
 };
 int launch_ba_map(const BaMapGeom& g, uint32_t max_slots, cudaStream_t s);
 
@@ -767,34 +772,40 @@ int sort_pairs_segmented(uint32_t*& keys, uint32_t*& vals, uint32_t*& keys_alt, 
                          uint32_t key_bits, uint32_t* hist, uint32_t* tile_sums, cudaStream_t s);
 size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words);
 
-// Schedule of the batch-affine halving rounds for this plan: how many rounds, which windows each pipeline owns, and for
-// every (round, pipeline) the slots per lane J and the launch bound in warps.  Everything is derived on the host from UPPER
-// bounds (a window holds at most pl.n entries; a round's slot count is at most entries / 2^r + one per bucket); the kernels read
-// the exact slot ranges from the offset arrays on the device.
+// Schedule of the batch-affine halving rounds: how many rounds; round 0 runs per upload GROUP (a group's sorted entries need
+// only that group's points, so its additions start while the later groups are still on the wire), rounds >= 1 run on the merged
+// lists - a bucket's level-1 list is the concatenation of its groups' - in PIPELINES (window groups on their own streams: one's
+// inversion kernel hides behind the other's additions).  For every lane the slots per thread J and the launch bound in warps.
+// Everything is derived on the host from UPPER bounds (a window segment holds at most lp.n entries; a level's slot count is at
+// most entries / 2^k + a few per bucket); the kernels read the exact slot ranges from the offset arrays on the device.
 #ifndef C12_BA_AUTO_MIN_LOG
 #define C12_BA_AUTO_MIN_LOG 22      // automatic rounds only from 2^22 (term, window) entries on: below, a round's launches and its inversion latency cost more than they save
 #endif
-// Ctx::knob: [0] J is chosen so that a pipeline's round still spans about this many waves of resident warps; [1] its upper
+// Ctx::knob: [0] J is chosen so that a lane's round still spans about this many waves of resident warps; [1] its upper
 // limit; [2] the automatic round count stops this many halvings early - lists of a few entries are cheaper to finish with
 // XYZZ additions than with rounds that are all launch and inversion latency
 struct BaSchedule {
-    uint32_t rounds = 0, pipes = 1;
-    uint32_t b_lo[BA_MAX_PIPES + 1];
-    uint32_t J[BA_MAX_ROUNDS][BA_MAX_PIPES], warps[BA_MAX_ROUNDS][BA_MAX_PIPES];
-    uint32_t region[2][BA_MAX_PIPES];     // start of pipeline p's region in ping-pong buffer 0 (round-1 sized) / 1 (round-2 sized)
-    uint32_t ref_region[BA_MAX_ROUNDS][BA_MAX_PIPES];
-    uint32_t final_region[BA_MAX_PIPES];  // start of lane p's region in the last round's output buffer
-    size_t slots[3] = {0, 0, 0};          // sizes of the two ping-pong buffers ([1], [2]) and of the last round's output ([0])
-    size_t refs = 0;                      // slot references of all rounds
-    size_t pool_stride = 0;               // pool entries reserved per pipeline
-    uint32_t max_slots = 0;               // bound on the slot count of round 0 (the largest)
+    uint32_t rounds = 0, groups = 1, pipes = 1, lanes = 1;
+    uint32_t b_lo[BA_MAX_PIPES + 1];                            // pipeline p owns the real buckets [b_lo[p], b_lo[p + 1])
+    uint32_t J0[BA_MAX_PIPES], warps0[BA_MAX_PIPES];            // round 0, per group
+    uint32_t region0[BA_MAX_PIPES];                             // a group's region in list buffer 0 / the prefix array / the round-0 slot references
+    uint32_t slots0 = 0;                                        // bound on one group's level-1 slot count
+    uint32_t J[BA_MAX_ROUNDS][BA_MAX_PIPES], warps[BA_MAX_ROUNDS][BA_MAX_PIPES];   // rounds >= 1, per pipeline
+    uint32_t ref_region[BA_MAX_ROUNDS][BA_MAX_PIPES];           // rounds >= 1: where (round, pipeline)'s slot references start
+    uint32_t region[2][BA_MAX_PIPES];                           // rounds >= 1: pipeline p's region in list buffer (round & 1)
+    uint32_t scratch_region[BA_MAX_PIPES];                      // rounds >= 1: pipeline p's region in the prefix array
+    uint32_t final_region[BA_MAX_PIPES];                        // where the last round writes (buffer 2; one round only: buffer 0 by group)
+    uint32_t slots_merged = 0;                                  // bound on the level-2 slot count (all pipelines)
+    // list buffers: [0] level 1 (round 0's output, by group), [1] / [3] the odd / even rounds >= 1 (by pipeline), [2] the last
+    // round.  The pipelines run rounds apart from each other, so no buffer a pipeline still reads is ever another one's target.
+    size_t buf[4] = {0, 0, 0, 0}, prefix = 0, refs = 0, pool_stride = 0;
 };
 
-inline BaSchedule msm_ba_schedule(const MsmPlan& pl)
+inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp)
 {
     BaSchedule sc;
     const Ctx& c = ctx();
-    const uint64_t N = (uint64_t)pl.n * pl.windows;
+    const uint64_t N = (uint64_t)lp.n * lp.windows;
     if (c.ba_rounds == 0 || N >= (1ull << 31) || pl.total == 0) return sc;
     uint32_t R = 0;
     while (R < 12 && (1ull << R) * pl.total < 2 * N) ++R;      // lists of twice the mean load would end up as single sums
@@ -806,50 +817,64 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl)
         R = R > (uint32_t)c.knob[2] ? R - (uint32_t)c.knob[2] : 0;
     if (R == 0) return sc;
     sc.rounds = R > BA_MAX_ROUNDS ? BA_MAX_ROUNDS : R;
+    sc.groups = lp.groups;
     sc.pipes = (uint32_t)c.ba_pipes < pl.windows ? (uint32_t)c.ba_pipes : pl.windows;
     if (sc.pipes < 1) sc.pipes = 1;
-    if (pl.groups > 1) sc.pipes = pl.groups;       // one pipeline per upload group: it starts when its group's points are there
+    sc.lanes = sc.groups > sc.pipes ? sc.groups : sc.pipes;
     const uint32_t resident = (uint32_t)(c.sm_count > 0 ? c.sm_count : 148) * (C12_BA_THREADS / 32) * 3;
+    const uint64_t jmax = c.knob[1] > 2 ? (uint64_t)c.knob[1] : 2, waves = (uint64_t)(c.knob[0] > 0 ? c.knob[0] : 1);
+    auto shape = [&](size_t slots, uint32_t& J, uint32_t& warps) {
+        uint64_t j = slots / (32ull * resident * waves);
+        j = j < 2 ? 2 : (j > jmax ? jmax : j);
+        J = (uint32_t)j;
+        warps = (uint32_t)((slots + 32 * j - 1) / (32 * j));
+        if (warps + 1 > sc.pool_stride) sc.pool_stride = warps + 1;
+    };
     for (uint32_t p = 0; p <= sc.pipes; ++p) sc.b_lo[p] = (pl.windows * p / sc.pipes) * pl.half;
-    // cap(k, p): bound on pipeline p's slot count in the numbering of round k (lists after k halvings)
+    // round 0: group g's level-1 lists hold at most (its entries) / 2 + one per bucket slots
+    const size_t cap0 = (size_t)(((uint64_t)pl.windows * lp.n) >> 1) + pl.total + 1;
+    sc.slots0 = (uint32_t)cap0;
+    for (uint32_t g = 0; g < sc.groups; ++g) {
+        sc.region0[g] = (uint32_t)(g * cap0);
+        shape(cap0, sc.J0[g], sc.warps0[g]);
+    }
+    // level k >= 2 of pipeline p: ceil(M1_b / 2^(k-1)) <= m_b / 2^k + groups + 1 per bucket
     auto cap = [&](uint32_t k, uint32_t p) {
         const uint64_t wins = (sc.b_lo[p + 1] - sc.b_lo[p]) / pl.half;
-        return (size_t)((wins * pl.n) >> k) + (size_t)wins * pl.half + 1;
+        return (size_t)((wins * lp.n * lp.groups) >> k) + (size_t)wins * pl.half * (lp.groups + 1) + 1;
     };
-    size_t ref_base = 0;
-    for (uint32_t r = 0; r < sc.rounds; ++r) {
+    size_t ref_base = cap0 * sc.groups;
+    for (uint32_t r = 1; r < sc.rounds; ++r) {
         size_t base = 0;
         for (uint32_t p = 0; p < sc.pipes; ++p) {
-            const size_t slots = cap(r + 1, p);
-            const uint64_t jmax = c.knob[1] > 2 ? (uint64_t)c.knob[1] : 2;
-            uint64_t J = slots / (32ull * resident * (uint64_t)(c.knob[0] > 0 ? c.knob[0] : 1));
-            J = J < 2 ? 2 : (J > jmax ? jmax : J);
-            sc.J[r][p] = (uint32_t)J;
-            sc.warps[r][p] = (uint32_t)((slots + 32 * J - 1) / (32 * J));
-            if (sc.warps[r][p] + 1 > sc.pool_stride) sc.pool_stride = sc.warps[r][p] + 1;
+            shape(cap(r + 1, p), sc.J[r][p], sc.warps[r][p]);
             sc.ref_region[r][p] = (uint32_t)(ref_base + base);
-            base += slots;
+            base += cap(r + 1, p);
         }
-        if (r == 0) sc.max_slots = (uint32_t)base;
+        if (r == 1) sc.slots_merged = (uint32_t)base;
         ref_base += base;
     }
     sc.refs = ref_base;
-    for (uint32_t k = 1; k <= 2; ++k) {
+    size_t lvl[4] = {0, 0, 0, 0};           // total capacity of levels 2, 3 and the last
+    for (uint32_t k = 2; k <= 3; ++k) {
         size_t base = 0;
         for (uint32_t p = 0; p < sc.pipes; ++p) {
-            sc.region[k - 1][p] = (uint32_t)base;
+            sc.region[(k - 1) & 1][p] = (uint32_t)base;           // level k is the output of round k - 1: buffer (k - 1) & 1
+            if (k == 2) sc.scratch_region[p] = (uint32_t)base;
             base += cap(k, p);
         }
-        sc.slots[k] = base;
+        lvl[k] = base;
     }
-    {
-        size_t base = 0;
-        for (uint32_t p = 0; p < sc.pipes; ++p) {
-            sc.final_region[p] = (uint32_t)base;
-            base += cap(sc.rounds, p);
-        }
-        sc.slots[0] = base;
+    size_t fin = 0;
+    for (uint32_t p = 0; p < sc.pipes; ++p) {
+        sc.final_region[p] = (uint32_t)fin;
+        fin += cap(sc.rounds, p);
     }
+    sc.buf[0] = cap0 * sc.groups;
+    sc.buf[1] = sc.rounds > 1 ? lvl[2] : 1;
+    sc.buf[2] = sc.rounds > 1 ? fin : 1;
+    sc.buf[3] = sc.rounds > 2 ? lvl[3] : 1;
+    sc.prefix = cap0 * sc.groups > lvl[2] ? cap0 * sc.groups : lvl[2];
     return sc;
 }
 
@@ -862,78 +887,55 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     size_t b = 0;
     b += align_up(sizeof(Affine<F>) * (size_t)pl.n);
     b += 4 * align_up(4 * N);
-    b += align_up(4 * hist_words) + align_up(4 * tile_words);
+    b += align_up(4 * hist_words) + align_up(4 * (tile_words + 16));
     b += 2 * align_up(4 * (size_t)lp.total);
-    b += align_up(4 * chunk_order_scratch_words(lp)) + align_up(sizeof(Proj<F>) * (size_t)lp.vmax);
+    b += align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(lp);
+    const BaSchedule sc = msm_ba_schedule(pl, lp);
     if (sc.rounds) {
-        // offsets and plan scratch: one array per upload group (+ one entry each), the list bounds of the accumulation
-        b += align_up(4 * (size_t)sc.rounds * ((size_t)lp.total + lp.groups)) + align_up(4 * lp.groups * ba_plan_scratch_words(lp.total / lp.groups, sc.rounds));
-        b += 2 * align_up(4 * ((size_t)lp.total + 1));
-        b += align_up(sizeof(Affine<F>) * sc.slots[1]) + align_up(sizeof(Affine<F>) * sc.slots[2]) + align_up(sizeof(Affine<F>) * sc.slots[0]);
-        b += align_up(sizeof(F) * sc.slots[1]) + align_up(8 * sc.refs);
-        b += align_up(sizeof(F) * sc.pool_stride * sc.pipes) + align_up(sizeof(F) * sc.pool_stride * sc.pipes * 32);
+        // level offsets: one level-1 array per group, levels 2 .. rounds merged; the plan scratch of both; the list bounds
+        b += align_up(4 * (size_t)(sc.groups + sc.rounds) * ((size_t)pl.total + 1));
+        b += align_up(4 * (sc.groups + 1) * ba_plan_scratch_words(pl.total, sc.rounds));
+        b += 2 * align_up(4 * ((size_t)pl.total + 1));
+        for (int k = 0; k < 4; ++k) b += align_up(sizeof(Affine<F>) * sc.buf[k]);
+        b += align_up(sizeof(F) * sc.prefix) + align_up(8 * sc.refs);
+        b += align_up(sizeof(F) * sc.pool_stride * sc.lanes) + align_up(sizeof(F) * sc.pool_stride * sc.lanes * 32);
     }
     b += align_up(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS) * (1 + 2 * PlaneShape<F>::SPLITS) + align_up(4 * (size_t)pl.windows * MSM_WPART_SLOTS);
     return b + 65536;
 }
 
-// one lane of the halving rounds: a pipeline (window group) of the single group, or a whole upload group
+// one lane of a halving round
 template <class F> struct BaLaneArgs {
     cudaStream_t stream;
-    const uint32_t* off;        // the offsets of the lane's group: off[r * (total + 1) + b]
-    uint32_t total;             // buckets of that group
-    uint32_t b_lo, b_hi;        // the lane's buckets in it
+    BaGeom g;
+    BaIo<F> io;
+    uint32_t warps;
+    bool first;
 };
 
-// the halving rounds of all lanes, issued round by round (lane p on lanes[p].stream, already ordered behind whatever that
-// lane needs).  The slot references (launch_ba_map) are in place.  E[2] receives the reduced lists, lane by lane.
-template <class F>
-int msm_ba_rounds_run(const BaSchedule& sc, const BaLaneArgs<F>* lanes, const Affine<F>* pts, const uint2* refs, Affine<F>* const E[3], F* prefix,
-                      F* pool, F* others)
+template <class F> int msm_ba_round_launch(const BaLaneArgs<F>& a)
 {
-    Ctx& c = ctx();
-    for (uint32_t r = 0; r < sc.rounds; ++r) {
-        for (uint32_t p = 0; p < sc.pipes; ++p) {
-            cudaStream_t sp = lanes[p].stream;
-            const bool last = r + 1 == sc.rounds;
-            BaGeom g;
-            g.off_out = lanes[p].off + (size_t)r * (lanes[p].total + 1);
-            g.refs = refs + sc.ref_region[r][p];
-            g.b_lo = lanes[p].b_lo;
-            g.b_hi = lanes[p].b_hi;
-            g.J = sc.J[r][p];
-            g.out_region = last ? sc.final_region[p] : sc.region[r & 1][p];
-            g.scratch_region = sc.region[0][p];
-            BaIo<F> io;
-            io.pts = pts;
-            io.lists = r ? E[(r - 1) & 1] : nullptr;
-            io.out = last ? E[2] : E[r & 1];
-            io.prefix = prefix;
-            io.pool = pool + (size_t)p * sc.pool_stride;
-            io.others = others + (size_t)p * sc.pool_stride * 32;
-            const unsigned blocks = cdiv(sc.warps[r][p], C12_BA_THREADS / 32);
-            if (r == 0)
-                k_ba_fwd<F, true><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
-            else
-                k_ba_fwd<F, false><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
-            C12_LAUNCHED();
-            k_ba_inv<F><<<cdiv(sc.warps[r][p], 128), 128, 0, sp>>>(g, io.pool);
-            C12_LAUNCHED();
-            if (r == 0)
-                k_ba_bwd<F, true><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
-            else
-                k_ba_bwd<F, false><<<blocks, C12_BA_THREADS, 0, sp>>>(g, io);
-            C12_LAUNCHED();
-        }
-    }
+    const unsigned blocks = cdiv(a.warps, C12_BA_THREADS / 32);
+    if (a.first)
+        k_ba_fwd<F, true><<<blocks, C12_BA_THREADS, 0, a.stream>>>(a.g, a.io);
+    else
+        k_ba_fwd<F, false><<<blocks, C12_BA_THREADS, 0, a.stream>>>(a.g, a.io);
+    C12_LAUNCHED();
+    k_ba_inv<F><<<cdiv(a.warps, 128), 128, 0, a.stream>>>(a.g, a.io.pool);
+    C12_LAUNCHED();
+    if (a.first)
+        k_ba_bwd<F, true><<<blocks, C12_BA_THREADS, 0, a.stream>>>(a.g, a.io);
+    else
+        k_ba_bwd<F, false><<<blocks, C12_BA_THREADS, 0, a.stream>>>(a.g, a.io);
+    C12_LAUNCHED();
     return C12381_OK;
 }
 
 // the plans of an n-term MSM under the current settings: window width, then the list-side plan for `groups` upload groups
-// (groups only exist where the halving rounds run - they are what makes the lists independent of the later groups' points)
+// (groups only exist where at least two halving rounds run: round 0 is what makes a group's lists independent of the later
+// groups' points, the merged rounds behind it are what keeps the groups from costing anything)
 template <class F> bool msm_plans(size_t n, uint32_t groups, MsmPlan& pl, MsmPlan& lp)
 {
     if (n == 0 || n > (1ull << 26) / MsmTraits<F>::PARTS * 2) return false;
@@ -943,7 +945,7 @@ template <class F> bool msm_plans(size_t n, uint32_t groups, MsmPlan& pl, MsmPla
     pl = msm_make_plan((uint32_t)n, cbits, parts, ctx().knob[3] > 0 ? (uint32_t)ctx().knob[3] : 0u);
     if (groups > BA_MAX_PIPES) groups = BA_MAX_PIPES;
     lp = msm_list_plan(pl, groups);
-    if (groups > 1 && msm_ba_schedule(lp).rounds == 0) lp = pl;
+    if (groups > 1 && msm_ba_schedule(pl, lp).rounds < 2) lp = pl;
     return true;
 }
 
@@ -960,9 +962,9 @@ template <class F> size_t msm_scratch_for(size_t n, uint32_t groups = 1)
 // Everything is enqueued on `s` (and the context's side streams, forked from and joined back into `s`); malformed input is
 // reported through the context flag word (c12381_sync_status / the host entry's return code), never by a different code path.
 // scalars_ready / points_ready: optional events, one per upload group, after which that group's slice of d_scalars / d_points is
-// valid.  The host entries upload group by group on a second stream; every group is a pipeline of its own from its scalars to
-// its reduced bucket lists (recode, sort, bounds, slot map; then parse and the halving rounds), so group 0's additions start
-// while the later groups are still on the wire.  The groups are ceil(n / groups) consecutive terms each.
+// valid.  The host entries upload group by group on a second stream; every group is a lane of its own from its scalars to its
+// level-1 lists (recode, sort, bounds, slot map; then parse and round 0), so group 0's additions start while the later groups are
+// still on the wire; the rounds behind that run on the merged lists.  The groups are ceil(n / groups) consecutive terms each.
 template <class F>
 int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint8_t* d_out, int out_mode, cudaStream_t s,
             uint32_t groups = 1, const cudaEvent_t* scalars_ready = nullptr, const cudaEvent_t* points_ready = nullptr)
@@ -980,7 +982,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     const uint32_t groups_req = groups;
     groups = lp.groups;
     const size_t N = (size_t)lp.n * lp.windows;
-    const uint32_t gtotal = lp.total / groups;                  // buckets of one group
+    const uint32_t B = pl.total;                                // real buckets; group g's copy of bucket b is list g * B + b
 
     int rc;
     const size_t hist_words = sort_scratch_words(lp.n, lp.windows, nullptr);
@@ -995,27 +997,27 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* tiles = (uint32_t*)arena_take(4 * (size_t)groups * (gtile_words + 2));
     uint32_t* start = (uint32_t*)arena_take(4 * (size_t)lp.total);
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)lp.total);
-    uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(lp));
-    Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)lp.vmax);
+    uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));
+    Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(lp);
-    uint32_t *ba_off = nullptr, *ba_tiles = nullptr, *ba_lstart = nullptr, *ba_lend = nullptr;
+    const BaSchedule sc = msm_ba_schedule(pl, lp);
+    const uint32_t R = sc.rounds;
+    uint32_t *off1 = nullptr, *offm = nullptr, *ba_tiles = nullptr, *ba_lstart = nullptr, *ba_lend = nullptr;
     uint2* ba_refs = nullptr;
-    Affine<F>* ba_lists[3] = {nullptr, nullptr, nullptr};   // the two ping-pong buffers and the last round's output
+    Affine<F>* E[4] = {nullptr, nullptr, nullptr, nullptr};    // list buffers (BaSchedule::buf)
     F *ba_prefix = nullptr, *ba_pool = nullptr, *ba_others = nullptr;
-    const size_t off_words = (size_t)sc.rounds * ((size_t)gtotal + 1), plan_words = ba_plan_scratch_words(gtotal, sc.rounds ? sc.rounds : 1);
-    if (sc.rounds) {
-        ba_off = (uint32_t*)arena_take(4 * off_words * groups);
-        ba_tiles = (uint32_t*)arena_take(4 * plan_words * groups);
-        ba_lstart = (uint32_t*)arena_take(4 * ((size_t)lp.total + 1));
-        ba_lend = (uint32_t*)arena_take(4 * ((size_t)lp.total + 1));
-        ba_lists[0] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[1]);
-        ba_lists[1] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[2]);
-        ba_lists[2] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.slots[0]);
-        ba_prefix = (F*)arena_take(sizeof(F) * sc.slots[1]);
+    const size_t lvl_words = (size_t)B + 1, plan_words = ba_plan_scratch_words(B, R ? R : 1);
+    if (R) {
+        off1 = (uint32_t*)arena_take(4 * lvl_words * groups);                  // level 1, per group
+        offm = (uint32_t*)arena_take(4 * lvl_words * R);                       // levels 2 .. R, merged: level k at (k - 2) * lvl_words
+        ba_tiles = (uint32_t*)arena_take(4 * plan_words * (groups + 1));
+        ba_lstart = (uint32_t*)arena_take(4 * lvl_words);
+        ba_lend = (uint32_t*)arena_take(4 * lvl_words);
+        for (int k = 0; k < 4; ++k) E[k] = (Affine<F>*)arena_take(sizeof(Affine<F>) * sc.buf[k]);
+        ba_prefix = (F*)arena_take(sizeof(F) * sc.prefix);
         ba_refs = (uint2*)arena_take(8 * sc.refs);
-        ba_pool = (F*)arena_take(sizeof(F) * sc.pool_stride * sc.pipes);
-        ba_others = (F*)arena_take(sizeof(F) * sc.pool_stride * sc.pipes * 32);
+        ba_pool = (F*)arena_take(sizeof(F) * sc.pool_stride * sc.lanes);
+        ba_others = (F*)arena_take(sizeof(F) * sc.pool_stride * sc.lanes * 32);
     }
     Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
@@ -1026,15 +1028,19 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
     C12_CUDA(cudaEventRecord(c.pev[0], s));
-    // ---- the scalar-only stages, group by group: recode, sort, bucket bounds, round offsets, slot map ---------------------
-    // group g > 0 runs on side stream g - 1, forked off `s` here (the arena is ours from this point of `s` on)
-    if (groups > 1) {
+    // Streams: group g runs on `s` (g = 0) or side stream g - 1; with several groups the merged plan runs on the plan stream so
+    // that it does not hold up group 0's round 0; pipeline p of the merged rounds on `s` (p = 0) or side stream p - 1.
+    auto lane_stream = [&](uint32_t i) { return i ? c.side[i - 1] : s; };
+    cudaStream_t plan_stream = groups > 1 ? c.plan_stream : s;
+    if (groups > 1) {           // the arena is ours from this point of `s` on
         C12_CUDA(cudaEventRecord(c.side_ev[0], s));
         for (uint32_t g = 1; g < groups; ++g) C12_CUDA(cudaStreamWaitEvent(c.side[g - 1], c.side_ev[0], 0));
+        C12_CUDA(cudaStreamWaitEvent(plan_stream, c.side_ev[0], 0));
     }
+    // ---- per group: the scalar-only stages (recode, sort, bucket bounds, level-1 offsets, round-0 slot map) -----------------
     uint32_t *skeys = keys, *svals = vals;       // where the sorted pairs end up (the passes ping-pong between the two buffers)
     for (uint32_t g = 0; g < groups; ++g) {
-        cudaStream_t sg = g ? c.side[g - 1] : s;
+        cudaStream_t sg = lane_stream(g);
         if (scalars_ready) {
             if (groups > 1)
                 C12_CUDA(cudaStreamWaitEvent(sg, scalars_ready[g], 0));
@@ -1053,107 +1059,175 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         if (g == 0) C12_CUDA(cudaEventRecord(c.pev[2], s));
         rc = launch_bucket_bounds(lp, g * pl.windows, pl.windows, skeys, start, end, sg);
         if (rc) return rc;
-        if (sc.rounds) {
-            uint32_t* off_g = ba_off + g * off_words;
-            rc = launch_ba_plan(gtotal, start + (size_t)g * gtotal, end + (size_t)g * gtotal, sc.rounds, off_g, ba_tiles + g * plan_words, sg);
+        if (R) {
+            uint32_t* off1_g = off1 + g * lvl_words;
+            rc = launch_ba_plan(B, start + (size_t)g * B, end + (size_t)g * B, 1, 0, 1, 1, off1_g, ba_tiles + g * plan_words, sg);
             if (rc) return rc;
-            // the lanes of this group: the schedule's pipelines (one group: window groups of it; upload groups: the group itself)
+            if (groups > 1) C12_CUDA(cudaEventRecord(c.msm_ev[g], sg));             // this group's bounds and level-1 offsets are in place
             BaMapGeom mg;
-            mg.start = start + (size_t)g * gtotal;
-            mg.end = end + (size_t)g * gtotal;
-            mg.off = off_g;
+            mg.start = start + (size_t)g * B;
+            mg.end = end + (size_t)g * B;
             mg.vals = svals;
+            mg.off_out[0] = off1_g;
+            mg.off_in[0] = nullptr;
+            mg.ref_region[0][0] = sc.region0[g];
+            mg.level1.groups = 0;
             mg.refs = ba_refs;
-            mg.total = gtotal;
-            mg.rounds = sc.rounds;
-            mg.pipes = groups > 1 ? 1 : sc.pipes;
-            for (uint32_t p = 0; p < mg.pipes; ++p) {
-                const uint32_t lane = groups > 1 ? g : p;
-                mg.b_lo[p] = groups > 1 ? 0 : sc.b_lo[p];
-                mg.list_region[0][p] = sc.region[0][lane];
-                mg.list_region[1][p] = sc.region[1][lane];
-                for (uint32_t r = 0; r < sc.rounds; ++r) mg.ref_region[r][p] = sc.ref_region[r][lane];
-            }
-            mg.b_lo[mg.pipes] = gtotal;
-            rc = launch_ba_map(mg, groups > 1 ? sc.max_slots / groups + 1 : sc.max_slots, sg);
+            mg.total = B;
+            mg.first_round = 0;
+            mg.rounds = 1;
+            mg.pipes = 1;
+            mg.b_lo[0] = 0;
+            mg.b_lo[1] = B;
+            rc = launch_ba_map(mg, sc.slots0, sg);
             if (rc) return rc;
         }
     }
-    // ---- the points: all at once in front of everything that reads them, or each upload group in front of its own lane -------
+    // ---- the merged levels: offsets of levels 2 .. R, slot maps of rounds 1 .. R - 1, the lists left for the accumulation ------
     uint32_t *order = nullptr, *vstart = nullptr, *vbucket = nullptr;
     const uint32_t *lstart = start, *lend = end;
-    BaLaneArgs<F> lanes[BA_MAX_PIPES];
-    BaListGeom lg;
-    if (sc.rounds) {
-        lg.lanes = sc.pipes;
-        lg.vtotal = lp.total;
-        for (uint32_t p = 0; p < sc.pipes; ++p) {
-            const uint32_t g = groups > 1 ? p : 0;
-            lanes[p].stream = p ? c.side[p - 1] : s;
-            lanes[p].off = ba_off + g * off_words;
-            lanes[p].total = gtotal;
-            lanes[p].b_lo = groups > 1 ? 0 : sc.b_lo[p];
-            lanes[p].b_hi = groups > 1 ? gtotal : sc.b_lo[p + 1];
-            lg.off[p] = lanes[p].off + (size_t)(sc.rounds - 1) * (gtotal + 1);
-            lg.b_lo[p] = lanes[p].b_lo;
-            lg.vb0[p] = sc.b_lo[p];
-            lg.final_region[p] = sc.final_region[p];
+    const Affine<F>* final_lists = nullptr;
+    if (groups > 1)
+        for (uint32_t g = 0; g < groups; ++g) C12_CUDA(cudaStreamWaitEvent(plan_stream, c.msm_ev[g], 0));
+    if (R) {
+        rc = launch_ba_plan(B, start, end, groups, B, 2, R - 1, offm, ba_tiles + groups * plan_words, plan_stream);
+        if (rc) return rc;
+        if (R > 1) {
+            BaMapGeom mg;
+            mg.start = mg.end = mg.vals = nullptr;
+            for (uint32_t r = 1; r < R; ++r) {
+                mg.off_out[r - 1] = offm + (size_t)(r - 1) * lvl_words;                       // level r + 1
+                mg.off_in[r - 1] = r >= 2 ? offm + (size_t)(r - 2) * lvl_words : nullptr;     // level r
+                for (uint32_t p = 0; p < sc.pipes; ++p) mg.ref_region[r - 1][p] = sc.ref_region[r][p];
+            }
+            for (uint32_t g = 0; g < groups; ++g) {
+                mg.level1.off1[g] = off1 + g * lvl_words;
+                mg.level1.region1[g] = sc.region0[g];
+            }
+            mg.level1.groups = groups;
+            mg.refs = ba_refs;
+            mg.total = B;
+            mg.first_round = 1;
+            mg.rounds = R - 1;
+            mg.pipes = sc.pipes;
+            for (uint32_t p = 0; p <= sc.pipes; ++p) mg.b_lo[p] = sc.b_lo[p];
+            for (uint32_t p = 0; p < sc.pipes; ++p) {
+                mg.list_region[0][p] = sc.region[0][p];
+                mg.list_region[1][p] = sc.region[1][p];
+            }
+            rc = launch_ba_map(mg, sc.slots_merged, plan_stream);
+            if (rc) return rc;
         }
-        lg.vb0[sc.pipes] = lp.total;
+        // what the rounds leave: level R - of the pipelines in buffer 2, or (one round only) of the single group in buffer 0
+        BaListGeom lg;
+        lg.lanes = R > 1 ? sc.pipes : 1;
+        lg.vtotal = B;
+        for (uint32_t p = 0; p < lg.lanes; ++p) {
+            lg.off[p] = R > 1 ? offm + (size_t)(R - 2) * lvl_words : off1;
+            lg.b_lo[p] = R > 1 ? sc.b_lo[p] : 0;
+            lg.vb0[p] = R > 1 ? sc.b_lo[p] : 0;
+            lg.final_region[p] = R > 1 ? sc.final_region[p] : sc.region0[0];
+        }
+        lg.vb0[lg.lanes] = B;
+        final_lists = R > 1 ? E[2] : E[0];
+        rc = launch_ba_list_bounds(lg, ba_lstart, ba_lend, plan_stream);
+        if (rc) return rc;
         lstart = ba_lstart;
         lend = ba_lend;
     }
-    if (groups == 1) {
-        // one group: the lists the accumulation will walk are known from the scalars alone - cut them into chunks now
-        if (sc.rounds) {
-            rc = launch_ba_list_bounds(lg, ba_lstart, ba_lend, s);
+    // bucket lists longer than pl.chunk entries are cut into chunks (XYZZ additions, one thread per chunk)
+    rc = launch_chunk_order(pl, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, plan_stream);
+    if (rc) return rc;
+    if (groups > 1) C12_CUDA(cudaEventRecord(c.msm_ev[BA_MAX_PIPES], plan_stream));
+    // ---- the points, group by group; round 0 of each group behind them ------------------------------------------------------
+    for (uint32_t g = 0; g < groups; ++g) {
+        cudaStream_t sg = lane_stream(g);
+        if (points_ready) {
+            if (groups > 1)
+                C12_CUDA(cudaStreamWaitEvent(sg, points_ready[g], 0));
+            else
+                for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(s, points_ready[q], 0));
+        }
+        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[3], s));
+        const uint32_t first = g * lp.n_group, last = first + lp.n_group < n ? first + lp.n_group : n;
+        if (first < last) {
+            k_parse_points<F><<<cdiv(last - first, 128), 128, 0, sg>>>(d_points, first, last, n, pl.parts, pts, flags_word());
+            C12_LAUNCHED();
+        }
+        if (g == 0) {
+            C12_CUDA(cudaEventRecord(c.ev[1], s));
+            C12_CUDA(cudaEventRecord(c.pev[4], s));
+        }
+        if (R) {
+            BaLaneArgs<F> a;
+            a.stream = sg;
+            a.first = true;
+            a.warps = sc.warps0[g];
+            a.g.off_out = off1 + g * lvl_words;
+            a.g.refs = ba_refs + sc.region0[g];
+            a.g.b_lo = 0;
+            a.g.b_hi = B;
+            a.g.J = sc.J0[g];
+            a.g.out_region = sc.region0[g];
+            a.g.scratch_region = sc.region0[g];
+            a.io.pts = pts;
+            a.io.lists = nullptr;
+            a.io.out = E[0];
+            a.io.prefix = ba_prefix;
+            a.io.pool = ba_pool + (size_t)g * sc.pool_stride;
+            a.io.others = ba_others + (size_t)g * sc.pool_stride * 32;
+            rc = msm_ba_round_launch<F>(a);
             if (rc) return rc;
         }
-        rc = launch_chunk_order(lp, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
-        if (rc) return rc;
-        if (points_ready)
-            for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(s, points_ready[q], 0));
-        C12_CUDA(cudaEventRecord(c.pev[3], s));
-        k_parse_points<F><<<cdiv(n, 128), 128, 0, s>>>(d_points, 0, n, n, pl.parts, pts, flags_word());
-        C12_LAUNCHED();
-        if (sc.pipes > 1) {     // the pipelines of the single group fork here, behind the parsed points
+    }
+    if (groups > 1) {           // join: all level-1 lists and the merged plan
+        for (uint32_t g = 1; g < groups; ++g) {
+            C12_CUDA(cudaEventRecord(c.side_ev[g], c.side[g - 1]));
+            C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[g], 0));
+        }
+        C12_CUDA(cudaStreamWaitEvent(s, c.msm_ev[BA_MAX_PIPES], 0));
+    }
+    // ---- rounds 1 .. R - 1 on the merged lists, pipeline by pipeline ------------------------------------------------------------
+    if (R > 1) {
+        if (sc.pipes > 1) {
             C12_CUDA(cudaEventRecord(c.side_ev[0], s));
             for (uint32_t p = 1; p < sc.pipes; ++p) C12_CUDA(cudaStreamWaitEvent(c.side[p - 1], c.side_ev[0], 0));
         }
-    } else {
-        for (uint32_t g = 0; g < groups; ++g) {
-            cudaStream_t sg = g ? c.side[g - 1] : s;
-            if (points_ready) C12_CUDA(cudaStreamWaitEvent(sg, points_ready[g], 0));
-            if (g == 0) C12_CUDA(cudaEventRecord(c.pev[3], s));
-            const uint32_t first = g * lp.n_group, last = first + lp.n_group < n ? first + lp.n_group : n;
-            if (first < last) {
-                k_parse_points<F><<<cdiv(last - first, 128), 128, 0, sg>>>(d_points, first, last, n, pl.parts, pts, flags_word());
-                C12_LAUNCHED();
+        for (uint32_t r = 1; r < R; ++r) {
+            for (uint32_t p = 0; p < sc.pipes; ++p) {
+                const bool last = r + 1 == R;
+                BaLaneArgs<F> a;
+                a.stream = lane_stream(p);
+                a.first = false;
+                a.warps = sc.warps[r][p];
+                a.g.off_out = offm + (size_t)(r - 1) * lvl_words;
+                a.g.refs = ba_refs + sc.ref_region[r][p];
+                a.g.b_lo = sc.b_lo[p];
+                a.g.b_hi = sc.b_lo[p + 1];
+                a.g.J = sc.J[r][p];
+                a.g.out_region = last ? sc.final_region[p] : sc.region[r & 1][p];
+                a.g.scratch_region = sc.scratch_region[p];
+                a.io.pts = nullptr;
+                a.io.lists = r == 1 ? E[0] : (((r - 1) & 1) ? E[1] : E[3]);
+                a.io.out = last ? E[2] : ((r & 1) ? E[1] : E[3]);
+                a.io.prefix = ba_prefix;
+                a.io.pool = ba_pool + (size_t)p * sc.pool_stride;
+                a.io.others = ba_others + (size_t)p * sc.pool_stride * 32;
+                rc = msm_ba_round_launch<F>(a);
+                if (rc) return rc;
             }
         }
-    }
-    C12_CUDA(cudaEventRecord(c.ev[1], s));
-    C12_CUDA(cudaEventRecord(c.pev[4], s));
-    if (sc.rounds) {
-        rc = msm_ba_rounds_run<F>(sc, lanes, pts, ba_refs, ba_lists, ba_prefix, ba_pool, ba_others);
-        if (rc) return rc;
-        for (uint32_t p = 1; p < sc.pipes; ++p) {       // join
+        for (uint32_t p = 1; p < sc.pipes; ++p) {
             C12_CUDA(cudaEventRecord(c.side_ev[p], c.side[p - 1]));
             C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[p], 0));
         }
-        if (groups > 1) {
-            // what the rounds left of every group's lists, as one pair of bound arrays; cut into chunks
-            rc = launch_ba_list_bounds(lg, ba_lstart, ba_lend, s);
-            if (rc) return rc;
-            rc = launch_chunk_order(lp, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, s);
-            if (rc) return rc;
-        }
-        k_accumulate<F, true><<<cdiv(lp.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(lp.vmax, lp.chunk, lstart, lend, nullptr, ba_lists[2], order, vbucket, vstart, vpartial);
-    } else {
-        k_accumulate<F, false><<<cdiv(lp.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(lp.vmax, lp.chunk, start, end, svals, pts, order, vbucket, vstart, vpartial);
     }
+    if (R)
+        k_accumulate<F, true><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, lstart, lend, nullptr, final_lists, order, vbucket, vstart, vpartial);
+    else
+        k_accumulate<F, false><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, start, end, svals, pts, order, vbucket, vstart, vpartial);
     C12_LAUNCHED();
-    k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, groups, vstart, vpartial, buckets);
+    k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, 1, vstart, vpartial, buckets);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));

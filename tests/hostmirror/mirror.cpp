@@ -81,40 +81,78 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
         }
     } else {
         // the batch-affine halving rounds (k_ba_fwd / k_ba_inv / k_ba_bwd over the flat slot space), one inversion per pair here
-        // instead of one per 32 J additions; then the accumulation over what the rounds leave (k_accumulate<F, true>)
-        std::vector<std::vector<uint32_t>> off(rounds + 1, std::vector<uint32_t>(pl.total + 1, 0));
-        for (uint32_t r = 1; r <= rounds; ++r)
-            for (uint32_t b = 0; b < pl.total; ++b) off[r][b + 1] = off[r][b] + ba_len(end[b] - start[b], r);
-        std::vector<Affine<F>> cur, next;
-        for (uint32_t r = 0; r < rounds; ++r) {
-            const uint32_t* off_in = r ? off[r].data() : start.data();
-            const uint32_t* off_out = off[r + 1].data();
-            next.assign(off_out[pl.total], affine_inf<F>());
+        // instead of one per 32 J additions: round 0 per upload group on its own copies of the buckets, the rounds behind it on
+        // the merged lists (a bucket's level-1 list = the concatenation of its groups', ba_ref_level1), then the accumulation over
+        // what the rounds leave (k_accumulate<F, true>) on the REAL buckets
+        const uint32_t B = rpl.total, G = groups;
+        auto add_pair = [&](const Affine<F>& X, const Affine<F>& Y) {
+            F den;
+            int kind = ba_denominator(X, Y, den);
+            return ba_finish(X, Y, kind, inv(den));
+        };
+        // round 0
+        std::vector<std::vector<uint32_t>> off1(G, std::vector<uint32_t>(B + 1, 0));
+        std::vector<uint32_t> region1(G, 0);
+        for (uint32_t g = 0; g < G; ++g) {
+            for (uint32_t b = 0; b < B; ++b) off1[g][b + 1] = off1[g][b] + ba_len(end[(size_t)g * B + b] - start[(size_t)g * B + b], 1);
+            if (g + 1 < G) region1[g + 1] = region1[g] + off1[g][B] + 3;     // regions apart, as the capacity-based ones on the device
+        }
+        std::vector<Affine<F>> lvl1(region1[G - 1] + off1[G - 1][B] + 3, affine_inf<F>());
+        for (uint32_t g = 0; g < G; ++g) {
             uint32_t hint = 0;
-            for (uint32_t slot = 0; slot < off_out[pl.total]; ++slot) {
-                const uint32_t b = ba_bucket_of(off_out, (slot & 7u) ? hint : 0u, pl.total, slot);   // with and without a hint
+            for (uint32_t slot = 0; slot < off1[g][B]; ++slot) {
+                const uint32_t b = ba_bucket_of(off1[g].data(), (slot & 7u) ? hint : 0u, B, slot);   // with and without a hint
                 hint = b;
-                if (!(off_out[b] <= slot && slot < off_out[b + 1])) return -3;
-                const uint32_t ii = slot - off_out[b], len = ba_len(end[b] - start[b], r), in0 = off_in[b] + 2 * ii;
-                Affine<F> X = r ? cur[in0] : ba_fetch<F>(sv.data(), P.data(), in0);
-                if (2 * ii + 1 >= len) {
-                    next[slot] = X;
-                    continue;
-                }
-                Affine<F> Y = r ? cur[in0 + 1] : ba_fetch<F>(sv.data(), P.data(), in0 + 1);
-                F den;
-                int kind = ba_denominator(X, Y, den);
-                next[slot] = ba_finish(X, Y, kind, inv(den));
+                if (!(off1[g][b] <= slot && slot < off1[g][b + 1])) return -3;
+                const uint32_t vb = g * B + b, ii = slot - off1[g][b], m = end[vb] - start[vb], in0 = start[vb] + 2 * ii;
+                Affine<F> X = ba_fetch<F>(sv.data(), P.data(), in0);
+                lvl1[region1[g] + slot] = 2 * ii + 1 < m ? add_pair(X, ba_fetch<F>(sv.data(), P.data(), in0 + 1)) : X;
             }
+        }
+        // merged rounds 1 .. rounds - 1
+        BaLevel1 L1;
+        L1.groups = G;
+        for (uint32_t g = 0; g < G; ++g) {
+            L1.off1[g] = off1[g].data();
+            L1.region1[g] = region1[g];
+        }
+        std::vector<uint32_t> m1(B, 0);
+        for (uint32_t b = 0; b < B; ++b)
+            for (uint32_t g = 0; g < G; ++g) m1[b] += off1[g][b + 1] - off1[g][b];
+        std::vector<Affine<F>> cur, next;
+        std::vector<uint32_t> off_in, off_out(B + 1, 0);
+        for (uint32_t r = 1; r < rounds; ++r) {
+            off_in = off_out;
+            for (uint32_t b = 0; b < B; ++b) off_out[b + 1] = off_out[b] + ba_len(m1[b], r);
+            next.assign(off_out[B], affine_inf<F>());
+            for (uint32_t b = 0; b < B; ++b)
+                for (uint32_t ii = 0; ii < off_out[b + 1] - off_out[b]; ++ii) {
+                    if (r == 1) {
+                        uint32_t rx, ry;
+                        ba_ref_level1(L1, b, ii, rx, ry);
+                        if (rx == 0xffffffffu) return -6;
+                        next[off_out[b] + ii] = ry != 0xffffffffu ? add_pair(lvl1[rx], lvl1[ry]) : lvl1[rx];
+                    } else {
+                        const uint32_t len = off_in[b + 1] - off_in[b], in0 = off_in[b] + 2 * ii;
+                        next[off_out[b] + ii] = 2 * ii + 1 < len ? add_pair(cur[in0], cur[in0 + 1]) : cur[in0];
+                    }
+                }
             cur.swap(next);
         }
-        const uint32_t* lo = off[rounds].data();
-        for (uint32_t b = 0; b < pl.total; ++b) {
+        buckets.assign(B, proj_inf<F>());
+        for (uint32_t b = 0; b < B; ++b) {
             XYZZ<F> acc = xyzz_inf<F>();
-            for (uint32_t j = lo[b]; j < lo[b + 1]; ++j)
-                if (!affine_is_inf(cur[j])) xyzz_madd(acc, cur[j]);
+            if (rounds == 1) {          // one round: the level-1 lists are what is left (the device runs this with a single group only)
+                for (uint32_t g = 0; g < G; ++g)
+                    for (uint32_t j = off1[g][b]; j < off1[g][b + 1]; ++j)
+                        if (!affine_is_inf(lvl1[region1[g] + j])) xyzz_madd(acc, lvl1[region1[g] + j]);
+            } else {
+                for (uint32_t j = off_out[b]; j < off_out[b + 1]; ++j)
+                    if (!affine_is_inf(cur[j])) xyzz_madd(acc, cur[j]);
+            }
             buckets[b] = xyzz_to_proj(acc);
         }
+        groups = 1;     // merged
     }
     if (groups > 1) {       // k_fold: the groups' copies of a bucket are added up
         std::vector<Proj<F>> merged(rpl.total);
