@@ -49,6 +49,10 @@ struct Ctx {
     int forced_window = 0;
     int ba_rounds = -1;     // batch-affine halving rounds in front of the XYZZ accumulation: -1 = chosen from the bucket load, 0 = none, k = k rounds
     int ba_pipes = 2;       // independent round pipelines (groups of windows on their own streams: one's inversion kernel hides behind the other's additions)
+    cudaStream_t front_stream = nullptr;   // highest priority.  One group: the scalar-only stages run here, the parse of the points beside them on the caller's stream (the default priority is the LOWEST there is, so it is the latency-bound chain that gets the high one; the parse fills what it leaves idle)
+    cudaEvent_t parse_ev[2] = {nullptr, nullptr};   // fork, join of that
+    int parse_aside = 1;
+    int front_end = 0;      // bucket lists: 0 = by counting (atomic ranks + scan + scatter), 1 = segmented radix sort + bounds search (stable; the A/B twin)
     int upload_groups = 2;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
     cudaEvent_t group_ev[4] = {nullptr, nullptr, nullptr, nullptr}, sgroup_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // a group's points / scalars have arrived
     int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation, [3] threads the segment running sums of the bucket reduction should fill (0 = default)

@@ -192,6 +192,12 @@ int c12381_init(int device)
     for (auto& ev : c.side_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.group_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.sgroup_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    for (auto& ev : c.parse_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    {
+        int least = 0, greatest = 0;
+        C12_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        C12_CUDA(cudaStreamCreateWithPriority(&c.front_stream, cudaStreamNonBlocking, greatest));
+    }
     C12_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
     C12_CUDA(cudaMalloc(&c.d_flags, 64 * sizeof(int)));
@@ -225,11 +231,14 @@ void c12381_shutdown(void)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : c.group_ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c.parse_ev)
+        if (ev) cudaEventDestroy(ev);
     for (auto& ev : c.sgroup_ev)
         if (ev) cudaEventDestroy(ev);
     for (auto& st : c.side)
         if (st) cudaStreamDestroy(st);
     if (c.plan_stream) cudaStreamDestroy(c.plan_stream);
+    if (c.front_stream) cudaStreamDestroy(c.front_stream);
     for (auto& ev : c.msm_ev)
         if (ev) cudaEventDestroy(ev);
     if (c.copy_stream) {
@@ -248,6 +257,8 @@ void c12381_set_knob(int id, int value)
 {
     if (id >= 0 && id < 4) ctx().knob[id] = value;
     if (id == 4) ctx().upload_groups = value < 1 ? 1 : (value > 4 ? 4 : value);
+    if (id == 5) ctx().front_end = value ? 1 : 0;
+    if (id == 6) ctx().parse_aside = value ? 1 : 0;
 }
 void c12381_set_msm_pipelines(int pipes) { ctx().ba_pipes = pipes < 1 ? 1 : (pipes > 4 ? 4 : pipes); }
 unsigned long long c12381_launch_count(void) { return ctx().launches; }

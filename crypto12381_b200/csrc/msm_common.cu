@@ -32,6 +32,174 @@ int launch_recode(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32
     return C12381_OK;
 }
 
+// ---- bucket lists by counting (the default front end) -----------------------------------------------------------------
+// A window's entries only have to be GROUPED by bucket: the order inside a bucket's list is irrelevant to the sum (the group
+// law is exact and the result leaves as a canonical encoding), so nothing has to be sorted.  Three steps instead of the
+// radix passes and the bounds search:
+//   k_recode_count    term -> digits; every entry takes its rank inside its bucket from an atomic counter (counts = the `end`
+//                     array, zeroed first) and parks (bucket | sign, rank)
+//   k_count_scan_*    exclusive scan of the counters -> start / end of every bucket (and, for the halving rounds, the level-1
+//                     slot offsets off1 = scan of ceil(count / 2) in the same pass)
+//   k_bucket_scatter  entry -> vals[start[bucket] + rank] = pipeline term | sign
+// The counters are 4 B x buckets (1 MiB at c = 16), resident in L2; ranks come back from the L2 atomic unit.  Equal keys in
+// neighbouring lanes (equal or tiny scalars: a whole window in one bucket) would serialise on one counter, so a warp that sees any
+// aggregates its equal keys with match_any first - one atomic per distinct bucket.
+constexpr uint32_t COUNT_NONE = 0xffffffffu;
+__global__ void k_ba_plan_top(uint32_t* __restrict__ tile_sums, uint32_t ntiles);
+
+struct RecodeCount {
+    uint32_t half;
+    bool live;
+    uint32_t* keys;
+    uint32_t* ranks;
+    uint32_t* counts;
+    __device__ __forceinline__ void operator()(uint32_t seg, uint64_t o, uint32_t d, uint32_t val)
+    {
+        const uint32_t full = 0xffffffffu, lane = threadIdx.x & 31;
+        const uint32_t b = (live && d) ? seg * half + (d - 1) : COUNT_NONE;
+        const uint32_t nb = __shfl_down_sync(full, b, 1);
+        uint32_t rank = 0;
+        if (__any_sync(full, lane < 31 && b == nb && b != COUNT_NONE)) {
+            const uint32_t peers = __match_any_sync(full, b);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if ((int)lane == leader && b != COUNT_NONE) base = atomicAdd(counts + b, (uint32_t)__popc(peers));
+            rank = __shfl_sync(full, base, leader) + __popc(peers & ((1u << lane) - 1u));
+        } else if (b != COUNT_NONE) {
+            rank = atomicAdd(counts + b, 1u);
+        }
+        if (live) {
+            keys[o] = d ? ((d - 1) | (val & 0x80000000u)) : COUNT_NONE;
+            ranks[o] = rank;
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) k_recode_count(MsmPlan pl, uint32_t first, uint32_t last, const uint8_t* __restrict__ scalars,
+                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ ranks, uint32_t* __restrict__ counts, int* flags)
+{
+    // every lane walks the loops (the emitter's shuffles are warp-wide); terms past `last` write nothing, the unused tail of
+    // the last group's segments (i >= n_in) recodes a zero scalar: entries that own no bucket
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < last, real = live && i < pl.n_in;
+    Scalar256 s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s.v[k] = 0;
+    if (real) {
+        s = scalar_from_be32(scalars + 32ull * i);
+        if (!scalar_is_canonical(s)) {
+            atomicOr(flags, FLAG_BAD_SCALAR);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s.v[k] = 0;
+        }
+    }
+    RecodeCount emit{pl.half, live, keys, ranks, counts};
+    msm_recode_each(pl, live ? i : first, s, emit);
+}
+
+constexpr int COUNT_SCAN_ITEMS = 8, COUNT_SCAN_TILE = 256 * COUNT_SCAN_ITEMS;
+
+// tile sums of the counts and of ceil(count / 2)
+__global__ void __launch_bounds__(256) k_count_scan_tiles(const uint32_t* __restrict__ counts, uint32_t total, uint32_t* __restrict__ tile_sums, uint32_t ntiles)
+{
+    const uint32_t base = blockIdx.x * COUNT_SCAN_TILE + threadIdx.x * COUNT_SCAN_ITEMS;
+    uint32_t s = 0, h = 0;
+#pragma unroll
+    for (int i = 0; i < COUNT_SCAN_ITEMS; ++i) {
+        const uint32_t m = base + i < total ? counts[base + i] : 0u;
+        s += m;
+        h += (m + 1) >> 1;
+    }
+    uint32_t tot;
+    block_exclusive_scan_256(s, &tot);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+    block_exclusive_scan_256(h, &tot);
+    if (threadIdx.x == 0) tile_sums[ntiles + blockIdx.x] = tot;
+}
+
+// counts (in `end`) -> start[b] = pos0 + sum of the counts before b, end[b] = start[b] + count; off1[b] = sum of ceil(count / 2)
+// before b (total + 1 entries; only if off1 != nullptr)
+__global__ void __launch_bounds__(256) k_count_scan_apply(uint32_t total, uint32_t pos0, const uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                                                          uint32_t* __restrict__ start, uint32_t* __restrict__ end, uint32_t* __restrict__ off1)
+{
+    const uint32_t base = blockIdx.x * COUNT_SCAN_TILE + threadIdx.x * COUNT_SCAN_ITEMS;
+    uint32_t v[COUNT_SCAN_ITEMS], s = 0, h = 0;
+#pragma unroll
+    for (int i = 0; i < COUNT_SCAN_ITEMS; ++i) {
+        v[i] = base + i < total ? end[base + i] : 0u;
+        s += v[i];
+        h += (v[i] + 1) >> 1;
+    }
+    uint32_t tot;
+    uint32_t e = block_exclusive_scan_256(s, &tot) + tile_sums[blockIdx.x] + pos0;
+    uint32_t o = block_exclusive_scan_256(h, &tot) + tile_sums[ntiles + blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < COUNT_SCAN_ITEMS; ++i) {
+        if (base + i < total) {
+            start[base + i] = e;
+            end[base + i] = e + v[i];
+        }
+        if (off1 && base + i <= total) off1[base + i] = o;          // entry `total` is the level's slot count
+        e += v[i];
+        o += (v[i] + 1) >> 1;
+    }
+}
+
+// refs == nullptr: the lists themselves (vals).  Otherwise the slot references of halving round 0 directly (what k_ba_map would
+// derive from the lists): slot off1[bucket] + rank / 2 adds the entries of ranks 2 i and 2 i + 1 (BA_NONE: an odd list's last).
+__global__ void __launch_bounds__(256) k_bucket_scatter(MsmPlan pl, uint32_t seg0, uint64_t entries, const uint32_t* __restrict__ keys,
+                                                        const uint32_t* __restrict__ ranks, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                                                        uint32_t* __restrict__ vals, const uint32_t* __restrict__ off1, uint2* __restrict__ refs)
+{
+    const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (t >= entries) return;
+    const uint64_t o = (uint64_t)seg0 * pl.n + t;
+    const uint32_t key = keys[o];
+    if (key == COUNT_NONE) return;
+    const uint32_t seg = (uint32_t)(o / pl.n), within = (uint32_t)(o - (uint64_t)seg * pl.n);
+    const uint32_t part = within / pl.n_group, li = within - part * pl.n_group, grp = seg / pl.real_windows;
+    const uint32_t val = (grp * pl.n_group + li + part * pl.n_in) | (key & 0x80000000u);
+    const size_t b = (size_t)seg * pl.half + (key & 0x7fffffffu);
+    const uint32_t rank = ranks[o];
+    if (!refs) {
+        vals[start[b] + rank] = val;
+        return;
+    }
+    uint32_t* slot = reinterpret_cast<uint32_t*>(refs + (off1[b - (size_t)seg0 * pl.half] + (rank >> 1)));
+    slot[rank & 1] = val;
+    if (!(rank & 1) && rank + 1 == end[b] - start[b]) slot[1] = BA_NONE;
+}
+
+size_t count_scan_scratch_words(uint32_t total) { return 2 * (size_t)cdiv((size_t)total + 1, COUNT_SCAN_TILE) + 8; }
+
+// Group `group` (< 0: everything) of the list plan: from its scalars to the bucket lists.  counts/end: zeroed here.  The bucket
+// bounds of the group's segments land in start / end (global positions in `vals`, the group's region starting at its first
+// segment), off1 (optional) gets the group's level-1 slot offsets.
+int launch_bucket_lists(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* ranks, uint32_t* vals, uint32_t* start,
+                        uint32_t* end, uint32_t* off1, uint2* refs, uint32_t* tile_sums, int* flags, cudaStream_t s, cudaEvent_t after_recode)
+{
+    const uint32_t g = group < 0 ? 0u : (uint32_t)group, ngroups = group < 0 ? pl.groups : 1u;
+    const uint32_t first = g * pl.n_group, last = first + ngroups * pl.n_group;
+    const uint32_t seg0 = g * pl.real_windows, nseg = ngroups * pl.real_windows, total = nseg * pl.half;
+    uint32_t *gstart = start + (size_t)seg0 * pl.half, *gend = end + (size_t)seg0 * pl.half;
+    if (last <= first) return C12381_OK;
+    C12_CUDA(cudaMemsetAsync(gend, 0, 4 * (size_t)total, s));
+    k_recode_count<<<cdiv(last - first, 128), 128, 0, s>>>(pl, first, last, d_scalars, keys, ranks, gend - (size_t)seg0 * pl.half, flags);
+    C12_LAUNCHED();
+    if (after_recode) C12_CUDA(cudaEventRecord(after_recode, s));
+    const uint32_t ntiles = cdiv((size_t)total + 1, COUNT_SCAN_TILE);
+    k_count_scan_tiles<<<ntiles, 256, 0, s>>>(gend, total, tile_sums, ntiles);
+    C12_LAUNCHED();
+    k_ba_plan_top<<<2, 256, 0, s>>>(tile_sums, ntiles);
+    C12_LAUNCHED();
+    k_count_scan_apply<<<ntiles, 256, 0, s>>>(total, (uint32_t)((uint64_t)seg0 * pl.n), tile_sums, ntiles, gstart, gend, off1);
+    C12_LAUNCHED();
+    const uint64_t entries = (uint64_t)nseg * pl.n;
+    k_bucket_scatter<<<(unsigned)cdiv(entries, (uint64_t)256), 256, 0, s>>>(pl, seg0, entries, keys, ranks, start, end, vals, off1, off1 ? refs : nullptr);
+    C12_LAUNCHED();
+    return C12381_OK;
+}
+
 // segments [seg0, seg0 + nseg) of the sorted key array -> bounds of their buckets (global positions, global bucket ids)
 int launch_bucket_bounds(const MsmPlan& pl, uint32_t seg0, uint32_t nseg, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s)
 {

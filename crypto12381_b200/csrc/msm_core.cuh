@@ -399,15 +399,15 @@ template <> struct MsmTraits<Fp2> {
     }
 };
 
-// Body of the recode kernel for term i: writes W (key, value) pairs at out index w * n + i.
-// The w-major layout keeps each window's entries in term order before the (stable) sort.
-// With a split on, term i yields `parts` pipeline terms: piece q at index q n_in + i (point [mu^q]P_i resp. [z^q]P_i).
-C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalars_be32, uint32_t* keys, uint32_t* vals)
+// Recoding of term i with scalar s: emit(segment, out index, digit magnitude d, value) once per (piece, window); d == 0 means
+// the term owns no bucket in that window.  Out index = segment * n + (place of the pipeline term inside its group's segments):
+// the w-major layout keeps each window's entries together.  With a split on, term i yields `parts` pipeline terms: piece q is
+// pipeline term q n_in + i (point [mu^q]P_i resp. [z^q]P_i); value = pipeline term | sign << 31.
+template <class Emit> C12_HD void msm_recode_each(const MsmPlan& pl, uint32_t i, const Scalar256& s, Emit& emit)
 {
-    Scalar256 s = scalar_from_be32(scalars_be32 + 32ull * i);
     // segment of (group, window w) = virtual window group * real_windows + w; the term's place inside its group's segments
     const uint32_t grp = i / pl.n_group, li = i - grp * pl.n_group;
-    const uint64_t seg0 = (uint64_t)grp * pl.real_windows;
+    const uint32_t seg0 = grp * pl.real_windows;
     if (pl.parts > 1) {
         ScalarParts sp;
         msm_split(s, pl.parts, sp);
@@ -424,14 +424,7 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
                     neg = 1;
                     carry = 1;
                 }
-                uint64_t o = (seg0 + w) * pl.n + (uint64_t)part * pl.n_group + li;
-                if (d == 0) {
-                    keys[o] = msm_invalid_key(pl);
-                    vals[o] = idx;
-                } else {
-                    keys[o] = d - 1;
-                    vals[o] = idx | ((neg ^ sgn) << 31);
-                }
+                emit(seg0 + w, (uint64_t)(seg0 + w) * pl.n + (uint64_t)part * pl.n_group + li, d, idx | ((neg ^ sgn) << 31));
             }
         }
         return;
@@ -446,15 +439,25 @@ C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalar
             neg = 1;
             carry = 1;
         }
-        uint64_t o = (seg0 + w) * pl.n + li;
-        if (d == 0) {
-            keys[o] = msm_invalid_key(pl);
-            vals[o] = i;
-        } else {
-            keys[o] = d - 1;
-            vals[o] = i | (neg << 31);
-        }
+        emit(seg0 + w, (uint64_t)(seg0 + w) * pl.n + li, d, i | (neg << 31));
     }
+}
+
+// Body of the recode kernel of the SORTED front end for term i: (key, value) pairs, key = bucket inside the window.
+struct RecodeToPairs {
+    uint32_t invalid;
+    uint32_t* keys;
+    uint32_t* vals;
+    C12_HD void operator()(uint32_t, uint64_t o, uint32_t d, uint32_t val)
+    {
+        keys[o] = d ? d - 1 : invalid;
+        vals[o] = d ? val : (val & 0x7fffffffu);
+    }
+};
+C12_HD void msm_recode_body(const MsmPlan& pl, uint32_t i, const uint8_t* scalars_be32, uint32_t* keys, uint32_t* vals)
+{
+    RecodeToPairs emit{msm_invalid_key(pl), keys, vals};
+    msm_recode_each(pl, i, scalar_from_be32(scalars_be32 + 32ull * i), emit);
 }
 
 // the unused tail of the last group's segments (n_in is not a multiple of the group count): entries that own no bucket

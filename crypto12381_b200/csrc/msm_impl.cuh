@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict_
 
 // defined once in msm_common.cu (kernels there are launched through these host functions)
 int launch_recode(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s);
+int launch_bucket_lists(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* ranks, uint32_t* vals, uint32_t* start,
+                        uint32_t* end, uint32_t* off1, uint2* refs, uint32_t* tile_sums, int* flags, cudaStream_t s, cudaEvent_t after_recode);
+size_t count_scan_scratch_words(uint32_t total);
 int launch_bucket_bounds(const MsmPlan& pl, uint32_t seg0, uint32_t nseg, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s);
 // chunking of the bucket lists: vstart[b] = first chunk of bucket b (total + 1 entries), vbucket[v] = bucket of chunk v,
 // order[] = chunk ids by decreasing length, padded with 0xffffffff up to pl.vmax
@@ -888,6 +891,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     b += align_up(sizeof(Affine<F>) * (size_t)pl.n);
     b += 4 * align_up(4 * N);
     b += align_up(4 * hist_words) + align_up(4 * (tile_words + 16));
+    b += align_up(4 * (size_t)BA_MAX_PIPES * count_scan_scratch_words(pl.total));
     b += 2 * align_up(4 * (size_t)lp.total);
     b += align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax);
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
@@ -995,6 +999,8 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* vals2 = (uint32_t*)arena_take(4 * N);
     uint32_t* hist = (uint32_t*)arena_take(4 * hist_words);
     uint32_t* tiles = (uint32_t*)arena_take(4 * (size_t)groups * (gtile_words + 2));
+    const size_t count_words = count_scan_scratch_words(B);
+    uint32_t* count_tiles = (uint32_t*)arena_take(4 * (size_t)groups * count_words);
     uint32_t* start = (uint32_t*)arena_take(4 * (size_t)lp.total);
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)lp.total);
     uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));
@@ -1037,32 +1043,51 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         for (uint32_t g = 1; g < groups; ++g) C12_CUDA(cudaStreamWaitEvent(c.side[g - 1], c.side_ev[0], 0));
         C12_CUDA(cudaStreamWaitEvent(plan_stream, c.side_ev[0], 0));
     }
+    // One group: the scalar-only stages (which wait on the L2 atomic unit and on launch latencies) run on the high-priority front
+    // stream, the parse of the points (integer pipe) beside them on `s`, filling what they leave idle.
+    const bool parse_aside = groups == 1 && c.parse_aside;
+    if (parse_aside) {
+        C12_CUDA(cudaEventRecord(c.parse_ev[0], s));
+        C12_CUDA(cudaStreamWaitEvent(c.front_stream, c.parse_ev[0], 0));
+        plan_stream = c.front_stream;
+    }
     // ---- per group: the scalar-only stages (recode, sort, bucket bounds, level-1 offsets, round-0 slot map) -----------------
     uint32_t *skeys = keys, *svals = vals;       // where the sorted pairs end up (the passes ping-pong between the two buffers)
     for (uint32_t g = 0; g < groups; ++g) {
-        cudaStream_t sg = lane_stream(g);
+        cudaStream_t sg = parse_aside ? c.front_stream : lane_stream(g);
         if (scalars_ready) {
             if (groups > 1)
                 C12_CUDA(cudaStreamWaitEvent(sg, scalars_ready[g], 0));
             else
-                for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(s, scalars_ready[q], 0));
+                for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(sg, scalars_ready[q], 0));
         }
-        rc = launch_recode(lp, groups > 1 ? (int)g : -1, d_scalars, keys, vals, flags_word(), sg);
-        if (rc) return rc;
-        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[1], s));
         const size_t seg_off = (size_t)g * pl.windows * lp.n;
-        uint32_t *k1 = keys + seg_off, *v1 = vals + seg_off, *k2 = keys2 + seg_off, *v2 = vals2 + seg_off;
-        rc = sort_pairs_segmented(k1, v1, k2, v2, lp.n, pl.windows, lp.c, hist + g * ghist_words, tiles + g * (gtile_words + 2), sg);
-        if (rc) return rc;
-        skeys = k1 - seg_off;
-        svals = v1 - seg_off;
-        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[2], s));
-        rc = launch_bucket_bounds(lp, g * pl.windows, pl.windows, skeys, start, end, sg);
-        if (rc) return rc;
-        if (R) {
-            uint32_t* off1_g = off1 + g * lvl_words;
-            rc = launch_ba_plan(B, start + (size_t)g * B, end + (size_t)g * B, 1, 0, 1, 1, off1_g, ba_tiles + g * plan_words, sg);
+        uint32_t* off1_g = R ? off1 + g * lvl_words : nullptr;
+        if (c.front_end == 0) {
+            // bucket lists by counting: (bucket | sign, rank) in keys / vals, the lists in vals2
+            rc = launch_bucket_lists(lp, groups > 1 ? (int)g : -1, d_scalars, keys, vals, vals2, start, end, off1_g, R ? ba_refs + sc.region0[g] : nullptr, count_tiles + g * count_words,
+                                     flags_word(), sg, g == 0 ? c.pev[1] : nullptr);
             if (rc) return rc;
+            svals = vals2;
+            if (g == 0) C12_CUDA(cudaEventRecord(c.pev[2], sg));
+        } else {
+            rc = launch_recode(lp, groups > 1 ? (int)g : -1, d_scalars, keys, vals, flags_word(), sg);
+            if (rc) return rc;
+            if (g == 0) C12_CUDA(cudaEventRecord(c.pev[1], sg));
+            uint32_t *k1 = keys + seg_off, *v1 = vals + seg_off, *k2 = keys2 + seg_off, *v2 = vals2 + seg_off;
+            rc = sort_pairs_segmented(k1, v1, k2, v2, lp.n, pl.windows, lp.c, hist + g * ghist_words, tiles + g * (gtile_words + 2), sg);
+            if (rc) return rc;
+            skeys = k1 - seg_off;
+            svals = v1 - seg_off;
+            if (g == 0) C12_CUDA(cudaEventRecord(c.pev[2], sg));
+            rc = launch_bucket_bounds(lp, g * pl.windows, pl.windows, skeys, start, end, sg);
+            if (rc) return rc;
+            if (R) {
+                rc = launch_ba_plan(B, start + (size_t)g * B, end + (size_t)g * B, 1, 0, 1, 1, off1_g, ba_tiles + g * plan_words, sg);
+                if (rc) return rc;
+            }
+        }
+        if (R) {
             if (groups > 1) C12_CUDA(cudaEventRecord(c.msm_ev[g], sg));             // this group's bounds and level-1 offsets are in place
             BaMapGeom mg;
             mg.start = start + (size_t)g * B;
@@ -1079,7 +1104,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
             mg.pipes = 1;
             mg.b_lo[0] = 0;
             mg.b_lo[1] = B;
-            rc = launch_ba_map(mg, sc.slots0, sg);
+            if (c.front_end != 0) rc = launch_ba_map(mg, sc.slots0, sg);      // by counting: the scatter wrote round 0's references itself
             if (rc) return rc;
         }
     }
@@ -1139,6 +1164,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     rc = launch_chunk_order(pl, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, plan_stream);
     if (rc) return rc;
     if (groups > 1) C12_CUDA(cudaEventRecord(c.msm_ev[BA_MAX_PIPES], plan_stream));
+    if (parse_aside) C12_CUDA(cudaEventRecord(c.parse_ev[1], c.front_stream));
     // ---- the points, group by group; round 0 of each group behind them ------------------------------------------------------
     for (uint32_t g = 0; g < groups; ++g) {
         cudaStream_t sg = lane_stream(g);
@@ -1148,12 +1174,13 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
             else
                 for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(s, points_ready[q], 0));
         }
-        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[3], s));
+        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[3], parse_aside ? c.front_stream : s));
         const uint32_t first = g * lp.n_group, last = first + lp.n_group < n ? first + lp.n_group : n;
         if (first < last) {
             k_parse_points<F><<<cdiv(last - first, 128), 128, 0, sg>>>(d_points, first, last, n, pl.parts, pts, flags_word());
             C12_LAUNCHED();
         }
+        if (parse_aside) C12_CUDA(cudaStreamWaitEvent(s, c.parse_ev[1], 0));      // join: the bucket lists and the plan
         if (g == 0) {
             C12_CUDA(cudaEventRecord(c.ev[1], s));
             C12_CUDA(cudaEventRecord(c.pev[4], s));
