@@ -396,17 +396,25 @@ def run_ours(args):
             hbm_src = "MEASURED_PEAKS.json"
         except Exception:
             hbm, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
-        passes = (stats["window_bits"] + 7) // 8
         ph = {kph: statistics.mean(v) for kph, v in phase_acc.items()}
-        sort_bytes = adds * 8 * 2 * passes      # (key, index) pairs read and written once per radix pass
         for kph, vph in ph.items():
             roofline["ms_" + kph] = vph
         roofline["ms_tail"] = ph["reduce1"] + ph["reduce2"] + ph["finish"]
-        if ph["sort"] > 0:
-            roofline.update({"hbm_phase_what": "segmented radix sort of the (bucket key, term index) pairs (bucket scatter)",
-                             "hbm_phase_bytes": sort_bytes, "hbm_phase_ms": ph["sort"], "hbm_phase_gbs": sort_bytes / (ph["sort"] * 1e-3) / 1e9,
-                             "hbm_phase_peak_gbs": hbm, "hbm_phase_frac": sort_bytes / (ph["sort"] * 1e-3) / 1e9 / hbm,
-                             "hbm_phase_peak_source": hbm_src, "hbm_phase_radix_passes": passes})
+        # The bucket-list phase (north_star's "bucket scatter"): scalars -> per-bucket lists.  By counting (the default since
+        # r03a): read the scalars, park (bucket | sign, rank) per entry, read them back, write one 4-byte slot reference per
+        # entry.  Its bound is the L2 atomic unit (one returning atomic per entry), not HBM: the fraction below says how far
+        # from an HBM-bound phase it is, the milliseconds say what it costs (the radix sort it replaced: 0.50 ms for these two
+        # phases at n = 2^20, 19 % of the copy bandwidth on 16 B per entry per pass).
+        list_ms = ph["recode"] + ph["sort"]
+        list_bytes = 32 * n + adds * (8 + 8 + 4)
+        if list_ms > 0:
+            roofline.update({"hbm_phase_what": "bucket lists by counting: k_recode_count (digits + one returning L2 atomic per entry) -> scan -> k_bucket_scatter; "
+                                               "runs beside the parse of the points, so its share of the step is smaller than its span",
+                             "hbm_phase_bytes": list_bytes, "hbm_phase_ms": list_ms, "hbm_phase_gbs": list_bytes / (list_ms * 1e-3) / 1e9,
+                             "hbm_phase_peak_gbs": hbm, "hbm_phase_frac": list_bytes / (list_ms * 1e-3) / 1e9 / hbm,
+                             "hbm_phase_peak_source": hbm_src, "hbm_phase_atomics_per_s": adds / (ph["recode"] * 1e-3) if ph["recode"] > 0 else None,
+                             "hbm_phase_bound": "L2 atomic unit (returning atomics on 2^(c-1) x windows counters), launch latencies of the scan",
+                             "ms_front_end": ph["recode"] + ph["sort"] + ph["bounds_order"] + ph["parse"]})
         roofline["multi_rank_result_ok"] = multi_ok
         roofline["e2e_result_ok"] = e2e_ok
         roofline["single_gpu_pipeline_ms"] = local_ms

@@ -53,7 +53,7 @@ struct Ctx {
     cudaEvent_t parse_ev[2] = {nullptr, nullptr};   // fork, join of that
     int parse_aside = 1;
     int front_end = 0;      // bucket lists: 0 = by counting (atomic ranks + scan + scatter), 1 = segmented radix sort + bounds search (stable; the A/B twin)
-    int upload_groups = 2;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
+    int upload_groups = 4;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
     cudaEvent_t group_ev[4] = {nullptr, nullptr, nullptr, nullptr}, sgroup_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // a group's points / scalars have arrived
     int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation, [3] threads the segment running sums of the bucket reduction should fill (0 = default)
     cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // streams of lanes 1 .. 3 (lane 0 runs on the caller's stream)

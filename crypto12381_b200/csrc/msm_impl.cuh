@@ -946,7 +946,10 @@ template <class F> bool msm_plans(size_t n, uint32_t groups, MsmPlan& pl, MsmPla
     constexpr uint32_t parts = MsmTraits<F>::PARTS;
     uint32_t cbits = ctx().forced_window ? (uint32_t)ctx().forced_window : msm_choose_window(parts * n, 256 / parts);
     if (cbits < 2 || cbits > 16) return false;
-    pl = msm_make_plan((uint32_t)n, cbits, parts, ctx().knob[3] > 0 ? (uint32_t)ctx().knob[3] : 0u);
+    // segment running sums of the bucket reduction: over Fp2 one block per SM is resident (148 x 128 threads), so the grid is kept
+    // within 16 Ki threads - one wave - there (G2 n = 2^18: tail 2.45 -> 2.22 ms, profiles/r02l_tail_tune.txt)
+    const uint32_t seg_wave = ctx().knob[3] > 0 ? (uint32_t)ctx().knob[3] : (sizeof(F) == sizeof(Fp2) ? 16384u : 0u);
+    pl = msm_make_plan((uint32_t)n, cbits, parts, seg_wave);
     if (groups > BA_MAX_PIPES) groups = BA_MAX_PIPES;
     lp = msm_list_plan(pl, groups);
     if (groups > 1 && msm_ba_schedule(pl, lp).rounds < 2) lp = pl;

@@ -27,4 +27,4 @@ for groups in (1, 2, 3, 4):
         st = dv.last_msm_stats()
         print(f"n=2^{int(np.log2(n))} groups={groups} tail={tail}: best {min(ts[1:]):.3f} median {sorted(ts[1:])[3]:.3f} ms  rounds {st['ba_rounds']} accumulate-phase {st['phases_ms']['accumulate']:.3f}", flush=True)
 assert len(res) == 1
-lib.c12381_set_knob(4, 2); lib.c12381_set_knob(2, 3)
+lib.c12381_set_knob(4, 4); lib.c12381_set_knob(2, 3)

@@ -32,6 +32,6 @@ for name, logn in (("G1", 20), ("G1", 19), ("G2", 18), ("G1", 21)):
             bad += not ok
             if not ok: print(f"{name} n={n} groups={groups} rep={rep}: DIFFERS", flush=True)
     print(f"{name} n={n}: checked", flush=True)
-lib.c12381_set_knob(4, 2)
+lib.c12381_set_knob(4, 4)
 print("mismatches:", bad)
 sys.exit(1 if bad else 0)
