@@ -187,7 +187,6 @@ int c12381_init(int device)
     for (auto& ev : c.copy_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaEventCreateWithFlags(&c.arena_ev, cudaEventDisableTiming));
     for (auto& st : c.side) C12_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    C12_CUDA(cudaStreamCreateWithFlags(&c.plan_stream, cudaStreamNonBlocking));
     for (auto& ev : c.msm_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.side_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.group_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -197,6 +196,7 @@ int c12381_init(int device)
         int least = 0, greatest = 0;
         C12_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         C12_CUDA(cudaStreamCreateWithPriority(&c.front_stream, cudaStreamNonBlocking, greatest));
+        C12_CUDA(cudaStreamCreateWithPriority(&c.plan_stream, cudaStreamNonBlocking, greatest));
     }
     C12_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));

@@ -120,13 +120,14 @@ template <class F> int pod_mul(void* object, const void* value)
     if (!object || !value) return set_error(C12381_EARG, "multiply: null pointer");
     const void* in[2] = {object, value};
     size_t sz[2] = {(size_t)Pod<F>::POINT, POD_BIG};
-    return with_staged(in, sz, 2, object, Pod<F>::POINT, 4096, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+    // a one-term sum of products: the MSM pipeline's lane-cooperative tail beats one thread's double-and-add (entry_mul_dev)
+    return with_staged(in, sz, 2, object, Pod<F>::POINT, 4096 + msm_scratch_for<F>(1), [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
         uint8_t* wire = (uint8_t*)arena_take(Wire<F>::AFFINE);
         uint8_t* sc = (uint8_t*)arena_take(32);
         uint8_t* res = (uint8_t*)arena_take(Wire<F>::AFFINE);
         int rc = pods_to_wire<F>(d_in[0], 1, wire, s);
         if (!rc) rc = bigs_to_scalars(d_in[1], 1, sc, s);
-        if (!rc) rc = scalar_mul_run<F>(wire, sc, 1, res, s, OUT_AFFINE);
+        if (!rc) rc = msm_run<F>(wire, sc, 1, res, OUT_AFFINE, s);
         if (!rc) rc = wire_to_pods<F>(res, 1, d_out, s);
         return rc;
     });

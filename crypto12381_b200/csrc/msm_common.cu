@@ -118,9 +118,9 @@ __global__ void __launch_bounds__(256) k_count_scan_tiles(const uint32_t* __rest
 }
 
 // counts (in `end`) -> start[b] = pos0 + sum of the counts before b, end[b] = start[b] + count; off1[b] = sum of ceil(count / 2)
-// before b (total + 1 entries; only if off1 != nullptr)
+// before b (total + 1 entries; only if off1 != nullptr); with refs the odd lists' last slots get their empty second reference
 __global__ void __launch_bounds__(256) k_count_scan_apply(uint32_t total, uint32_t pos0, const uint32_t* __restrict__ tile_sums, uint32_t ntiles,
-                                                          uint32_t* __restrict__ start, uint32_t* __restrict__ end, uint32_t* __restrict__ off1)
+                                                          uint32_t* __restrict__ start, uint32_t* __restrict__ end, uint32_t* __restrict__ off1, uint2* __restrict__ refs)
 {
     const uint32_t base = blockIdx.x * COUNT_SCAN_TILE + threadIdx.x * COUNT_SCAN_ITEMS;
     uint32_t v[COUNT_SCAN_ITEMS], s = 0, h = 0;
@@ -140,16 +140,18 @@ __global__ void __launch_bounds__(256) k_count_scan_apply(uint32_t total, uint32
             end[base + i] = e + v[i];
         }
         if (off1 && base + i <= total) off1[base + i] = o;          // entry `total` is the level's slot count
+        if (refs && (v[i] & 1u)) refs[o + (v[i] >> 1)].y = BA_NONE;  // an odd list's last entry has no partner (the scatter writes only entries)
         e += v[i];
         o += (v[i] + 1) >> 1;
     }
 }
 
 // refs == nullptr: the lists themselves (vals).  Otherwise the slot references of halving round 0 directly (what k_ba_map would
-// derive from the lists): slot off1[bucket] + rank / 2 adds the entries of ranks 2 i and 2 i + 1 (BA_NONE: an odd list's last).
+// derive from the lists): slot off1[bucket] + rank / 2 adds the entries of ranks 2 i and 2 i + 1 (an odd list's last slot got its
+// BA_NONE from the scan) - one gather and one 4-byte store per entry.
 __global__ void __launch_bounds__(256) k_bucket_scatter(MsmPlan pl, uint32_t seg0, uint64_t entries, const uint32_t* __restrict__ keys,
-                                                        const uint32_t* __restrict__ ranks, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
-                                                        uint32_t* __restrict__ vals, const uint32_t* __restrict__ off1, uint2* __restrict__ refs)
+                                                        const uint32_t* __restrict__ ranks, const uint32_t* __restrict__ start, uint32_t* __restrict__ vals,
+                                                        const uint32_t* __restrict__ off1, uint2* __restrict__ refs)
 {
     const uint64_t t = (uint64_t)blockIdx.x * 256 + threadIdx.x;
     if (t >= entries) return;
@@ -165,9 +167,7 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(MsmPlan pl, uint32_t seg
         vals[start[b] + rank] = val;
         return;
     }
-    uint32_t* slot = reinterpret_cast<uint32_t*>(refs + (off1[b - (size_t)seg0 * pl.half] + (rank >> 1)));
-    slot[rank & 1] = val;
-    if (!(rank & 1) && rank + 1 == end[b] - start[b]) slot[1] = BA_NONE;
+    reinterpret_cast<uint32_t*>(refs + (off1[b - (size_t)seg0 * pl.half] + (rank >> 1)))[rank & 1] = val;
 }
 
 size_t count_scan_scratch_words(uint32_t total) { return 2 * (size_t)cdiv((size_t)total + 1, COUNT_SCAN_TILE) + 8; }
@@ -176,7 +176,7 @@ size_t count_scan_scratch_words(uint32_t total) { return 2 * (size_t)cdiv((size_
 // bounds of the group's segments land in start / end (global positions in `vals`, the group's region starting at its first
 // segment), off1 (optional) gets the group's level-1 slot offsets.
 int launch_bucket_lists(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* ranks, uint32_t* vals, uint32_t* start,
-                        uint32_t* end, uint32_t* off1, uint2* refs, uint32_t* tile_sums, int* flags, cudaStream_t s, cudaEvent_t after_recode)
+                        uint32_t* end, uint32_t* off1, uint2* refs, uint32_t* tile_sums, int* flags, cudaStream_t s, cudaEvent_t after_recode, cudaEvent_t after_scan)
 {
     const uint32_t g = group < 0 ? 0u : (uint32_t)group, ngroups = group < 0 ? pl.groups : 1u;
     const uint32_t first = g * pl.n_group, last = first + ngroups * pl.n_group;
@@ -192,10 +192,11 @@ int launch_bucket_lists(const MsmPlan& pl, int group, const uint8_t* d_scalars, 
     C12_LAUNCHED();
     k_ba_plan_top<<<2, 256, 0, s>>>(tile_sums, ntiles);
     C12_LAUNCHED();
-    k_count_scan_apply<<<ntiles, 256, 0, s>>>(total, (uint32_t)((uint64_t)seg0 * pl.n), tile_sums, ntiles, gstart, gend, off1);
+    k_count_scan_apply<<<ntiles, 256, 0, s>>>(total, (uint32_t)((uint64_t)seg0 * pl.n), tile_sums, ntiles, gstart, gend, off1, off1 ? refs : nullptr);
     C12_LAUNCHED();
+    if (after_scan) C12_CUDA(cudaEventRecord(after_scan, s));        // bounds and level-1 offsets are in place: all the merged plan needs
     const uint64_t entries = (uint64_t)nseg * pl.n;
-    k_bucket_scatter<<<(unsigned)cdiv(entries, (uint64_t)256), 256, 0, s>>>(pl, seg0, entries, keys, ranks, start, end, vals, off1, off1 ? refs : nullptr);
+    k_bucket_scatter<<<(unsigned)cdiv(entries, (uint64_t)256), 256, 0, s>>>(pl, seg0, entries, keys, ranks, start, vals, off1, off1 ? refs : nullptr);
     C12_LAUNCHED();
     return C12381_OK;
 }

@@ -58,8 +58,12 @@ struct MsmPlan {
 //   tail          ~1.05 ms of latency-bound reduction / Horner, growing with the bucket count (1.38 ms at c = 16)
 // The top window sees only  t = (bits - 1) - c (W - 1)  bits of the magnitudes: widths with t < c / 2 would send every
 // term of that window to a handful of buckets and are skipped.
+// Measured correction (profiles/r03c_window_sweep_*.txt, r03d): from 2^17 (GLV halves) / 2^16 (GLS quarters) pipeline terms on the
+// widest window wins outright over the split scalars - its lists are a handful of entries, so the accumulation is no longer one thread's chain of 32+ dependent
+// additions (G1 n = 2^16: 1.96 -> 1.74 ms; G2 n = 2^16: 6.40 -> 3.63 ms).
 inline uint32_t msm_choose_window(uint64_t n, uint32_t bits = 256)
 {
+    if (bits < 256 && n >= (bits <= 64 ? (1ull << 16) : (1ull << 17))) return 16;
     uint32_t best = 4;
     double best_cost = 1e300;
     for (uint32_t c = 4; c <= 16; ++c) {

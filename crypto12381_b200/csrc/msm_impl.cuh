@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) k_parse_points(const uint8_t* __restrict_
 // defined once in msm_common.cu (kernels there are launched through these host functions)
 int launch_recode(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* vals, int* flags, cudaStream_t s);
 int launch_bucket_lists(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32_t* keys, uint32_t* ranks, uint32_t* vals, uint32_t* start,
-                        uint32_t* end, uint32_t* off1, uint2* refs, uint32_t* tile_sums, int* flags, cudaStream_t s, cudaEvent_t after_recode);
+                        uint32_t* end, uint32_t* off1, uint2* refs, uint32_t* tile_sums, int* flags, cudaStream_t s, cudaEvent_t after_recode, cudaEvent_t after_scan);
 size_t count_scan_scratch_words(uint32_t total);
 int launch_bucket_bounds(const MsmPlan& pl, uint32_t seg0, uint32_t nseg, const uint32_t* keys, uint32_t* start, uint32_t* end, cudaStream_t s);
 // chunking of the bucket lists: vstart[b] = first chunk of bucket b (total + 1 entries), vbucket[v] = bucket of chunk v,
@@ -1040,7 +1040,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     // Streams: group g runs on `s` (g = 0) or side stream g - 1; with several groups the merged plan runs on the plan stream so
     // that it does not hold up group 0's round 0; pipeline p of the merged rounds on `s` (p = 0) or side stream p - 1.
     auto lane_stream = [&](uint32_t i) { return i ? c.side[i - 1] : s; };
-    cudaStream_t plan_stream = groups > 1 ? c.plan_stream : s;
+    cudaStream_t plan_stream = groups > 1 ? c.plan_stream : s;      // the merged plan needs only the bucket COUNTS: it runs beside the scatter / the groups' own stages
     if (groups > 1) {           // the arena is ours from this point of `s` on
         C12_CUDA(cudaEventRecord(c.side_ev[0], s));
         for (uint32_t g = 1; g < groups; ++g) C12_CUDA(cudaStreamWaitEvent(c.side[g - 1], c.side_ev[0], 0));
@@ -1052,7 +1052,8 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     if (parse_aside) {
         C12_CUDA(cudaEventRecord(c.parse_ev[0], s));
         C12_CUDA(cudaStreamWaitEvent(c.front_stream, c.parse_ev[0], 0));
-        plan_stream = c.front_stream;
+        plan_stream = c.plan_stream;
+        C12_CUDA(cudaStreamWaitEvent(plan_stream, c.parse_ev[0], 0));
     }
     // ---- per group: the scalar-only stages (recode, sort, bucket bounds, level-1 offsets, round-0 slot map) -----------------
     uint32_t *skeys = keys, *svals = vals;       // where the sorted pairs end up (the passes ping-pong between the two buffers)
@@ -1069,7 +1070,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         if (c.front_end == 0) {
             // bucket lists by counting: (bucket | sign, rank) in keys / vals, the lists in vals2
             rc = launch_bucket_lists(lp, groups > 1 ? (int)g : -1, d_scalars, keys, vals, vals2, start, end, off1_g, R ? ba_refs + sc.region0[g] : nullptr, count_tiles + g * count_words,
-                                     flags_word(), sg, g == 0 ? c.pev[1] : nullptr);
+                                     flags_word(), sg, g == 0 ? c.pev[1] : nullptr, plan_stream != s ? c.msm_ev[g] : nullptr);
             if (rc) return rc;
             svals = vals2;
             if (g == 0) C12_CUDA(cudaEventRecord(c.pev[2], sg));
@@ -1089,9 +1090,9 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
                 rc = launch_ba_plan(B, start + (size_t)g * B, end + (size_t)g * B, 1, 0, 1, 1, off1_g, ba_tiles + g * plan_words, sg);
                 if (rc) return rc;
             }
+            if (plan_stream != s) C12_CUDA(cudaEventRecord(c.msm_ev[g], sg));      // this group's bounds and level-1 offsets are in place (by counting: recorded behind the scan)
         }
         if (R) {
-            if (groups > 1) C12_CUDA(cudaEventRecord(c.msm_ev[g], sg));             // this group's bounds and level-1 offsets are in place
             BaMapGeom mg;
             mg.start = start + (size_t)g * B;
             mg.end = end + (size_t)g * B;
@@ -1115,7 +1116,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t *order = nullptr, *vstart = nullptr, *vbucket = nullptr;
     const uint32_t *lstart = start, *lend = end;
     const Affine<F>* final_lists = nullptr;
-    if (groups > 1)
+    if (plan_stream != s)
         for (uint32_t g = 0; g < groups; ++g) C12_CUDA(cudaStreamWaitEvent(plan_stream, c.msm_ev[g], 0));
     if (R) {
         rc = launch_ba_plan(B, start, end, groups, B, 2, R - 1, offm, ba_tiles + groups * plan_words, plan_stream);
@@ -1166,7 +1167,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     // bucket lists longer than pl.chunk entries are cut into chunks (XYZZ additions, one thread per chunk)
     rc = launch_chunk_order(pl, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, plan_stream);
     if (rc) return rc;
-    if (groups > 1) C12_CUDA(cudaEventRecord(c.msm_ev[BA_MAX_PIPES], plan_stream));
+    if (plan_stream != s) C12_CUDA(cudaEventRecord(c.msm_ev[BA_MAX_PIPES], plan_stream));
     if (parse_aside) C12_CUDA(cudaEventRecord(c.parse_ev[1], c.front_stream));
     // ---- the points, group by group; round 0 of each group behind them ------------------------------------------------------
     for (uint32_t g = 0; g < groups; ++g) {
@@ -1177,13 +1178,16 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
             else
                 for (uint32_t q = 0; q < groups_req; ++q) C12_CUDA(cudaStreamWaitEvent(s, points_ready[q], 0));
         }
-        if (g == 0) C12_CUDA(cudaEventRecord(c.pev[3], parse_aside ? c.front_stream : s));
+        if (g == 0 && !parse_aside) C12_CUDA(cudaEventRecord(c.pev[3], s));
         const uint32_t first = g * lp.n_group, last = first + lp.n_group < n ? first + lp.n_group : n;
         if (first < last) {
             k_parse_points<F><<<cdiv(last - first, 128), 128, 0, sg>>>(d_points, first, last, n, pl.parts, pts, flags_word());
             C12_LAUNCHED();
         }
-        if (parse_aside) C12_CUDA(cudaStreamWaitEvent(s, c.parse_ev[1], 0));      // join: the bucket lists and the plan
+        if (parse_aside) {          // join: the bucket lists.  Phase events: what is left of the parse behind the scatter counts as "bounds_order"
+            C12_CUDA(cudaStreamWaitEvent(s, c.parse_ev[1], 0));
+            C12_CUDA(cudaEventRecord(c.pev[3], s));
+        }
         if (g == 0) {
             C12_CUDA(cudaEventRecord(c.ev[1], s));
             C12_CUDA(cudaEventRecord(c.pev[4], s));
@@ -1215,8 +1219,8 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
             C12_CUDA(cudaEventRecord(c.side_ev[g], c.side[g - 1]));
             C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[g], 0));
         }
-        C12_CUDA(cudaStreamWaitEvent(s, c.msm_ev[BA_MAX_PIPES], 0));
     }
+    if (plan_stream != s) C12_CUDA(cudaStreamWaitEvent(s, c.msm_ev[BA_MAX_PIPES], 0));
     // ---- rounds 1 .. R - 1 on the merged lists, pipeline by pipeline ------------------------------------------------------------
     if (R > 1) {
         if (sc.pipes > 1) {
@@ -1512,10 +1516,19 @@ template <class F> int entry_sum_dev(const uint8_t* d_points, size_t n, uint8_t*
     return sum_run<F>(d_points, n, d_out, OUT_COMPRESSED, pick_stream(stream));
 }
 
+// A batch of ONE (the reference's multiply(point&, big) called term by term) is a one-term sum of products: the MSM pipeline's
+// tail runs on lane-cooperative point arithmetic, a single thread's double-and-add does not (G1 2.48 -> 0.86 ms, G2 4.58 ->
+// 1.4 ms per call, profiles/r03c_latency_probe.txt).  Same bytes: both leave as the canonical compressed encoding.
 template <class F> int entry_mul_dev(const uint8_t* d_points, const uint8_t* d_scalars, size_t n, uint8_t* d_out, void* stream)
 {
     C12_REQUIRE_CTX();
     if (n && (!d_out || !d_points || !d_scalars)) return set_error(C12381_EARG, "mul_batch: null pointer");
+    if (n == 1) {
+        cudaStream_t s = pick_stream(stream);
+        int rc = arena_begin(msm_scratch_for<F>(1), s);
+        if (rc) return rc;
+        return msm_run<F>(d_points, d_scalars, 1, d_out, OUT_COMPRESSED, s);
+    }
     return scalar_mul_run<F>(d_points, d_scalars, n, d_out, pick_stream(stream));
 }
 
@@ -1525,7 +1538,8 @@ template <class F> int entry_mul_host(const uint8_t* points, const uint8_t* scal
     if (n && (!out || !points || !scalars)) return set_error(C12381_EARG, "mul_batch: null pointer");
     const void* in[2] = {points, scalars};
     size_t sz[2] = {n * Wire<F>::AFFINE, n * 32};
-    return with_staged(in, sz, 2, out, n * Wire<F>::COMPRESSED, 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+    return with_staged(in, sz, 2, out, n * Wire<F>::COMPRESSED, n == 1 ? msm_scratch_for<F>(1) : 0, [&](uint8_t** d_in, uint8_t* d_out, cudaStream_t s) {
+        if (n == 1) return msm_run<F>(d_in[0], d_in[1], 1, d_out, OUT_COMPRESSED, s);      // see entry_mul_dev
         return scalar_mul_run<F>(d_in[0], d_in[1], n, d_out, s);
     });
 }
