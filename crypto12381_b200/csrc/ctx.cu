@@ -186,7 +186,6 @@ int c12381_init(int device)
     C12_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     for (auto& ev : c.copy_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     C12_CUDA(cudaEventCreateWithFlags(&c.arena_ev, cudaEventDisableTiming));
-    for (auto& st : c.side) C12_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     for (auto& ev : c.msm_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.side_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     for (auto& ev : c.group_ev) C12_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -197,6 +196,9 @@ int c12381_init(int device)
         C12_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
         C12_CUDA(cudaStreamCreateWithPriority(&c.front_stream, cudaStreamNonBlocking, greatest));
         C12_CUDA(cudaStreamCreateWithPriority(&c.plan_stream, cudaStreamNonBlocking, greatest));
+        // the side streams outrank the caller's (default = lowest priority): pipeline 1 - the high windows of the split tail - gets its
+        // blocks placed first, finishes its rounds early, and its reduction runs under pipeline 0's last rounds
+        for (auto& st : c.side) C12_CUDA(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
     }
     C12_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
     C12_CUDA(cudaMallocHost(&c.h_flags, 64 * sizeof(int)));
@@ -259,6 +261,7 @@ void c12381_set_knob(int id, int value)
     if (id == 4) ctx().upload_groups = value < 1 ? 1 : (value > 4 ? 4 : value);
     if (id == 5) ctx().front_end = value ? 1 : 0;
     if (id == 6) ctx().parse_aside = value ? 1 : 0;
+    if (id == 7) ctx().split_tail = value ? 1 : 0;
 }
 void c12381_set_msm_pipelines(int pipes) { ctx().ba_pipes = pipes < 1 ? 1 : (pipes > 4 ? 4 : pipes); }
 unsigned long long c12381_launch_count(void) { return ctx().launches; }

@@ -457,10 +457,10 @@ __global__ void __launch_bounds__(128) k_fold(uint32_t total, uint32_t groups, c
 
 // level 0 of the bucket reduction: one thread per (window, segment of seg_len buckets)
 template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? 3 : 1) k_reduce_level0(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ scratch)
+__global__ void __launch_bounds__(128, sizeof(F) == sizeof(Fp) ? 3 : 1) k_reduce_level0(MsmPlan pl, const Proj<F>* __restrict__ buckets, Proj<F>* __restrict__ scratch, uint32_t w0)
 {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t w = blockIdx.y;
+    uint32_t w = w0 + blockIdx.y;
     if (t >= pl.segs) return;
     uint32_t lo = t * pl.seg_len, hi = lo + pl.seg_len;
     if (hi > pl.half) hi = pl.half;
@@ -568,13 +568,13 @@ template <class F> struct PlaneShape {
 };
 template <class F>
 __global__ void __launch_bounds__(PlaneShape<F>::THREADS, 2) k_reduce_planes(MsmPlan pl, const Proj<F>* __restrict__ scratch, Proj<F>* __restrict__ parts,
-                                                                            uint32_t* __restrict__ tickets, Proj<F>* __restrict__ planes)
+                                                                            uint32_t* __restrict__ tickets, Proj<F>* __restrict__ planes, uint32_t w0)
 {
     constexpr int THREADS = PlaneShape<F>::THREADS;
     constexpr uint32_t SPLITS = PlaneShape<F>::SPLITS;
     __shared__ Proj<F> sh[THREADS / 4];
     __shared__ uint32_t s_last;
-    const uint32_t j = blockIdx.x, w = blockIdx.y, z = blockIdx.z;
+    const uint32_t j = blockIdx.x, w = w0 + blockIdx.y, z = blockIdx.z;
     const uint32_t splits = j == pl.plane_bits ? 2 * SPLITS : SPLITS;
     if (z >= splits) return;
     Proj<F> acc = msm_plane_slice_body<F>(pl, scratch + msm_sum0_offset(pl, w), scratch + msm_run1_offset(pl, w), j, z * THREADS + threadIdx.x,
@@ -608,16 +608,21 @@ template <class F> __device__ void write_point(uint8_t* out, const Proj<F>& r, i
         Wire<F>::compress(out, a);
 }
 
-// One block of 8 warps.  Warp v, for windows v, v + 8, ...: recombines the planes  S_w = T + L (P_0 + 2 (P_1 + ...))  with
-// lane-cooperative doublings and additions.  Then warp 0 runs the Horner combination over windows  acc = 2^c acc + S_w,
-// normalises and encodes.
-template <class F> __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __restrict__ planes, uint8_t* out, int out_mode)
+// One block of 8 warps over the windows [w_lo, w_hi).  Warp v, for windows w_lo + v, + 8, ...: recombines the planes
+// S_w = T + L (P_0 + 2 (P_1 + ...))  with lane-cooperative doublings and additions.  Then warp 0 runs the Horner combination
+// acc = 2^c acc + S_w  down to w_lo, multiplies by 2^(c shift) (the windows below a HIGH part), adds add_in (the high part's
+// result, for the low part), and either parks the point (part_out) or normalises and encodes it.  One launch over all windows
+// with shift = 0 is the whole tail; two launches let the high windows' chain of doublings - c (W - 1) of them whatever the
+// split - run while the low windows are still being added up (msm_run, "split tail").
+template <class F>
+__global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __restrict__ planes, uint8_t* out, int out_mode, uint32_t w_lo, uint32_t w_hi,
+                                                uint32_t shift, const Proj<F>* __restrict__ add_in, Proj<F>* __restrict__ part_out)
 {
     extern __shared__ __align__(16) unsigned char finish_smem[];
     Proj<F>* wsum = reinterpret_cast<Proj<F>*>(finish_smem);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t full = 0xffffffffu;
-    for (uint32_t w = warp; w < pl.windows; w += 8) {
+    for (uint32_t w = w_lo + warp; w < w_hi; w += 8) {
         const Proj<F>* slot = planes + (size_t)w * MSM_WPART_SLOTS;
         Proj<F> acc = slot[pl.plane_bits];
         if (pl.plane_bits > 0) {
@@ -631,18 +636,25 @@ template <class F> __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, c
             for (uint32_t len = pl.seg_len; len > 1; len >>= 1) acc = coop_dbl(acc, full);
             acc = coop_add(acc, slot[pl.plane_bits], full);
         }
-        if (lane == 0) wsum[w] = acc;
+        if (lane == 0) wsum[w - w_lo] = acc;
     }
     __syncthreads();
     if (warp) return;
-    Proj<F> acc = wsum[pl.windows - 1];
+    Proj<F> acc = wsum[w_hi - 1 - w_lo];
 #pragma unroll 1
-    for (uint32_t w = pl.windows - 1; w > 0; --w) {
+    for (uint32_t w = w_hi - 1; w > w_lo; --w) {
 #pragma unroll 1
         for (uint32_t k = 0; k < pl.c; ++k) acc = coop_dbl(acc, full);
-        acc = coop_add(acc, wsum[w - 1], full);
+        acc = coop_add(acc, wsum[w - 1 - w_lo], full);
     }
-    if (lane == 0) write_point<F>(out, acc, out_mode);
+#pragma unroll 1
+    for (uint32_t k = 0; k < shift * pl.c; ++k) acc = coop_dbl(acc, full);
+    if (add_in) acc = coop_add(acc, *add_in, full);
+    if (part_out) {
+        if (lane == 0) *part_out = acc;
+    } else if (lane == 0) {
+        write_point<F>(out, acc, out_mode);
+    }
 }
 
 // sum of n wire-format points (merging all-gathered per-rank partials; also a general point-sum entry)
@@ -789,6 +801,7 @@ size_t sort_scratch_words(uint32_t n, uint32_t nseg, size_t* tile_words);
 // XYZZ additions than with rounds that are all launch and inversion latency
 struct BaSchedule {
     uint32_t rounds = 0, groups = 1, pipes = 1, lanes = 1;
+    bool split_tail = false;
     uint32_t b_lo[BA_MAX_PIPES + 1];                            // pipeline p owns the real buckets [b_lo[p], b_lo[p + 1])
     uint32_t J0[BA_MAX_PIPES], warps0[BA_MAX_PIPES];            // round 0, per group
     uint32_t region0[BA_MAX_PIPES];                             // a group's region in list buffer 0 / the prefix array / the round-0 slot references
@@ -834,6 +847,13 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp)
         if (warps + 1 > sc.pool_stride) sc.pool_stride = warps + 1;
     };
     for (uint32_t p = 0; p <= sc.pipes; ++p) sc.b_lo[p] = (pl.windows * p / sc.pipes) * pl.half;
+    // split tail (msm_run): two pipelines, the HIGH windows the smaller one (3 of 8, 1 of 4) - it finishes its rounds first and its
+    // reduction and chain of doublings run under the low windows' last rounds
+    sc.split_tail = c.split_tail && sc.rounds > 1 && sc.pipes == 2 && pl.windows >= 4;
+    if (sc.split_tail) {
+        const uint32_t high = pl.windows * 3 / 8 > 0 ? pl.windows * 3 / 8 : 1;
+        sc.b_lo[1] = (pl.windows - high) * pl.half;
+    }
     // round 0: group g's level-1 lists hold at most (its entries) / 2 + one per bucket slots
     const size_t cap0 = (size_t)(((uint64_t)pl.windows * lp.n) >> 1) + pl.total + 1;
     sc.slots0 = (uint32_t)cap0;
@@ -893,7 +913,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     b += align_up(4 * hist_words) + align_up(4 * (tile_words + 16));
     b += align_up(4 * (size_t)BA_MAX_PIPES * count_scan_scratch_words(pl.total));
     b += 2 * align_up(4 * (size_t)lp.total);
-    b += align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax);
+    b += 2 * (align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax)) + align_up(sizeof(Proj<F>));      // twice: the split tail orders and accumulates each pipeline's buckets on their own
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
     const BaSchedule sc = msm_ba_schedule(pl, lp);
     if (sc.rounds) {
@@ -1008,6 +1028,9 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     uint32_t* end = (uint32_t*)arena_take(4 * (size_t)lp.total);
     uint32_t* chunk_scratch = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));
     Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
+    uint32_t* chunk_scratch2 = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));      // split tail: the second pipeline's
+    Proj<F>* vpartial2 = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
+    Proj<F>* hpart = (Proj<F>*)arena_take(sizeof(Proj<F>));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
     const BaSchedule sc = msm_ba_schedule(pl, lp);
     const uint32_t R = sc.rounds;
@@ -1165,8 +1188,22 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
         lend = ba_lend;
     }
     // bucket lists longer than pl.chunk entries are cut into chunks (XYZZ additions, one thread per chunk)
-    rc = launch_chunk_order(pl, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, plan_stream);
-    if (rc) return rc;
+    // split tail: each pipeline's buckets are ordered, accumulated, folded and reduced on their own (bucket ids relative to b_lo)
+    const bool split_tail = sc.split_tail;
+    MsmPlan tp[2] = {pl, pl};
+    uint32_t *t_order[2] = {nullptr, nullptr}, *t_vstart[2] = {nullptr, nullptr}, *t_vbucket[2] = {nullptr, nullptr};
+    if (split_tail) {
+        for (uint32_t p = 0; p < 2; ++p) {
+            tp[p].total = sc.b_lo[p + 1] - sc.b_lo[p];
+            tp[p].vmax = tp[p].total + (pl.vmax - pl.total);
+            rc = launch_chunk_order(tp[p], lstart + sc.b_lo[p], lend + sc.b_lo[p], p ? chunk_scratch2 : chunk_scratch, &t_vstart[p], &t_vbucket[p], &t_order[p],
+                                    plan_stream);
+            if (rc) return rc;
+        }
+    } else {
+        rc = launch_chunk_order(pl, lstart, lend, chunk_scratch, &vstart, &vbucket, &order, plan_stream);
+        if (rc) return rc;
+    }
     if (plan_stream != s) C12_CUDA(cudaEventRecord(c.msm_ev[BA_MAX_PIPES], plan_stream));
     if (parse_aside) C12_CUDA(cudaEventRecord(c.parse_ev[1], c.front_stream));
     // ---- the points, group by group; round 0 of each group behind them ------------------------------------------------------
@@ -1251,10 +1288,51 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
                 if (rc) return rc;
             }
         }
-        for (uint32_t p = 1; p < sc.pipes; ++p) {
-            C12_CUDA(cudaEventRecord(c.side_ev[p], c.side[p - 1]));
-            C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[p], 0));
+        if (!split_tail)
+            for (uint32_t p = 1; p < sc.pipes; ++p) {
+                C12_CUDA(cudaEventRecord(c.side_ev[p], c.side[p - 1]));
+                C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[p], 0));
+            }
+    }
+    if (split_tail) {
+        // Pipeline 1 (the high windows, the smaller share) finishes its rounds first: what is left of its lists, its bucket
+        // reduction and its part of the Horner chain - INCLUDING the c * (windows below) doublings that carry it to its place -
+        // run on its stream while pipeline 0 is still adding.  Pipeline 0 then has only its own windows' doublings to do.
+        const uint32_t wsplit = sc.b_lo[1] / pl.half;
+        for (uint32_t p = 0; p < 2; ++p) {
+            cudaStream_t st = lane_stream(p);
+            const uint32_t b0 = sc.b_lo[p], nb = tp[p].total, w0 = b0 / pl.half, nw = nb / pl.half;
+            k_accumulate<F, true><<<cdiv(tp[p].vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, st>>>(tp[p].vmax, pl.chunk, lstart + b0, lend + b0, nullptr, final_lists,
+                                                                                                           t_order[p], t_vbucket[p], t_vstart[p], p ? vpartial2 : vpartial);
+            C12_LAUNCHED();
+            k_fold<F><<<cdiv(nb, 128), 128, 0, st>>>(nb, 1, t_vstart[p], p ? vpartial2 : vpartial, buckets + b0);
+            C12_LAUNCHED();
+            if (p == 0) {
+                C12_CUDA(cudaEventRecord(c.ev[2], s));
+                C12_CUDA(cudaEventRecord(c.pev[5], s));
+            }
+            k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), nw), 128, 0, st>>>(pl, buckets, partial, w0);
+            C12_LAUNCHED();
+            if (p == 0) C12_CUDA(cudaEventRecord(c.pev[6], s));
+            k_reduce_planes<F><<<dim3(pl.plane_bits + 1, nw, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, st>>>(pl, partial, plane_parts, plane_tickets, wsum, w0);
+            C12_LAUNCHED();
+            if (p == 0) C12_CUDA(cudaEventRecord(c.pev[7], s));
         }
+        k_finish<F><<<1, 256, sizeof(Proj<F>) * (pl.windows - wsplit), c.side[0]>>>(pl, wsum, nullptr, out_mode, wsplit, pl.windows, wsplit, nullptr, hpart);
+        C12_LAUNCHED();
+        C12_CUDA(cudaEventRecord(c.side_ev[1], c.side[0]));
+        C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[1], 0));
+        k_finish<F><<<1, 256, sizeof(Proj<F>) * wsplit, s>>>(pl, wsum, d_out, out_mode, 0, wsplit, 0, hpart, nullptr);
+        C12_LAUNCHED();
+        C12_CUDA(cudaEventRecord(c.pev[8], s));
+        C12_CUDA(cudaEventRecord(c.ev[3], s));
+        c.stats.window_bits = (int)pl.c;
+        c.stats.ba_rounds = (int)sc.rounds;
+        c.stats.ba_pipes = (int)sc.pipes;
+        c.stats.groups = (int)groups;
+        c.stats.bucket_adds = N;
+        c.stats.accumulate_ms = -1.0;
+        return C12381_OK;
     }
     if (R)
         k_accumulate<F, true><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, lstart, lend, nullptr, final_lists, order, vbucket, vstart, vpartial);
@@ -1265,13 +1343,13 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));
-    k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial);
+    k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial, 0);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.pev[6], s));
-    k_reduce_planes<F><<<dim3(pl.plane_bits + 1, pl.windows, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, s>>>(pl, partial, plane_parts, plane_tickets, wsum);
+    k_reduce_planes<F><<<dim3(pl.plane_bits + 1, pl.windows, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, s>>>(pl, partial, plane_parts, plane_tickets, wsum, 0);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.pev[7], s));
-    k_finish<F><<<1, 256, sizeof(Proj<F>) * pl.windows, s>>>(pl, wsum, d_out, out_mode);
+    k_finish<F><<<1, 256, sizeof(Proj<F>) * pl.windows, s>>>(pl, wsum, d_out, out_mode, 0, pl.windows, 0, nullptr, nullptr);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.pev[8], s));
     C12_CUDA(cudaEventRecord(c.ev[3], s));

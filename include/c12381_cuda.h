@@ -77,7 +77,10 @@ C12381_API void c12381_set_msm_pipelines(int pipes);
  * 5 = how the bucket lists are made: 0 (default) by counting - atomic ranks, one scan, one scatter - or 1 by the stable segmented
  * radix sort and a bounds search (same results; the order inside a bucket's list is irrelevant to its sum),
  * 6 = device-resident single-group calls: 1 (default) runs the scalar-only stages on a high-priority stream beside the parse of
- * the points, 0 runs everything in line */
+ * the points, 0 runs everything in line,
+ * 7 = two pipelines of halving rounds: 1 gives the high windows the smaller pipeline and runs their bucket reduction and their part
+ * of the Horner chain under the low windows' last rounds, 0 (default; measured equal or faster) joins the pipelines before one
+ * common tail */
 C12381_API void c12381_set_knob(int id, int value);
 
 /* ---- multi-scalar multiplication ------------------------------------------------------------------------- */
