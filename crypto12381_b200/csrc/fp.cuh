@@ -180,7 +180,9 @@ C12_HD Fp fp_add(const Fp& a, const Fp& b)
 #if defined(C12_COUNT_FP_MUL) && !defined(__CUDA_ARCH__)
     ++host::addsub_counter();
 #endif
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(C12_EXP_LAZY_ADDS) && defined(C12_PAIRING_TU)
+    fp_add_noreduce_ptx(r.v, a.v, b.v);      // TIMING EXPERIMENT ONLY (wrong values): what the tower would cost with bounds-tracked lazy additions
+#elif defined(__CUDA_ARCH__)
     fp_add_ptx(r.v, a.v, b.v);
 #else
     uint32_t t[13];
@@ -202,7 +204,9 @@ C12_HD Fp fp_sub(const Fp& a, const Fp& b)
 #if defined(C12_COUNT_FP_MUL) && !defined(__CUDA_ARCH__)
     ++host::addsub_counter();
 #endif
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(C12_EXP_LAZY_ADDS) && defined(C12_PAIRING_TU)
+    fp_sub_addp_ptx(r.v, a.v, b.v);          // TIMING EXPERIMENT ONLY
+#elif defined(__CUDA_ARCH__)
     fp_sub_ptx(r.v, a.v, b.v);
 #else
     int64_t borrow = 0;

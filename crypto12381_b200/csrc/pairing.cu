@@ -3,6 +3,7 @@
 // pairing.cuh.  Replaces the one-at-a-time bridge calls pair_ate / pair_double_ate / pair_final_exponentiation /
 // multiply(fp12&) / pow(fp12&) (reference: src/miracl_core_interface.cpp:251-289).
 #include <stdlib.h>
+#define C12_PAIRING_TU 1      // fp.cuh: scope of the -DC12_EXP_LAZY_ADDS timing experiment
 
 // Measured defaults of this translation unit (profiles/r01ah_pairing_lockstep_ab.txt; -DC12_PAIR_NO_LOCKSTEP restores the old build):
 //  * block-wide barriers keep the warps of a block at the same place of the straight-line code (pairing.cuh, C12_BLOCK_ALIGN):

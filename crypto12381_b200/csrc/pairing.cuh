@@ -288,6 +288,9 @@ C12_HD_NOINLINE Fp12 miller_loop(const Affine<Fp>* P, const Affine<Fp2>* Q, uint
 #pragma unroll 1
     for (uint32_t j = 0; j < k; ++j) {
         live[j] = !affine_is_inf(P[j]);
+#if defined(C12_EXP_LAZY_ADDS)
+        live[j] = true;     // timing experiment (fp.cuh): the garbage values must not shorten the loop
+#endif
         B[j] = proj_from_affine(Q[j]);  // identity stays (0:1:0), as ECP2_affine leaves it
         A[j] = B[j];
     }
