@@ -29,6 +29,11 @@ if [ "${SKIP_NCU:-0}" = "0" ] && [ $BE -eq 0 ]; then
   echo "ncu launches exit $?" | tee -a $OUT/status.txt
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_accumulate -s 2 -c 1 -o $OUT/prof_accumulate -f $CMD > $OUT/ncu_full_acc.log 2>&1
   echo "ncu full accumulate exit $?" | tee -a $OUT/status.txt
+  # the dominant launch of the headline step: the first unwinding pass of the halving rounds (n = 2^20, default settings)
+  timeout 600 python tools/gpu/msm_once.py G1 20 > $OUT/plain_msm_once.log 2>&1 &&
+  timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_ba_bwd -s 7 -c 1 -o $OUT/prof_k_ba_bwd -f python tools/gpu/msm_once.py G1 20 > $OUT/ncu_full_ba_bwd.log 2>&1
+  echo "ncu full k_ba_bwd exit $?" | tee -a $OUT/status.txt
+  ncu -i $OUT/prof_k_ba_bwd.ncu-rep --page raw --csv > $OUT/prof_k_ba_bwd.raw.csv 2>/dev/null && rm -f $OUT/prof_k_ba_bwd.ncu-rep
   timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_pairing_coop -s 1 -c 1 -o $OUT/prof_pairing_coop -f $CMD > $OUT/ncu_full_pair_coop.log 2>&1
   echo "ncu full pairing (cooperative, 2^14 instances) exit $?" | tee -a $OUT/status.txt
   ncu -i $OUT/prof_pairing_coop.ncu-rep --page raw --csv > $OUT/prof_pairing_coop.raw.csv 2>/dev/null && rm -f $OUT/prof_pairing_coop.ncu-rep
