@@ -44,7 +44,7 @@ int launch_recode(const MsmPlan& pl, int group, const uint8_t* d_scalars, uint32
 // The counters are 4 B x buckets (1 MiB at c = 16), resident in L2; ranks come back from the L2 atomic unit.  Equal keys in
 // neighbouring lanes (equal or tiny scalars: a whole window in one bucket) would serialise on one counter, so a warp that sees any
 // aggregates its equal keys with match_any first - one atomic per distinct bucket.
-constexpr uint32_t COUNT_NONE = 0xffffffffu;
+constexpr uint32_t COUNT_NONE = MSM_NO_BUCKET;
 __global__ void k_ba_plan_top(uint32_t* __restrict__ tile_sums, uint32_t ntiles);
 
 struct RecodeCount {
@@ -69,7 +69,7 @@ struct RecodeCount {
             rank = atomicAdd(counts + b, 1u);
         }
         if (live) {
-            keys[o] = d ? ((d - 1) | (val & 0x80000000u)) : COUNT_NONE;
+            keys[o] = msm_count_key(d, val);
             ranks[o] = rank;
         }
     }
@@ -158,10 +158,8 @@ __global__ void __launch_bounds__(256) k_bucket_scatter(MsmPlan pl, uint32_t seg
     const uint64_t o = (uint64_t)seg0 * pl.n + t;
     const uint32_t key = keys[o];
     if (key == COUNT_NONE) return;
-    const uint32_t seg = (uint32_t)(o / pl.n), within = (uint32_t)(o - (uint64_t)seg * pl.n);
-    const uint32_t part = within / pl.n_group, li = within - part * pl.n_group, grp = seg / pl.real_windows;
-    const uint32_t val = (grp * pl.n_group + li + part * pl.n_in) | (key & 0x80000000u);
-    const size_t b = (size_t)seg * pl.half + (key & 0x7fffffffu);
+    const uint32_t val = msm_entry_term(pl, o) | (key & 0x80000000u);
+    const size_t b = (size_t)(o / pl.n) * pl.half + (key & 0x7fffffffu);
     const uint32_t rank = ranks[o];
     if (!refs) {
         vals[start[b] + rank] = val;

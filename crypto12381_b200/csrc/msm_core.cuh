@@ -447,6 +447,17 @@ template <class Emit> C12_HD void msm_recode_each(const MsmPlan& pl, uint32_t i,
     }
 }
 
+// Inverse of msm_recode_each's layout: the pipeline term (piece q of caller's term i is q n_in + i) whose entry sits at out index o.
+C12_HD uint32_t msm_entry_term(const MsmPlan& pl, uint64_t o)
+{
+    const uint32_t seg = (uint32_t)(o / pl.n), within = (uint32_t)(o - (uint64_t)seg * pl.n);
+    const uint32_t part = within / pl.n_group, li = within - part * pl.n_group, grp = seg / pl.real_windows;
+    return grp * pl.n_group + li + part * pl.n_in;
+}
+// The entry of the COUNTING front end: bucket inside the window | sign << 31, all ones when the term owns no bucket there.
+constexpr uint32_t MSM_NO_BUCKET = 0xffffffffu;
+C12_HD uint32_t msm_count_key(uint32_t d, uint32_t val) { return d ? ((d - 1) | (val & 0x80000000u)) : MSM_NO_BUCKET; }
+
 // Body of the recode kernel of the SORTED front end for term i: (key, value) pairs, key = bucket inside the window.
 struct RecodeToPairs {
     uint32_t invalid;

@@ -24,7 +24,7 @@ MsmPlan make_plan(uint32_t n, uint32_t c, uint32_t seg_len, uint32_t parts)
 }
 
 // parts = 1: no split; MsmTraits<F>::PARTS: the split the device entries use
-template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0, uint32_t chunk_override = 0, uint32_t groups = 1)
+template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in, uint32_t c, uint32_t seg_len, uint8_t* out, uint32_t parts = 1, uint32_t rounds = 0, uint32_t chunk_override = 0, uint32_t groups = 1, uint32_t counting = 0)
 {
     using W = Wire<F>;
     if (n_in == 0) {
@@ -57,6 +57,47 @@ template <class F> int msm(const uint8_t* pts, const uint8_t* sc, uint32_t n_in,
     std::vector<uint32_t> sk(N), sv(N);
     for (size_t i = 0; i < N; ++i) { sk[i] = keys[order[i]]; sv[i] = vals[order[i]]; }
     std::vector<uint32_t> start(pl.total, 0), end(pl.total, 0);
+    if (counting) {
+        // The device's default front end (k_recode_count -> scan -> k_bucket_scatter): every entry takes a rank inside its bucket
+        // from a counter, the lists are filled by (bucket start + rank).  The atomic arrival order is arbitrary on the device;
+        // here the entries arrive in a scrambled order (counting = the stride of the walk), which must not change the sum.
+        struct Emit {
+            std::vector<uint32_t>& k;
+            void operator()(uint32_t, uint64_t o, uint32_t d, uint32_t val) { k[o] = msm_count_key(d, val); }
+        };
+        std::vector<uint32_t> ck(N, 0xdeadbeefu), rank(N, 0), counts(pl.total, 0);
+        Emit emit{ck};
+        Scalar256 zero;
+        for (int k = 0; k < 8; ++k) zero.v[k] = 0;
+        for (uint32_t i = 0; i < pl.groups * pl.n_group; ++i) msm_recode_each(pl, i, i < n_in ? scalar_from_be32(sc + 32ull * i) : zero, emit);
+        size_t stride = counting;
+        auto gcd = [](size_t a, size_t b) { while (b) { size_t t = a % b; a = b; b = t; } return a; };
+        while (gcd(stride, N) != 1) ++stride;
+        for (size_t j = 0, o = 0; j < N; ++j, o = (o + stride) % N) {
+            if (ck[o] == 0xdeadbeefu) return -6;
+            if (ck[o] == MSM_NO_BUCKET) continue;
+            rank[o] = counts[(o / n) * pl.half + (ck[o] & 0x7fffffffu)]++;
+        }
+        for (uint32_t seg = 0, pos = 0; seg < pl.windows; ++seg) {
+            pos = (uint32_t)((size_t)seg * n);                    // a segment's lists start at its first entry, as on the device per group
+            if (seg % pl.real_windows) pos = end[(size_t)seg * pl.half - 1];
+            for (uint32_t k = 0; k < pl.half; ++k) {
+                const size_t b = (size_t)seg * pl.half + k;
+                start[b] = pos;
+                pos += counts[b];
+                end[b] = pos;
+            }
+        }
+        std::fill(sv.begin(), sv.end(), 0xdeadbeefu);
+        for (size_t o = 0; o < N; ++o) {
+            if (ck[o] == MSM_NO_BUCKET) continue;
+            const size_t b = (o / n) * pl.half + (ck[o] & 0x7fffffffu);
+            const uint32_t val = msm_entry_term(pl, o) | (ck[o] & 0x80000000u);
+            // the same (term | sign) the sorted front end attaches to this entry
+            if (val != vals[o]) return -7;
+            sv[start[b] + rank[o]] = val;
+        }
+    } else
     for (uint32_t w = 0; w < pl.windows; ++w)
         for (size_t i = 0; i < n; ++i) {
             size_t g = (size_t)w * n + i;
@@ -229,6 +270,15 @@ int hm_g1_msm_groups(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c,
 int hm_g2_msm_groups(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint32_t groups, uint8_t* out97)
 {
     return msm<Fp2>(p, s, n, c, 0, out97, MsmTraits<Fp2>::PARTS, rounds, 0, groups);
+}
+// the same with the bucket lists made by counting (the device's default front end), entries arriving in a walk of stride `arrival`
+int hm_g1_msm_counting(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint32_t groups, uint32_t arrival, uint8_t* out49)
+{
+    return msm<Fp>(p, s, n, c, 0, out49, MsmTraits<Fp>::PARTS, rounds, 0, groups, arrival ? arrival : 1);
+}
+int hm_g2_msm_counting(const uint8_t* p, const uint8_t* s, uint32_t n, uint32_t c, uint32_t rounds, uint32_t groups, uint32_t arrival, uint8_t* out97)
+{
+    return msm<Fp2>(p, s, n, c, 0, out97, MsmTraits<Fp2>::PARTS, rounds, 0, groups, arrival ? arrival : 1);
 }
 
 int hm_g1_mul(const uint8_t* p96, const uint8_t* s32, uint32_t n, uint8_t* out49)

@@ -234,6 +234,32 @@ def test_msm_upload_groups(golden_msm):
     assert l.hm_g1_msm_groups(H(e["points"]), H(e["scalars"]), len(H(e["scalars"])) // 32, 4, 2, 3, out) == 0 and out.raw == H(e["result"])
 
 
+def test_msm_bucket_lists_by_counting(golden_msm):
+    """The device's default front end: ranks from per-bucket counters, bounds from one scan, lists filled by (start + rank) -
+    msm_recode_each / msm_count_key / msm_entry_term, the bodies k_recode_count and k_bucket_scatter run.  The arrival order of
+    the entries (the atomics' order on the device) is scrambled with different strides and must not change a byte; the (term |
+    sign) derived from an entry's position must be the one the sorted front end attaches to it."""
+    l = hm.lib()
+    H = bytes.fromhex
+    for case in golden_msm["cases"]:
+        if case["n"] > 300:
+            continue
+        g1 = case["group"] == "g1"
+        pts = (hm.g1_fixed_base if g1 else hm.g2_fixed_base)(H(case["point_scalars"]))
+        for groups, rounds, c, arrival in ((1, 0, 4, 1), (1, 0, 5, 7), (1, 2, 3, 1001), (2, 1, 4, 13), (3, 3, 2, 5), (4, 0, 6, 3)):
+            out = ctypes.create_string_buffer(49 if g1 else 97)
+            fn = l.hm_g1_msm_counting if g1 else l.hm_g2_msm_counting
+            assert fn(pts, H(case["scalars"]), case["n"], c, rounds, groups, arrival, out) == 0, (case["group"], case["n"], groups, rounds, c, arrival)
+            assert out.raw == H(case["result"]), (case["group"], case["n"], groups, rounds, c, arrival)
+    for key, want in (("edge_g1", None), ("cancel_g1", bytes(49))):
+        e = golden_msm[key]
+        n = len(H(e["scalars"])) // 32
+        for groups, rounds, arrival in ((1, 0, 1), (1, 3, 11), (3, 2, 7)):
+            out = ctypes.create_string_buffer(49)
+            assert l.hm_g1_msm_counting(H(e["points"]), H(e["scalars"]), n, 4, rounds, groups, arrival, out) == 0
+            assert out.raw == (want if want is not None else H(e["result"])), (key, groups, rounds, arrival)
+
+
 def test_msm_chunked_accumulation(golden_msm):
     """Bucket lists cut into chunks (k_accumulate over virtual buckets + k_fold), down to chunks of one and three entries."""
     l = hm.lib()
