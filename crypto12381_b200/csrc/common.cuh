@@ -55,12 +55,12 @@ struct Ctx {
     int split_tail = 0;     // knob 7 (A/B): the high windows get the smaller of two pipelines and their reduction + Horner part run under the low windows' last rounds.  Measured (profiles/r03g_split_tail_ab.txt): tail 1.24 -> 1.02 ms but the uneven rounds cost as much - 6.82 -> 6.78 ms at n = 2^20, slower at 2^22 and over G2; off
     int front_end = 0;      // bucket lists: 0 = by counting (atomic ranks + scan + scatter), 1 = segmented radix sort + bounds search (stable; the A/B twin)
     int upload_groups = 4;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
-    cudaEvent_t group_ev[4] = {nullptr, nullptr, nullptr, nullptr}, sgroup_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // a group's points / scalars have arrived
+    cudaEvent_t group_ev[8] = {}, sgroup_ev[8] = {};   // a group's points / scalars have arrived
     int knob[4] = {1, 32, 3, 0};   // c12381_set_knob: [0] waves a pipeline round should span, [1] largest J, [2] halvings left to the XYZZ accumulation, [3] threads the segment running sums of the bucket reduction should fill (0 = default)
-    cudaStream_t side[3] = {nullptr, nullptr, nullptr};      // streams of lanes 1 .. 3 (lane 0 runs on the caller's stream)
+    cudaStream_t side[7] = {};      // streams of lanes 1 .. 7 (lane 0 runs on the caller's stream)
     cudaStream_t plan_stream = nullptr;                      // several upload groups: the merged plan, beside the groups' own stages
-    cudaEvent_t msm_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // a group's bucket bounds are in place (0 .. 3); the merged plan is (4)
-    cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // fork + one join per side stream
+    cudaEvent_t msm_ev[9] = {};   // a group's bucket bounds are in place (0 .. 7); the merged plan is (8)
+    cudaEvent_t side_ev[8] = {};   // fork + one join per side stream
     void* fb_table[2] = {nullptr, nullptr};   // fixed-base window tables (G1, G2), built on first use
     MsmStats stats;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

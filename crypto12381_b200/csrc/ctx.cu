@@ -258,7 +258,7 @@ void c12381_set_msm_batch_affine(int rounds) { ctx().ba_rounds = rounds < 0 ? -1
 void c12381_set_knob(int id, int value)
 {
     if (id >= 0 && id < 4) ctx().knob[id] = value;
-    if (id == 4) ctx().upload_groups = value < 1 ? 1 : (value > 4 ? 4 : value);
+    if (id == 4) ctx().upload_groups = value < 1 ? 1 : (value > 8 ? 8 : value);
     if (id == 5) ctx().front_end = value ? 1 : 0;
     if (id == 6) ctx().parse_aside = value ? 1 : 0;
     if (id == 7) ctx().split_tail = value ? 1 : 0;

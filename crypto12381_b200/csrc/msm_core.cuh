@@ -555,7 +555,7 @@ C12_HD uint32_t ba_bucket_of(const uint32_t* off, uint32_t hint, uint32_t hi, ui
 // Round 1 works on the MERGED level-1 lists: bucket b's list is the concatenation, in group order, of what round 0 left of
 // the groups' copies of it (group q's at position region1[q] + off1[q][b] of list buffer 0).  Output slot ii of the bucket adds
 // entries 2 ii and 2 ii + 1 of that concatenation; ry = 0xffffffff when there is no second entry.
-constexpr uint32_t BA_MAX_GROUPS = 4;
+constexpr uint32_t BA_MAX_GROUPS = 8;
 struct BaLevel1 {
     const uint32_t* off1[BA_MAX_GROUPS];
     uint32_t region1[BA_MAX_GROUPS];

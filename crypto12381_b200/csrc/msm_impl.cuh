@@ -1559,7 +1559,7 @@ template <class F> int entry_msm_host(const uint8_t* points, const uint8_t* scal
     uint8_t* d_out = (uint8_t*)arena_take(out_bytes);
     rc = flags_reset(s);
     if (rc) return rc;
-    cudaEvent_t ready_s[BA_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr}, ready_p[BA_MAX_PIPES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ready_s[BA_MAX_PIPES] = {}, ready_p[BA_MAX_PIPES] = {};
     if (n) {
         // copy stream, behind the point of `s` from which the arena is ours: scalars and points of group 0, of group 1, ...
         C12_CUDA(cudaEventRecord(c.copy_ev[0], s));

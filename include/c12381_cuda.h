@@ -72,7 +72,7 @@ C12381_API void c12381_set_msm_pipelines(int pipes);
 /* measurement knobs of the halving rounds (A/B runs; same results): id 0 = waves of resident warps a pipeline's round should
  * span (slots per lane J follows), 1 = largest J, 2 = halvings left to the XYZZ accumulation by the automatic round count,
  * 3 = threads the segment running sums of the bucket reduction should fill (sets the segment length; 0 = default),
- * 4 = upload groups of the host-pointer MSM entries (1 .. 4: the points are uploaded in that many pieces, each in front of its
+ * 4 = upload groups of the host-pointer MSM entries (1 .. 8; four measured best, profiles/r03n: the points are uploaded in that many pieces, each in front of its
  * own pipeline of halving rounds; default 4),
  * 5 = how the bucket lists are made: 0 (default) by counting - atomic ranks, one scan, one scatter - or 1 by the stable segmented
  * radix sort and a bounds search (same results; the order inside a bucket's list is irrelevant to its sum),

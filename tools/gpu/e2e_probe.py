@@ -20,7 +20,7 @@ h_p = d_p.cpu().pin_memory()
 h_out = torch.empty(49 if g1 else 97, dtype=torch.uint8).pin_memory()
 host = lib.c12381_g1_msm if g1 else lib.c12381_g2_msm
 results = set()
-for groups in (1, 2, 3, 4, 2):
+for groups in (1, 2, 4, 5, 6, 8, 4):
     lib.c12381_set_knob(4, groups)
     best = 1e9
     for it in range(6):
