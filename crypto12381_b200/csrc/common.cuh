@@ -52,6 +52,7 @@ struct Ctx {
     cudaStream_t front_stream = nullptr;   // highest priority.  One group: the scalar-only stages run here, the parse of the points beside them on the caller's stream (the default priority is the LOWEST there is, so it is the latency-bound chain that gets the high one; the parse fills what it leaves idle)
     cudaEvent_t parse_ev[2] = {nullptr, nullptr};   // fork, join of that
     int parse_aside = 1;
+    int ba_fill_pct = 100;  // knob 8 (A/B): share of the resident warps (3 blocks per SM counted) one lane's round is sized for, in percent
     int split_tail = 0;     // knob 7 (A/B): the high windows get the smaller of two pipelines and their reduction + Horner part run under the low windows' last rounds.  Measured (profiles/r03g_split_tail_ab.txt): tail 1.24 -> 1.02 ms but the uneven rounds cost as much - 6.82 -> 6.78 ms at n = 2^20, slower at 2^22 and over G2; off
     int front_end = 0;      // bucket lists: 0 = by counting (atomic ranks + scan + scatter), 1 = segmented radix sort + bounds search (stable; the A/B twin)
     int upload_groups = 4;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds

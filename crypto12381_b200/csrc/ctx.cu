@@ -262,6 +262,7 @@ void c12381_set_knob(int id, int value)
     if (id == 5) ctx().front_end = value ? 1 : 0;
     if (id == 6) ctx().parse_aside = value ? 1 : 0;
     if (id == 7) ctx().split_tail = value ? 1 : 0;
+    if (id == 8) ctx().ba_fill_pct = value < 10 ? 10 : (value > 800 ? 800 : value);
 }
 void c12381_set_msm_pipelines(int pipes) { ctx().ba_pipes = pipes < 1 ? 1 : (pipes > 4 ? 4 : pipes); }
 unsigned long long c12381_launch_count(void) { return ctx().launches; }

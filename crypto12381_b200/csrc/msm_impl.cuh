@@ -817,7 +817,7 @@ struct BaSchedule {
     size_t buf[4] = {0, 0, 0, 0}, prefix = 0, refs = 0, pool_stride = 0;
 };
 
-inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp)
+inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp, uint32_t blocks_per_sm)
 {
     BaSchedule sc;
     const Ctx& c = ctx();
@@ -837,10 +837,12 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp)
     sc.pipes = (uint32_t)c.ba_pipes < pl.windows ? (uint32_t)c.ba_pipes : pl.windows;
     if (sc.pipes < 1) sc.pipes = 1;
     sc.lanes = sc.groups > sc.pipes ? sc.groups : sc.pipes;
-    const uint32_t resident = (uint32_t)(c.sm_count > 0 ? c.sm_count : 148) * (C12_BA_THREADS / 32) * 3;
+    // one lane's round is sized for the warps that are resident at once: BaShape<F>::MIN_BLOCKS blocks per SM (4 over Fp, 2 over
+    // Fp2; a fixed 3 until r03o: accumulation -1 % over G1, -2 % over G2 at n = 2^20, profiles/r03o_fill_sweep.txt)
+    const uint32_t resident = (uint32_t)(c.sm_count > 0 ? c.sm_count : 148) * (C12_BA_THREADS / 32) * blocks_per_sm;
     const uint64_t jmax = c.knob[1] > 2 ? (uint64_t)c.knob[1] : 2, waves = (uint64_t)(c.knob[0] > 0 ? c.knob[0] : 1);
     auto shape = [&](size_t slots, uint32_t& J, uint32_t& warps) {
-        uint64_t j = slots / (32ull * resident * waves);
+        uint64_t j = slots * 100ull / (32ull * resident * waves * (uint64_t)(c.ba_fill_pct > 0 ? c.ba_fill_pct : 100));
         j = j < 2 ? 2 : (j > jmax ? jmax : j);
         J = (uint32_t)j;
         warps = (uint32_t)((slots + 32 * j - 1) / (32 * j));
@@ -915,7 +917,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     b += 2 * align_up(4 * (size_t)lp.total);
     b += 2 * (align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax)) + align_up(sizeof(Proj<F>));      // twice: the split tail orders and accumulates each pipeline's buckets on their own
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(pl, lp);
+    const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS);
     if (sc.rounds) {
         // level offsets: one level-1 array per group, levels 2 .. rounds merged; the plan scratch of both; the list bounds
         b += align_up(4 * (size_t)(sc.groups + sc.rounds) * ((size_t)pl.total + 1));
@@ -972,7 +974,7 @@ template <class F> bool msm_plans(size_t n, uint32_t groups, MsmPlan& pl, MsmPla
     pl = msm_make_plan((uint32_t)n, cbits, parts, seg_wave);
     if (groups > BA_MAX_PIPES) groups = BA_MAX_PIPES;
     lp = msm_list_plan(pl, groups);
-    if (groups > 1 && msm_ba_schedule(pl, lp).rounds < 2) lp = pl;
+    if (groups > 1 && msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS).rounds < 2) lp = pl;
     return true;
 }
 
@@ -1032,7 +1034,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     Proj<F>* vpartial2 = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
     Proj<F>* hpart = (Proj<F>*)arena_take(sizeof(Proj<F>));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(pl, lp);
+    const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS);
     const uint32_t R = sc.rounds;
     uint32_t *off1 = nullptr, *offm = nullptr, *ba_tiles = nullptr, *ba_lstart = nullptr, *ba_lend = nullptr;
     uint2* ba_refs = nullptr;

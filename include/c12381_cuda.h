@@ -80,7 +80,8 @@ C12381_API void c12381_set_msm_pipelines(int pipes);
  * the points, 0 runs everything in line,
  * 7 = two pipelines of halving rounds: 1 gives the high windows the smaller pipeline and runs their bucket reduction and their part
  * of the Horner chain under the low windows' last rounds, 0 (default; measured equal or faster) joins the pipelines before one
- * common tail */
+ * common tail,
+ * 8 = percent of the resident warps (BA kernels' blocks per SM x 4 warps x SMs) one lane's halving round is sized for (default 100) */
 C12381_API void c12381_set_knob(int id, int value);
 
 /* ---- multi-scalar multiplication ------------------------------------------------------------------------- */
