@@ -184,6 +184,9 @@ template <class F> __device__ __forceinline__ F shfl_xor_obj(const F& x, int mas
 #endif
 template <class F> struct BaShape {
     static constexpr int MIN_BLOCKS = sizeof(F) == sizeof(Fp) ? C12_BA_MIN_BLOCKS : C12_BA2_MIN_BLOCKS;
+    // automatic rounds from this many (term, window) entries on: 2^22 over Fp, 2^21 over Fp2 (an Fp2 addition saves more per round:
+    // G2 n = 2^17 5.06 -> 4.83 ms, profiles/r03q_rounds_sweep.txt)
+    static constexpr uint32_t AUTO_MIN_LOG = sizeof(F) == sizeof(Fp) ? 22 : 21;
 };
 
 // the input a slot reference names, as a signed affine point
@@ -504,26 +507,59 @@ template <class F, int N> __device__ __forceinline__ void coop_mul(F (&out)[N], 
     for (int i = 0; i < N; ++i) out[i] = group_bcast_obj(m, i, mask);
 }
 
+// WARP-WIDE variant (all 32 lanes hold the same operands; k_finish, k_fixed_base_windows).  Over Fp it is the 8-lane scheme.  Over
+// Fp2 the N Karatsuba products are 3 N Fp products on 3 N lanes - lane 3 i + j computes a.a b.a / a.b b.b / (a.a + a.b)(b.a + b.b)
+// of product i, lane 3 i collects the three and finishes the recombination - so a layer costs one Fp product latency instead
+// of three (G2 Horner chain: ~10 us -> ~5 us per doubling).
+template <int N> __device__ __forceinline__ void coop_mul_warp(Fp (&out)[N], const Fp (&a)[N], const Fp (&b)[N]) { coop_mul<Fp, N>(out, a, b, 0xffffffffu); }
+template <int N> __device__ __forceinline__ void coop_mul_warp(Fp2 (&out)[N], const Fp2 (&a)[N], const Fp2 (&b)[N])
+{
+    static_assert(3 * N <= 32, "one lane per Fp product");
+    const int lane = threadIdx.x & 31, i = lane / 3, j = lane - 3 * i;
+    Fp2 xa = a[0], xb = b[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) {
+        xa = select(i == k, a[k], xa);
+        xb = select(i == k, b[k], xb);
+    }
+    const Fp x = fp_select(j == 0, xa.a, fp_select(j == 1, xa.b, fp_add(xa.a, xa.b)));
+    const Fp y = fp_select(j == 0, xb.a, fp_select(j == 1, xb.b, fp_add(xb.a, xb.b)));
+    const Fp m = fp_mul_inl(x, y);
+    const Fp t1 = shfl_down_obj(m, 1), t2 = shfl_down_obj(m, 2);       // meaningful on lanes 3 i: m = a.a b.a, t1 = a.b b.b, t2 = the cross product
+    const Fp2 r = Fp2{fp_sub(m, t1), fp_sub(fp_sub(t2, m), t1)};
+#pragma unroll
+    for (int k = 0; k < N; ++k) out[k] = shfl_bcast_obj(r, 3 * k);
+}
+
 // proj_dbl (RCB15 Algorithm 9), same value
-template <class F> __device__ Proj<F> coop_dbl(const Proj<F>& p, uint32_t mask)
+template <class F, bool WARP = false> __device__ Proj<F> coop_dbl(const Proj<F>& p, uint32_t mask)
 {
     F a1[4] = {p.y, p.y, p.z, p.x}, b1[4] = {p.y, p.z, p.z, p.y}, m[4];
-    coop_mul<F, 4>(m, a1, b1, mask);                // t0 = Y^2, t1 = YZ, t2 = Z^2, XY
+    if constexpr (WARP)
+        coop_mul_warp<4>(m, a1, b1);
+    else
+        coop_mul<F, 4>(m, a1, b1, mask);                // t0 = Y^2, t1 = YZ, t2 = Z^2, XY
     F z3 = mul8(m[0]);
     F t2 = FieldOps<F>::mul_b3(m[2]);
     F y3 = add(m[0], t2);
     F t0 = sub(m[0], mul3(t2));
     F a2[4] = {t2, z3, y3, t0}, b2[4] = {z3, m[1], t0, m[3]}, n[4];
-    coop_mul<F, 4>(n, a2, b2, mask);                // x3, Z3, y3 t0, t0 XY
+    if constexpr (WARP)
+        coop_mul_warp<4>(n, a2, b2);
+    else
+        coop_mul<F, 4>(n, a2, b2, mask);                // x3, Z3, y3 t0, t0 XY
     return Proj<F>{dbl(n[3]), add(n[2], n[0]), n[1]};
 }
 
 // proj_add (RCB15 Algorithm 7), same value
-template <class F> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& q, uint32_t mask)
+template <class F, bool WARP = false> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& q, uint32_t mask)
 {
     F a1[6] = {p.x, p.y, p.z, add(p.x, p.y), add(p.y, p.z), add(p.x, p.z)};
     F b1[6] = {q.x, q.y, q.z, add(q.x, q.y), add(q.y, q.z), add(q.x, q.z)}, m[6];
-    coop_mul<F, 6>(m, a1, b1, mask);
+    if constexpr (WARP)
+        coop_mul_warp<6>(m, a1, b1);
+    else
+        coop_mul<F, 6>(m, a1, b1, mask);
     F t3 = sub(m[3], add(m[0], m[1]));
     F t4 = sub(m[4], add(m[1], m[2]));
     F y3 = FieldOps<F>::mul_b3(sub(m[5], add(m[0], m[2])));
@@ -532,7 +568,10 @@ template <class F> __device__ Proj<F> coop_add(const Proj<F>& p, const Proj<F>& 
     F z3 = add(m[1], t2);
     F t1 = sub(m[1], t2);
     F a2[6] = {y3, t3, y3, t1, t0, z3}, b2[6] = {t4, t1, t0, z3, t3, t4}, n[6];
-    coop_mul<F, 6>(n, a2, b2, mask);
+    if constexpr (WARP)
+        coop_mul_warp<6>(n, a2, b2);
+    else
+        coop_mul<F, 6>(n, a2, b2, mask);
     return Proj<F>{sub(n[1], n[0]), add(n[2], n[3]), add(n[5], n[4])};
 }
 
@@ -629,12 +668,12 @@ __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __res
             acc = slot[pl.plane_bits - 1];
 #pragma unroll 1
             for (uint32_t j = pl.plane_bits - 1; j > 0; --j) {
-                acc = coop_dbl(acc, full);
-                acc = coop_add(acc, slot[j - 1], full);
+                acc = coop_dbl<F, true>(acc, full);
+                acc = coop_add<F, true>(acc, slot[j - 1], full);
             }
 #pragma unroll 1
-            for (uint32_t len = pl.seg_len; len > 1; len >>= 1) acc = coop_dbl(acc, full);
-            acc = coop_add(acc, slot[pl.plane_bits], full);
+            for (uint32_t len = pl.seg_len; len > 1; len >>= 1) acc = coop_dbl<F, true>(acc, full);
+            acc = coop_add<F, true>(acc, slot[pl.plane_bits], full);
         }
         if (lane == 0) wsum[w - w_lo] = acc;
     }
@@ -644,12 +683,12 @@ __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __res
 #pragma unroll 1
     for (uint32_t w = w_hi - 1; w > w_lo; --w) {
 #pragma unroll 1
-        for (uint32_t k = 0; k < pl.c; ++k) acc = coop_dbl(acc, full);
-        acc = coop_add(acc, wsum[w - 1 - w_lo], full);
+        for (uint32_t k = 0; k < pl.c; ++k) acc = coop_dbl<F, true>(acc, full);
+        acc = coop_add<F, true>(acc, wsum[w - 1 - w_lo], full);
     }
 #pragma unroll 1
-    for (uint32_t k = 0; k < shift * pl.c; ++k) acc = coop_dbl(acc, full);
-    if (add_in) acc = coop_add(acc, *add_in, full);
+    for (uint32_t k = 0; k < shift * pl.c; ++k) acc = coop_dbl<F, true>(acc, full);
+    if (add_in) acc = coop_add<F, true>(acc, *add_in, full);
     if (part_out) {
         if (lane == 0) *part_out = acc;
     } else if (lane == 0) {
@@ -707,7 +746,7 @@ __global__ void __launch_bounds__(32) k_fixed_base_windows(const uint8_t* __rest
         if (lane == 0) wbase[j * FB_WINDOWS + w] = acc;
         if (w + 1 < FB_WINDOWS) {
 #pragma unroll 1
-            for (int i = 0; i < 8; ++i) acc = coop_dbl(acc, 0xffffffffu);
+            for (int i = 0; i < 8; ++i) acc = coop_dbl<F, true>(acc, 0xffffffffu);
         }
     }
 }
@@ -817,7 +856,7 @@ struct BaSchedule {
     size_t buf[4] = {0, 0, 0, 0}, prefix = 0, refs = 0, pool_stride = 0;
 };
 
-inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp, uint32_t blocks_per_sm)
+inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp, uint32_t blocks_per_sm, uint32_t auto_min_log = C12_BA_AUTO_MIN_LOG)
 {
     BaSchedule sc;
     const Ctx& c = ctx();
@@ -827,7 +866,7 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp, uint32_t
     while (R < 12 && (1ull << R) * pl.total < 2 * N) ++R;      // lists of twice the mean load would end up as single sums
     if (c.ba_rounds > 0)
         R = (uint32_t)c.ba_rounds;
-    else if (N < (1ull << C12_BA_AUTO_MIN_LOG))
+    else if (N < (1ull << auto_min_log))
         return sc;
     else
         R = R > (uint32_t)c.knob[2] ? R - (uint32_t)c.knob[2] : 0;
@@ -917,7 +956,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     b += 2 * align_up(4 * (size_t)lp.total);
     b += 2 * (align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax)) + align_up(sizeof(Proj<F>));      // twice: the split tail orders and accumulates each pipeline's buckets on their own
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS);
+    const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS, BaShape<F>::AUTO_MIN_LOG);
     if (sc.rounds) {
         // level offsets: one level-1 array per group, levels 2 .. rounds merged; the plan scratch of both; the list bounds
         b += align_up(4 * (size_t)(sc.groups + sc.rounds) * ((size_t)pl.total + 1));
@@ -974,7 +1013,7 @@ template <class F> bool msm_plans(size_t n, uint32_t groups, MsmPlan& pl, MsmPla
     pl = msm_make_plan((uint32_t)n, cbits, parts, seg_wave);
     if (groups > BA_MAX_PIPES) groups = BA_MAX_PIPES;
     lp = msm_list_plan(pl, groups);
-    if (groups > 1 && msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS).rounds < 2) lp = pl;
+    if (groups > 1 && msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS, BaShape<F>::AUTO_MIN_LOG).rounds < 2) lp = pl;
     return true;
 }
 
@@ -1034,7 +1073,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     Proj<F>* vpartial2 = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
     Proj<F>* hpart = (Proj<F>*)arena_take(sizeof(Proj<F>));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
-    const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS);
+    const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS, BaShape<F>::AUTO_MIN_LOG);
     const uint32_t R = sc.rounds;
     uint32_t *off1 = nullptr, *offm = nullptr, *ba_tiles = nullptr, *ba_lstart = nullptr, *ba_lend = nullptr;
     uint2* ba_refs = nullptr;
