@@ -441,15 +441,22 @@ __global__ void __launch_bounds__(AccShape<F>::THREADS, AccShape<F>::MIN_BLOCKS)
 #endif
 }
 
-// bucket b = the partial sums of its chunks, over all upload groups (group g's copy of the bucket is list g * total + b)
+// bucket b = the partial sums of its chunks, over all upload groups (group g's copy of the bucket is list g * total + b).
+// A bucket with more than FOLD_SERIAL_MAX chunks (skewed scalars: a whole window in one bucket is thousands of chunks) is not
+// folded by its one thread - that chain was 120 ms for 2^18 equal scalars over G2 - but handed to k_fold_heavy through a list.
+constexpr uint32_t FOLD_SERIAL_MAX = 16;
 template <class F>
 __global__ void __launch_bounds__(128) k_fold(uint32_t total, uint32_t groups, const uint32_t* __restrict__ vstart, const Proj<F>* __restrict__ vpartial,
-                                              Proj<F>* __restrict__ buckets)
+                                              Proj<F>* __restrict__ buckets, uint32_t* __restrict__ heavy)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= total) return;
-    const uint32_t v0 = vstart[b];
-    Proj<F> acc = msm_fold_body<F>(vpartial + v0, vstart[b + 1] - v0);
+    const uint32_t v0 = vstart[b], nch = vstart[b + 1] - v0;
+    if (heavy && groups == 1 && nch > FOLD_SERIAL_MAX) {
+        heavy[1 + atomicAdd(heavy, 1u)] = b;          // heavy[0]: count, then the bucket ids
+        return;
+    }
+    Proj<F> acc = msm_fold_body<F>(vpartial + v0, nch);
 #pragma unroll 1
     for (uint32_t g = 1; g < groups; ++g) {
         const uint32_t v = vstart[g * total + b];
@@ -593,6 +600,26 @@ template <class F, int THREADS> __device__ void block_sum_coop(Proj<F> acc, Proj
             const Proj<F> r = coop_add(sh[g], sh[g + n], mask);
             if ((tid & 7) == 0) sh[g] = r;
         }
+        __syncthreads();
+    }
+}
+
+// the buckets k_fold left: one block per bucket at a time, every thread adds up a strided share of the chunk partials, the block's
+// tree (block_sum_coop) the rest.  A group sum: any order gives the same bucket.  With no heavy bucket (random scalars) the blocks
+// read the count and leave.
+template <class F> __global__ void __launch_bounds__(128) k_fold_heavy(const uint32_t* __restrict__ heavy, const uint32_t* __restrict__ vstart,
+                                                                          const Proj<F>* __restrict__ vpartial, Proj<F>* __restrict__ buckets)
+{
+    __shared__ Proj<F> sh[128 / 4];
+    const uint32_t count = heavy[0];
+#pragma unroll 1
+    for (uint32_t h = blockIdx.x; h < count; h += gridDim.x) {
+        const uint32_t b = heavy[1 + h], v0 = vstart[b], nch = vstart[b + 1] - v0;
+        Proj<F> acc = proj_inf<F>();
+#pragma unroll 1
+        for (uint32_t j = threadIdx.x; j < nch; j += 128) acc = proj_add(acc, vpartial[v0 + j]);
+        block_sum_coop<F, 128>(acc, sh);
+        if (threadIdx.x == 0) buckets[b] = sh[0];
         __syncthreads();
     }
 }
@@ -967,7 +994,8 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
         b += align_up(sizeof(F) * sc.pool_stride * sc.lanes) + align_up(sizeof(F) * sc.pool_stride * sc.lanes * 32);
     }
     b += align_up(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
-    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS) * (1 + 2 * PlaneShape<F>::SPLITS) + align_up(4 * (size_t)pl.windows * MSM_WPART_SLOTS);
+    b += align_up(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS) * (1 + 2 * PlaneShape<F>::SPLITS) + align_up(4 * ((size_t)pl.windows * MSM_WPART_SLOTS + 8));
+    b += align_up(4 * 2 * ((size_t)pl.total + 1));
     return b + 65536;
 }
 
@@ -1095,9 +1123,13 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     Proj<F>* partial = (Proj<F>*)arena_take(sizeof(Proj<F>) * msm_reduce_scratch_points(pl));
     Proj<F>* wsum = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS);
     Proj<F>* plane_parts = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.windows * MSM_WPART_SLOTS * 2 * PlaneShape<F>::SPLITS);
-    uint32_t* plane_tickets = (uint32_t*)arena_take(4 * (size_t)pl.windows * MSM_WPART_SLOTS);
-    if (!plane_tickets) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
+    uint32_t* plane_tickets = (uint32_t*)arena_take(4 * ((size_t)pl.windows * MSM_WPART_SLOTS + 8));      // + the two counts of the heavy-bucket lists (k_fold)
+    uint32_t* heavy_lists = (uint32_t*)arena_take(4 * 2 * ((size_t)pl.total + 1));
+    if (!heavy_lists) return set_error(C12381_ECUDA, "msm: scratch arena bound too small");
+    uint32_t* heavy[2] = {heavy_lists, heavy_lists + pl.total + 1};
     C12_CUDA(cudaMemsetAsync(plane_tickets, 0, 4 * (size_t)pl.windows * MSM_WPART_SLOTS, s));
+    C12_CUDA(cudaMemsetAsync(heavy[0], 0, 4, s));
+    C12_CUDA(cudaMemsetAsync(heavy[1], 0, 4, s));
 
     C12_CUDA(cudaEventRecord(c.ev[0], s));
     C12_CUDA(cudaEventRecord(c.pev[0], s));
@@ -1346,7 +1378,9 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
             k_accumulate<F, true><<<cdiv(tp[p].vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, st>>>(tp[p].vmax, pl.chunk, lstart + b0, lend + b0, nullptr, final_lists,
                                                                                                            t_order[p], t_vbucket[p], t_vstart[p], p ? vpartial2 : vpartial);
             C12_LAUNCHED();
-            k_fold<F><<<cdiv(nb, 128), 128, 0, st>>>(nb, 1, t_vstart[p], p ? vpartial2 : vpartial, buckets + b0);
+            k_fold<F><<<cdiv(nb, 128), 128, 0, st>>>(nb, 1, t_vstart[p], p ? vpartial2 : vpartial, buckets + b0, heavy[p]);
+            C12_LAUNCHED();
+            k_fold_heavy<F><<<2 * (unsigned)(c.sm_count > 0 ? c.sm_count : 148), 128, 0, st>>>(heavy[p], t_vstart[p], p ? vpartial2 : vpartial, buckets + b0);
             C12_LAUNCHED();
             if (p == 0) {
                 C12_CUDA(cudaEventRecord(c.ev[2], s));
@@ -1380,7 +1414,9 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     else
         k_accumulate<F, false><<<cdiv(pl.vmax, AccShape<F>::THREADS), AccShape<F>::THREADS, 0, s>>>(pl.vmax, pl.chunk, start, end, svals, pts, order, vbucket, vstart, vpartial);
     C12_LAUNCHED();
-    k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, 1, vstart, vpartial, buckets);
+    k_fold<F><<<cdiv(pl.total, 128), 128, 0, s>>>(pl.total, 1, vstart, vpartial, buckets, heavy[0]);
+    C12_LAUNCHED();
+    k_fold_heavy<F><<<2 * (unsigned)(c.sm_count > 0 ? c.sm_count : 148), 128, 0, s>>>(heavy[0], vstart, vpartial, buckets);
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));
