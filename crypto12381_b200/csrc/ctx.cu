@@ -115,25 +115,38 @@ __global__ void __launch_bounds__(PROBE_THREADS) k_probe_madc(uint32_t* out, int
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
 
-// kind 2: 8 independent mad.wide.u32 chains (32x32 -> 64 + 64)
+// kind 2: 8 independent mad.wide.u32 chains (32x32 -> 64 + 64).  Every chain multiplies the low word of ITS OWN accumulator: with
+// one shared pair of multiplicands (the probe until r03u) ptxas computes the product once per step and the eight "mad.wide" turn into
+// 64-bit additions on the ALU pipe - ncu showed fmaheavy 27 %, ALU 76 % and only 41 IMAD.WIDE per 320 in the SASS
+// (profiles/r03u_k_probe_wide_full.md): that "13.6 T/s" was not a multiplier rate.
 __global__ void __launch_bounds__(PROBE_THREADS) k_probe_wide(uint32_t* out, int iters, uint32_t seed)
 {
     unsigned long long a0 = threadIdx.x + seed, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    uint32_t m = seed | 1u, q = seed * 3u + 5u;
+    uint32_t q = seed * 3u + 5u;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            asm volatile("mad.wide.u32 %0, %8, %9, %0;\n\t"
-                         "mad.wide.u32 %1, %8, %9, %1;\n\t"
-                         "mad.wide.u32 %2, %8, %9, %2;\n\t"
-                         "mad.wide.u32 %3, %8, %9, %3;\n\t"
-                         "mad.wide.u32 %4, %8, %9, %4;\n\t"
-                         "mad.wide.u32 %5, %8, %9, %5;\n\t"
-                         "mad.wide.u32 %6, %8, %9, %6;\n\t"
-                         "mad.wide.u32 %7, %8, %9, %7;\n\t"
+            asm volatile("{\n\t"
+                         ".reg .u32 t0, t1, t2, t3, t4, t5, t6, t7;\n\t"
+                         "cvt.u32.u64 t0, %0;\n\t"
+                         "cvt.u32.u64 t1, %1;\n\t"
+                         "cvt.u32.u64 t2, %2;\n\t"
+                         "cvt.u32.u64 t3, %3;\n\t"
+                         "cvt.u32.u64 t4, %4;\n\t"
+                         "cvt.u32.u64 t5, %5;\n\t"
+                         "cvt.u32.u64 t6, %6;\n\t"
+                         "cvt.u32.u64 t7, %7;\n\t"
+                         "mad.wide.u32 %0, t0, %8, %0;\n\t"
+                         "mad.wide.u32 %1, t1, %8, %1;\n\t"
+                         "mad.wide.u32 %2, t2, %8, %2;\n\t"
+                         "mad.wide.u32 %3, t3, %8, %3;\n\t"
+                         "mad.wide.u32 %4, t4, %8, %4;\n\t"
+                         "mad.wide.u32 %5, t5, %8, %5;\n\t"
+                         "mad.wide.u32 %6, t6, %8, %6;\n\t"
+                         "mad.wide.u32 %7, t7, %8, %7;\n\t"
+                         "}\n\t"
                          : "+l"(a0), "+l"(a1), "+l"(a2), "+l"(a3), "+l"(a4), "+l"(a5), "+l"(a6), "+l"(a7)
-                         : "r"(m), "r"(q));
-            m += (uint32_t)a7;
+                         : "r"(q));
         }
     }
     unsigned long long x = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;

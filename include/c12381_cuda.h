@@ -240,7 +240,8 @@ C12381_API int c12381_fp12_pow_miracl(void* result_fp12, const void* base_fp12, 
  * instruction mix on every SM and return achieved giga-ops/s in *out_gops (ops as documented per kind):
  *   kind 0: mad.lo.u32 (IMAD)            ops = 32-bit multiply-adds
  *   kind 1: mad.lo.cc / madc.hi.cc pairs ops = 32-bit multiply-add instructions
- *   kind 2: mad.wide.u32 (IMAD.WIDE)     ops = 32x32->64 multiply-adds
+ *   kind 2: mad.wide.u32 (IMAD.WIDE)     ops = 32x32->64 multiply-adds, every chain multiplying a value of its own (until round 2's
+ *           last visit all chains shared their operands and ptxas hoisted the product: that rate was not a multiplier rate)
  *   kind 3: full Fp Montgomery product   ops = Fp multiplications
  *   kind 4: full Fp Montgomery squaring  ops = Fp squarings */
 C12381_API int c12381_probe(int kind, int iters, double* out_gops, double* out_ms);
