@@ -10,7 +10,10 @@ seeded synthetic (point, scalar) terms per GPU.  With N GPUs every rank owns 2^2
 (weak scaling): per-rank partial -> one all-gather of the 96-byte partials over NCCL -> every rank adds them.
   value      whole-job points/s with inputs resident in HBM (device entries, CUDA events, max over ranks)
   e2e        the same through the host-pointer C-ABI call c12381_g1_msm (pinned host buffers, H2D + D2H inside)
-  roofline   dominant kernel k_accumulate against the integer-multiply peak measured live by c12381_probe
+  roofline   the bucket accumulation (batch-affine halving rounds + XYZZ rest) against the integer pipe's rate for 32x32->64
+             multiply-adds, measured live by c12381_probe: IMAD rate / 2 (two fmaheavy slots per wide multiply-add; ncu evidence in
+             profiles/r03u, r03v - the 13.6 T/s of rounds 1-2 came from a probe whose product ptxas had hoisted;
+             frac_r01_denominator keeps that figure beside the corrected one)
   cpu_baseline   the reference's own CPU path (oracle/_ref: MIRACL ECP_muln via the unmodified bridge) on a
              bounded sample of the same points, all host threads, rank 0 only
   secondary  batched 4-pair pairing products (BASELINE configs[3]) as pairings/s, G2 MSM (configs[2]), the G1 sweep

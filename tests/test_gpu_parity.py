@@ -328,6 +328,24 @@ def test_skewed_scalars_and_repeated_points(cuda, ba_rounds):
     assert cuda.msm1(same, ss) == cuda.mul1(pts[:96], be32(sum(ints(ss)) % R))
 
 
+def test_heavy_buckets_at_size(cuda):
+    """2^16 equal scalars (G1) / 2^14 (G2): every window is ONE bucket of thousands of chunks - the lists k_fold hands to
+    k_fold_heavy - under the default settings (halving rounds off at this size) and with rounds forced on."""
+    from crypto12381_b200 import _lib
+    s = 0x5A5A1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+    for g1, n in ((True, 1 << 16), (False, 1 << 14)):
+        ks = rand_scalars(n, 77)
+        gen = bytes.fromhex(load_golden("points.json")["g1_generator" if g1 else "g2_generator"])
+        pts = (cuda.fixed_base1 if g1 else cuda.fixed_base2)(ks)
+        want = (cuda.mul1 if g1 else cuda.mul2)(gen, be32(sum(ints(ks)) * s % R))
+        for rounds in (-1, 3):
+            _lib.lib().c12381_set_msm_batch_affine(rounds)
+            try:
+                assert (cuda.msm1 if g1 else cuda.msm2)(pts, be32(s) * n) == want, (g1, rounds)
+            finally:
+                _lib.lib().c12381_set_msm_batch_affine(-1)
+
+
 def test_pairing_check_full_batch(cuda, pairing_kernel):
     """2^12 instances x 4 pairs with  Π_j e(a_j G1, b_j G2) · e(-(Σ a_j b_j) G1, G2) == 1; flipped instances fail."""
     B, k = 1 << 12, 4
