@@ -201,7 +201,13 @@ template <class F, bool FIRST> __device__ __forceinline__ const Affine<F>* ba_in
 {
     return FIRST ? io.pts + (ref & 0x7fffffffu) : io.lists + ref;
 }
-#if defined(C12_BA_PREFETCH_L1)
+// The next slot's operands used to be pulled into L2 ahead of their use.  With 16 resident warps per SM (4 blocks, r02q) the
+// warps hide that latency themselves and the prefetches only add traffic (the ncu capture of round 0 showed 0.5 GB of reads
+// beyond what the 64-byte fetch granularity explains): without them G1 n = 2^20 -0.4 %, n = 2^22 -0.6 %, G2 n = 2^20 -1.5 %
+// (profiles/r03y_prefetch_ab.txt).  -DC12_BA_PREFETCH brings them back, -DC12_BA_PREFETCH_L1 aims them at L1.
+#if !defined(C12_BA_PREFETCH) && !defined(C12_BA_PREFETCH_L1)
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#elif defined(C12_BA_PREFETCH_L1)
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
