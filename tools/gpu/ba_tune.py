@@ -28,7 +28,7 @@ for name, logn in cases:
     base_ms, want = run(msm, p, s)
     print(f"{name} n=2^{logn} XYZZ only: {base_ms:.3f} ms  acc {dv.last_msm_stats()['phases_ms']['accumulate']:.3f}", flush=True)
     L.c12381_set_msm_batch_affine(-1)
-    for pipes, waves, jmax, tail in itertools.product((1, 2), (4, 2, 1), (32, 16), (3, 2, 4)):
+    for pipes, waves, jmax, tail in itertools.product((2, 3, 1), (1, 2), (32, 48), (3, 2, 4)):
         L.c12381_set_msm_pipelines(pipes); L.c12381_set_knob(0, waves); L.c12381_set_knob(1, jmax); L.c12381_set_knob(2, tail)
         ms, got = run(msm, p, s)
         ph = dv.last_msm_stats()["phases_ms"]
