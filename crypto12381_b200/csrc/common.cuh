@@ -53,7 +53,7 @@ struct Ctx {
     cudaEvent_t parse_ev[2] = {nullptr, nullptr};   // fork, join of that
     int parse_aside = 1;
     int ba_fill_pct = 100;  // knob 8 (A/B): share of the resident warps (3 blocks per SM counted) one lane's round is sized for, in percent
-    int split_tail = 0;     // knob 7 (A/B): the high windows get the smaller of two pipelines and their reduction + Horner part run under the low windows' last rounds.  Measured (profiles/r03g_split_tail_ab.txt): tail 1.24 -> 1.02 ms but the uneven rounds cost as much - 6.82 -> 6.78 ms at n = 2^20, slower at 2^22 and over G2; off
+    int split_tail = 2;     // knob 7: 0 = one common tail; 1 = EARLY split (the high windows as the smaller of two pipelines, their whole tail under the low windows' last rounds: tail 1.24 -> 1.02 ms but the uneven rounds give it back, profiles/r03g); 2 (default) = LATE split (one accumulation, then the high half's reduction + Horner chain on a side stream beside the low half's: G1 n = 2^20 -0.7 %, n = 2^16 -5 %, n = 2^10 -8 %, G2 unchanged, profiles/r04c)
     int front_end = 0;      // bucket lists: 0 = by counting (atomic ranks + scan + scatter), 1 = segmented radix sort + bounds search (stable; the A/B twin)
     int upload_groups = 4;  // host-pointer MSM entries: the points go up in this many groups, each in front of its own pipeline of halving rounds
     cudaEvent_t group_ev[8] = {}, sgroup_ev[8] = {};   // a group's points / scalars have arrived

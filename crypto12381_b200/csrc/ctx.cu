@@ -274,7 +274,7 @@ void c12381_set_knob(int id, int value)
     if (id == 4) ctx().upload_groups = value < 1 ? 1 : (value > 8 ? 8 : value);
     if (id == 5) ctx().front_end = value ? 1 : 0;
     if (id == 6) ctx().parse_aside = value ? 1 : 0;
-    if (id == 7) ctx().split_tail = value ? 1 : 0;
+    if (id == 7) ctx().split_tail = value < 0 || value > 2 ? 0 : value;
     if (id == 8) ctx().ba_fill_pct = value < 10 ? 10 : (value > 800 ? 800 : value);
 }
 void c12381_set_msm_pipelines(int pipes) { ctx().ba_pipes = pipes < 1 ? 1 : (pipes > 4 ? 4 : pipes); }

@@ -729,6 +729,13 @@ __global__ void __launch_bounds__(256) k_finish(MsmPlan pl, const Proj<F>* __res
     }
 }
 
+// the two halves of a split tail -> the result (one warp, lane-cooperative addition)
+template <class F> __global__ void __launch_bounds__(32) k_combine2(const Proj<F>* __restrict__ a, const Proj<F>* __restrict__ b, uint8_t* out, int out_mode)
+{
+    const Proj<F> r = coop_add<F, true>(*a, *b, 0xffffffffu);
+    if ((threadIdx.x & 31) == 0) write_point<F>(out, r, out_mode);
+}
+
 // sum of n wire-format points (merging all-gathered per-rank partials; also a general point-sum entry)
 template <class F>
 __global__ void __launch_bounds__(256) k_sum_points(const uint8_t* __restrict__ bytes, uint32_t n, uint8_t* out, int out_mode, int* flags)
@@ -923,7 +930,7 @@ inline BaSchedule msm_ba_schedule(const MsmPlan& pl, const MsmPlan& lp, uint32_t
     for (uint32_t p = 0; p <= sc.pipes; ++p) sc.b_lo[p] = (pl.windows * p / sc.pipes) * pl.half;
     // split tail (msm_run): two pipelines, the HIGH windows the smaller one (3 of 8, 1 of 4) - it finishes its rounds first and its
     // reduction and chain of doublings run under the low windows' last rounds
-    sc.split_tail = c.split_tail && sc.rounds > 1 && sc.pipes == 2 && pl.windows >= 4;
+    sc.split_tail = c.split_tail == 1 && sc.rounds > 1 && sc.pipes == 2 && pl.windows >= 4;
     if (sc.split_tail) {
         const uint32_t high = pl.windows * 3 / 8 > 0 ? pl.windows * 3 / 8 : 1;
         sc.b_lo[1] = (pl.windows - high) * pl.half;
@@ -987,7 +994,7 @@ template <class F> size_t msm_scratch_bytes(const MsmPlan& pl, const MsmPlan& lp
     b += align_up(4 * hist_words) + align_up(4 * (tile_words + 16));
     b += align_up(4 * (size_t)BA_MAX_PIPES * count_scan_scratch_words(pl.total));
     b += 2 * align_up(4 * (size_t)lp.total);
-    b += 2 * (align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax)) + align_up(sizeof(Proj<F>));      // twice: the split tail orders and accumulates each pipeline's buckets on their own
+    b += 2 * (align_up(4 * chunk_order_scratch_words(pl)) + align_up(sizeof(Proj<F>) * (size_t)pl.vmax)) + align_up(2 * sizeof(Proj<F>));      // twice: the split tail orders and accumulates each pipeline's buckets on their own
     b += align_up(sizeof(Proj<F>) * (size_t)pl.total);
     const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS, BaShape<F>::AUTO_MIN_LOG);
     if (sc.rounds) {
@@ -1105,7 +1112,7 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     Proj<F>* vpartial = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
     uint32_t* chunk_scratch2 = (uint32_t*)arena_take(4 * chunk_order_scratch_words(pl));      // split tail: the second pipeline's
     Proj<F>* vpartial2 = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.vmax);
-    Proj<F>* hpart = (Proj<F>*)arena_take(sizeof(Proj<F>));
+    Proj<F>* hpart = (Proj<F>*)arena_take(2 * sizeof(Proj<F>));
     Proj<F>* buckets = (Proj<F>*)arena_take(sizeof(Proj<F>) * (size_t)pl.total);
     const BaSchedule sc = msm_ba_schedule(pl, lp, BaShape<F>::MIN_BLOCKS, BaShape<F>::AUTO_MIN_LOG);
     const uint32_t R = sc.rounds;
@@ -1426,14 +1433,41 @@ int msm_run(const uint8_t* d_points, const uint8_t* d_scalars, size_t n_sz, uint
     C12_LAUNCHED();
     C12_CUDA(cudaEventRecord(c.ev[2], s));
     C12_CUDA(cudaEventRecord(c.pev[5], s));
-    k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial, 0);
-    C12_LAUNCHED();
-    C12_CUDA(cudaEventRecord(c.pev[6], s));
-    k_reduce_planes<F><<<dim3(pl.plane_bits + 1, pl.windows, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, s>>>(pl, partial, plane_parts, plane_tickets, wsum, 0);
-    C12_LAUNCHED();
-    C12_CUDA(cudaEventRecord(c.pev[7], s));
-    k_finish<F><<<1, 256, sizeof(Proj<F>) * pl.windows, s>>>(pl, wsum, d_out, out_mode, 0, pl.windows, 0, nullptr, nullptr);
-    C12_LAUNCHED();
+    if (c.split_tail == 2 && pl.windows >= 4) {
+        // LATE split (knob 7 = 2): one accumulation, then the reduction and the Horner part of the HIGH half of the windows as a chain
+        // of its own on a side stream (which outranks `s`), beside the low half's.  The high chain is still c (W - 1) doublings
+        // long; what it gains is that its planes are ready before all windows' would be.
+        const uint32_t wsplit = pl.windows / 2, nhi = pl.windows - wsplit;
+        C12_CUDA(cudaEventRecord(c.side_ev[0], s));
+        C12_CUDA(cudaStreamWaitEvent(c.side[0], c.side_ev[0], 0));
+        k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), nhi), 128, 0, c.side[0]>>>(pl, buckets, partial, wsplit);
+        C12_LAUNCHED();
+        k_reduce_planes<F><<<dim3(pl.plane_bits + 1, nhi, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, c.side[0]>>>(pl, partial, plane_parts, plane_tickets, wsum, wsplit);
+        C12_LAUNCHED();
+        k_finish<F><<<1, 256, sizeof(Proj<F>) * nhi, c.side[0]>>>(pl, wsum, nullptr, out_mode, wsplit, pl.windows, wsplit, nullptr, hpart);
+        C12_LAUNCHED();
+        C12_CUDA(cudaEventRecord(c.side_ev[1], c.side[0]));
+        k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), wsplit), 128, 0, s>>>(pl, buckets, partial, 0);
+        C12_LAUNCHED();
+        C12_CUDA(cudaEventRecord(c.pev[6], s));
+        k_reduce_planes<F><<<dim3(pl.plane_bits + 1, wsplit, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, s>>>(pl, partial, plane_parts, plane_tickets, wsum, 0);
+        C12_LAUNCHED();
+        C12_CUDA(cudaEventRecord(c.pev[7], s));
+        k_finish<F><<<1, 256, sizeof(Proj<F>) * wsplit, s>>>(pl, wsum, nullptr, out_mode, 0, wsplit, 0, nullptr, hpart + 1);      // the low chain, beside the high one
+        C12_LAUNCHED();
+        C12_CUDA(cudaStreamWaitEvent(s, c.side_ev[1], 0));
+        k_combine2<F><<<1, 32, 0, s>>>(hpart, hpart + 1, d_out, out_mode);
+        C12_LAUNCHED();
+    } else {
+        k_reduce_level0<F><<<dim3(cdiv(pl.segs, 128), pl.windows), 128, 0, s>>>(pl, buckets, partial, 0);
+        C12_LAUNCHED();
+        C12_CUDA(cudaEventRecord(c.pev[6], s));
+        k_reduce_planes<F><<<dim3(pl.plane_bits + 1, pl.windows, 2 * PlaneShape<F>::SPLITS), PlaneShape<F>::THREADS, 0, s>>>(pl, partial, plane_parts, plane_tickets, wsum, 0);
+        C12_LAUNCHED();
+        C12_CUDA(cudaEventRecord(c.pev[7], s));
+        k_finish<F><<<1, 256, sizeof(Proj<F>) * pl.windows, s>>>(pl, wsum, d_out, out_mode, 0, pl.windows, 0, nullptr, nullptr);
+        C12_LAUNCHED();
+    }
     C12_CUDA(cudaEventRecord(c.pev[8], s));
     C12_CUDA(cudaEventRecord(c.ev[3], s));
     c.stats.window_bits = (int)pl.c;

@@ -78,9 +78,9 @@ C12381_API void c12381_set_msm_pipelines(int pipes);
  * radix sort and a bounds search (same results; the order inside a bucket's list is irrelevant to its sum),
  * 6 = device-resident single-group calls: 1 (default) runs the scalar-only stages on a high-priority stream beside the parse of
  * the points, 0 runs everything in line,
- * 7 = two pipelines of halving rounds: 1 gives the high windows the smaller pipeline and runs their bucket reduction and their part
- * of the Horner chain under the low windows' last rounds, 0 (default; measured equal or faster) joins the pipelines before one
- * common tail,
+ * 7 = the tail (bucket reduction + Horner combination): 0 = one chain over all windows; 1 = early split (two pipelines of halving
+ * rounds, the high windows the smaller one, their whole tail under the low windows' last rounds); 2 (default) = late split (one
+ * accumulation, then the high half of the windows reduced and combined on a side stream beside the low half),
  * 8 = percent of the resident warps (BA kernels' blocks per SM x 4 warps x SMs) one lane's halving round is sized for (default 100) */
 C12381_API void c12381_set_knob(int id, int value);
 

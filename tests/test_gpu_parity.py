@@ -84,13 +84,13 @@ def test_points_golden(cuda):
     ps.check_points(cuda)
 
 
-@pytest.fixture(params=[(0, 1, 1, 0, 0), (1, 1, 1, 0, 0), (3, 2, 2, 0, 0), (9, 4, 3, 0, 0), (2, 1, 4, 0, 0), (0, 1, 1, 1, 0), (3, 2, 2, 1, 0), (4, 2, 2, 0, 1)],
+@pytest.fixture(params=[(0, 1, 1, 0, 2), (1, 1, 1, 0, 0), (3, 2, 2, 0, 2), (9, 4, 3, 0, 2), (2, 1, 4, 0, 0), (0, 1, 1, 1, 2), (3, 2, 2, 1, 0), (4, 2, 2, 0, 1)],
                 ids=["xyzz-only", "batch-affine-1", "batch-affine-3x2-groups2", "batch-affine-9-groups3", "batch-affine-2-groups4",
                      "xyzz-only-sorted-lists", "batch-affine-3x2-groups2-sorted-lists", "batch-affine-4x2-split-tail"])
 def ba_rounds(request):
     """(forced batch-affine halving rounds, pipelines they are split into, upload groups of the host entry, front end: bucket
-    lists by counting = 0 / by the segmented radix sort = 1, split tail); the defaults are -1 (rounds chosen from the bucket
-    load), 2, 4, 0, 0"""
+    lists by counting = 0 / by the segmented radix sort = 1, tail: 0 one chain / 1 early split / 2 late split); the defaults are -1
+    (rounds chosen from the bucket load), 2, 4, 0, 2"""
     from crypto12381_b200 import _lib
     _lib.lib().c12381_set_msm_batch_affine(request.param[0])
     _lib.lib().c12381_set_msm_pipelines(request.param[1])
@@ -102,7 +102,7 @@ def ba_rounds(request):
     _lib.lib().c12381_set_msm_pipelines(2)
     _lib.lib().c12381_set_knob(4, 4)
     _lib.lib().c12381_set_knob(5, 0)
-    _lib.lib().c12381_set_knob(7, 0)
+    _lib.lib().c12381_set_knob(7, 2)
 
 
 def test_msm_golden_all_windows(cuda, ba_rounds):
